@@ -1,0 +1,733 @@
+// C ABI of librfsurf_b200.so — see include/rfsurfhmc.h for the contract and the reference
+// interfaces each entry point replaces.  Host-side orchestration only: plan building, workspace,
+// kernel launches.  No CPU fallback: every numerical result comes from the sm_100a kernels.
+#include "../../include/rfsurfhmc.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "hmc_kernels.cuh"
+#include "joint_kernels.cuh"
+#include "rf_kernels.cuh"
+#include "swd_kernels.cuh"
+
+using namespace rfs;
+
+namespace {
+
+struct Buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct rfs_ctx {
+  int device = 0;
+  std::string err;
+  long long launches = 0;
+  cudaStream_t stream = nullptr;  // used by the *_host entry points
+  // ---- SWD configuration
+  bool has_swd = false;
+  int n_swd = 0, mode = 0, stale = 1;
+  SwdPlan plan;
+  std::vector<double> periods;
+  Buf d_periods;
+  // ---- RF configuration
+  bool has_rf = false;
+  int n_rf = 0, nt = 0, nft = 0, logn = 0, n2 = 0, rf_type = 1, method = 1;
+  double ray_p = 0, dt = 0, gauss = 0, tshift = 0, water = 0.001;
+  // ---- observations
+  bool has_obs = false;
+  double sigma1 = 1.0, sigma2 = 1.0;
+  std::vector<double> dobs;
+  Buf d_dobs;
+  // ---- workspace (grown on demand, never shrunk)
+  Buf w_swd, w_rfm, w_chain, w_qa, w_qb, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
+      w_urf, w_grf, w_rftr;
+  Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
+  // ---- HMC
+  long long hmc_evals = 0;
+  Buf h_state, h_rng, h_misc, h_x, h_p, h_out;
+  size_t ws_budget = (size_t)24 << 30;  // workspace budget per chunk (bytes)
+};
+
+namespace {
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                     \
+      return RFS_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define LAUNCH(kern, grid, block, smem, st, ...)                 \
+  do {                                                           \
+    kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);        \
+    ctx->launches++;                                             \
+    CK(cudaGetLastError());                                      \
+  } while (0)
+
+int ensure(rfs_ctx *ctx, Buf &b, size_t bytes) {
+  if (bytes <= b.cap) return RFS_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return RFS_OK;
+}
+
+int fail(rfs_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+inline unsigned gridFor(long long total, int block) { return (unsigned)((total + block - 1) / block); }
+
+int nmax_for(int n) {
+  if (n <= 8) return 8;
+  if (n <= 16) return 16;
+  if (n <= 48) return 48;
+  if (n <= 208) return 208;
+  return -1;
+}
+
+bool same_periods(const double *a, int na, const double *b, int nb) {
+  if (na != nb) return false;
+  for (int i = 0; i < na; i++)
+    if (a[i] != b[i]) return false;
+  return true;
+}
+
+// Build the sequence / row plan for the requested wave types (see swd_kernels.cuh).
+// want_kernels: group-velocity rows need the 1.05 T / 0.95 T sequences (surfdisp.cpp:234-241).
+int build_plan(rfs_ctx *ctx, SwdPlan &P, std::vector<double> &periods, const int nts[4],
+               const double *ts[4], int mode, bool want_kernels) {
+  memset(&P, 0, sizeof(P));
+  periods.clear();
+  P.nmode = mode + 1;
+  int per_off[4] = {0, 0, 0, 0};
+  for (int w = 0; w < 4; w++) {
+    per_off[w] = (int)periods.size();
+    for (int i = 0; i < nts[w]; i++) {
+      if (!(ts[w][i] > 0.0)) return fail(ctx, RFS_E_ARG, "periods must be positive");
+      if (i > 0 && !(ts[w][i] > ts[w][i - 1]))
+        return fail(ctx, RFS_E_ARG, "periods must be strictly ascending (surfdisp96.f:356-362)");
+      periods.push_back(ts[w][i]);
+    }
+  }
+  auto add_seq = [&](int ifunc, int poff, int nper, double scale) {
+    SwdSeq &s = P.seq[P.nseq];
+    s.ifunc = ifunc;
+    s.per_off = poff;
+    s.nper = nper;
+    s.out_off = P.nsolve;
+    s.scale = scale;
+    P.nsolve += nper;
+    return P.nseq++;
+  };
+  int d_off = 0;
+  for (int fam = 0; fam < 2; fam++) {  // 0 Rayleigh (types 0,1), 1 Love (types 2,3)
+    const int wc = fam * 2, wg = fam * 2 + 1;
+    const int ifunc = fam == 0 ? 2 : 1;
+    int sc = -1;
+    if (nts[wc] > 0) {
+      sc = add_seq(ifunc, per_off[wc], nts[wc], 1.0);
+      SwdRow &r = P.row[P.nrow++];
+      r.type = wc;
+      r.nper = nts[wc];
+      r.per_off = per_off[wc];
+      r.s0 = sc;
+      r.s1 = r.s2 = -1;
+      r.d_off = d_off;
+      d_off += nts[wc];
+    }
+    if (nts[wg] > 0) {
+      int s0;
+      if (sc >= 0 && same_periods(ts[wc], nts[wc], ts[wg], nts[wg]))
+        s0 = sc;  // the reference recomputes these roots (surfdisp.cpp:239); they are identical
+      else
+        s0 = add_seq(ifunc, per_off[wg], nts[wg], 1.0);
+      SwdRow &r = P.row[P.nrow++];
+      r.type = wg;
+      r.nper = nts[wg];
+      r.per_off = per_off[wg];
+      r.s0 = s0;
+      r.s1 = r.s2 = -1;
+      if (want_kernels) {
+        r.s1 = add_seq(ifunc, per_off[wg], nts[wg], 1.0 + 0.05);
+        r.s2 = add_seq(ifunc, per_off[wg], nts[wg], 1.0 - 0.05);
+      }
+      r.d_off = d_off;
+      d_off += nts[wg];
+    }
+  }
+  P.ndata = d_off;
+  return RFS_OK;
+}
+
+// ---- SWD pipeline on a prepared model block: roots + eigen solves
+int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const double *d_swd,
+            long long B, int n, bool all_modes, bool want_eigen, cudaStream_t st) {
+  const int nmo = all_modes ? P.nmode : 1;
+  int rc;
+  if ((rc = ensure(ctx, ctx->w_croot, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
+  if ((rc = ensure(ctx, ctx->w_cwork, sizeof(double) * (size_t)P.nsolve * B))) return rc;
+  if ((rc = ensure(ctx, ctx->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
+  LAUNCH(swd_roots_kernel, gridFor(B * P.nseq, 128), 128, 0, st, P, d_swd, B, n, d_periods,
+         all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
+         (int *)ctx->w_ierr.p);
+  if (!want_eigen) return RFS_OK;
+  if ((rc = ensure(ctx, ctx->w_ugr, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
+  if ((rc = ensure(ctx, ctx->w_kern, sizeof(double) * (size_t)nmo * P.nsolve * 4 * n * B)))
+    return rc;
+  const long long tot = B * P.nsolve * nmo;
+#define EIG(NM)                                                                                 \
+  LAUNCH(swd_eigen_kernel<NM>, gridFor(tot, 128), 128, 0, st, P, d_swd, B, n, d_periods, nmo,  \
+         (const double *)ctx->w_croot.p, (double *)ctx->w_ugr.p, (double *)ctx->w_kern.p)
+  switch (nmax_for(n)) {
+    case 8: EIG(8); break;
+    case 16: EIG(16); break;
+    case 48: EIG(48); break;
+    case 208: EIG(208); break;
+    default: return fail(ctx, RFS_E_ARG, "too many layers (max 208)");
+  }
+#undef EIG
+  return RFS_OK;
+}
+
+// ---- RF pipeline on a prepared model block (freq method)
+// nq: 0 forward only, 2 chain-rule rows (vs, thk), 4 all parameters
+int run_rf_spectra(rfs_ctx *ctx, const double *d_rfm, const double *d_chain, const double *d_qa,
+                   const double *d_qb, long long B, int n, int nq, double sigma, cudaStream_t st) {
+  int rc;
+  const int n2 = ctx->n2;
+  if ((rc = ensure(ctx, ctx->w_spec, sizeof(double2) * (size_t)B * 2 * n2))) return rc;
+  if (nq > 0)
+    if ((rc = ensure(ctx, ctx->w_dspec, sizeof(double2) * (size_t)B * nq * n * n2))) return rc;
+  double2 *dsp = nq > 0 ? (double2 *)ctx->w_dspec.p : nullptr;
+  const long long tot = B * n2;
+#define PROP(NM, NQ)                                                                           \
+  LAUNCH((rf_propagate_kernel<NM, NQ>), gridFor(tot, 128), 128, 0, st, d_rfm, d_chain, d_qa,   \
+         d_qb, B, n, n2, ctx->nft, ctx->dt, ctx->ray_p, sigma, ctx->rf_type,                   \
+         (double2 *)ctx->w_spec.p, dsp)
+#define PROPQ(NM)    \
+  if (nq == 2) {     \
+    PROP(NM, 2);     \
+  } else {           \
+    PROP(NM, 4);     \
+  }
+  switch (nmax_for(n)) {
+    case 8: PROPQ(8); break;
+    case 16: PROPQ(16); break;
+    case 48: PROPQ(48); break;
+    case 208: PROPQ(208); break;
+    default: return fail(ctx, RFS_E_ARG, "too many layers (max 208)");
+  }
+#undef PROPQ
+#undef PROP
+  return RFS_OK;
+}
+
+size_t decon_smem(int nft, int n2) { return sizeof(double) * (2 * (size_t)nft + 6 * (size_t)n2 + 64); }
+int decon_threads(int nft) { return std::max(64, std::min(512, nft / 2)); }
+
+int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, double *d_rf,
+                 long long ldrf, double *d_U, double *d_grad, double sigma, double tshift,
+                 cudaStream_t st) {
+  const size_t sm = decon_smem(ctx->nft, ctx->n2);
+  if (sm > 48 * 1024)
+    CK(cudaFuncSetAttribute(rf_decon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  LAUNCH(rf_decon_kernel, (unsigned)B, decon_threads(ctx->nft), sm, st,
+         (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt,
+         ctx->nft, ctx->logn, ctx->dt, ctx->gauss, tshift, ctx->water, sigma, d_dobs, d_rf, ldrf,
+         d_U, d_grad);
+  return RFS_OK;
+}
+
+int set_rf_cfg(rfs_ctx *ctx, int n, double ray_p, int nt, double dt, double gauss,
+               double time_shift, double water, int rf_type, int method) {
+  if (rf_type != 1 && rf_type != 2) return fail(ctx, RFS_E_ARG, "rf_type should be one of [P,p,S,s]");
+  if (method != 0 && method != 1) return fail(ctx, RFS_E_ARG, "method should be time or freq");
+  if (nt < 1 || !(dt > 0.0) || n < 2) return fail(ctx, RFS_E_ARG, "bad nt/dt/nlayer");
+  if (nmax_for(n) < 0) return fail(ctx, RFS_E_ARG, "too many layers (max 208)");
+  ctx->n_rf = n;
+  ctx->ray_p = ray_p;
+  ctx->nt = nt;
+  ctx->dt = dt;
+  ctx->gauss = gauss;
+  ctx->tshift = time_shift;
+  ctx->water = water;
+  ctx->rf_type = rf_type;
+  ctx->method = method;
+  int nft = 1, lg = 0;
+  while (nft < nt) {
+    nft *= 2;
+    lg++;
+  }
+  if (nft < 2) {
+    nft = 2;
+    lg = 1;
+  }
+  ctx->nft = nft;
+  ctx->logn = lg;
+  ctx->n2 = nft / 2 + 1;
+  if (decon_smem(nft, ctx->n2) > 200 * 1024) return fail(ctx, RFS_E_ARG, "nt too large (max 8192)");
+  return RFS_OK;
+}
+
+// bytes of workspace one model needs in the fused path (used to size chunks)
+size_t per_model_bytes(const rfs_ctx *ctx, int which) {
+  size_t s = 0;
+  if (which != 1 && ctx->has_swd) {
+    const SwdPlan &P = ctx->plan;
+    s += sizeof(double) * ((size_t)SWD_NF * ctx->n_swd + 3 * (size_t)P.nsolve +
+                           (size_t)P.nsolve * 4 * ctx->n_swd) + sizeof(int) * P.nseq;
+  }
+  if (which != 2 && ctx->has_rf) {
+    s += sizeof(double) * (6 * (size_t)ctx->n_rf) +
+         sizeof(double2) * ((size_t)2 * ctx->n2 + (size_t)2 * ctx->n_rf * ctx->n2) +
+         sizeof(double) * (1 + 2 * (size_t)ctx->n_rf);
+  }
+  return s + 64;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rfs_version(void) { return "rfsurf_b200 0.1 sm_100a"; }
+
+int rfs_create(rfs_ctx **out, int device) {
+  if (!out) return RFS_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return RFS_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return RFS_E_CUDA;
+  rfs_ctx *ctx = new rfs_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return RFS_E_CUDA;
+  }
+  *out = ctx;
+  return RFS_OK;
+}
+
+void rfs_destroy(rfs_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain, &ctx->w_qa,
+                &ctx->w_qb,      &ctx->w_croot, &ctx->w_cwork, &ctx->w_ugr, &ctx->w_kern, &ctx->w_ierr,
+                &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
+                &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
+                &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state, &ctx->h_rng,
+                &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out};
+  for (Buf *b : all)
+    if (b->p) cudaFree(b->p);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *rfs_last_error(rfs_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+long long rfs_launch_count(rfs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int ntRg,
+                   const double *tRg, int ntLc, const double *tLc, int ntLg, const double *tLg,
+                   int mode, int sphere, int stale) {
+  if (!ctx) return RFS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (sphere) return fail(ctx, RFS_E_UNSUPPORTED, "spherical earth (sphere=True) is not built yet");
+  if (nlayer < 2 || nmax_for(nlayer) < 0) return fail(ctx, RFS_E_ARG, "bad layer count");
+  if (mode < 0 || mode > 16) return fail(ctx, RFS_E_ARG, "bad mode");
+  const int nts[4] = {ntRc, ntRg, ntLc, ntLg};
+  const double *ts[4] = {tRc, tRg, tLc, tLg};
+  int rc = build_plan(ctx, ctx->plan, ctx->periods, nts, ts, mode, true);
+  if (rc) return rc;
+  if (ctx->plan.ndata == 0) return fail(ctx, RFS_E_ARG, "no periods given");
+  if ((rc = ensure(ctx, ctx->d_periods, sizeof(double) * ctx->periods.size()))) return rc;
+  CK(cudaMemcpy(ctx->d_periods.p, ctx->periods.data(), sizeof(double) * ctx->periods.size(),
+                cudaMemcpyHostToDevice));
+  ctx->n_swd = nlayer;
+  ctx->mode = mode;
+  ctx->stale = stale ? 1 : 0;
+  ctx->has_swd = true;
+  return RFS_OK;
+}
+
+int rfs_config_rf(rfs_ctx *ctx, int nlayer, double ray_p, int nt, double dt, double gauss,
+                  double time_shift, double water, int rf_type, int method) {
+  if (!ctx) return RFS_E_ARG;
+  int rc = set_rf_cfg(ctx, nlayer, ray_p, nt, dt, gauss, time_shift, water, rf_type, method);
+  if (rc) return rc;
+  ctx->has_rf = true;
+  return RFS_OK;
+}
+
+int rfs_config_obs(rfs_ctx *ctx, double sigma1, double sigma2, const double *dobs, int ndobs) {
+  if (!ctx || !dobs || ndobs <= 0) return RFS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->sigma1 = sigma1;
+  ctx->sigma2 = sigma2;
+  ctx->dobs.assign(dobs, dobs + ndobs);
+  int rc = ensure(ctx, ctx->d_dobs, sizeof(double) * ndobs);
+  if (rc) return rc;
+  CK(cudaMemcpy(ctx->d_dobs.p, dobs, sizeof(double) * ndobs, cudaMemcpyHostToDevice));
+  ctx->has_obs = true;
+  return RFS_OK;
+}
+
+int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, double *U,
+                        double *grad, double *dsyn, unsigned char *flag, void *stream) {
+  if (!ctx) return RFS_E_ARG;
+  if (B <= 0) return RFS_OK;
+  if (which < 0 || which > 2) return fail(ctx, RFS_E_ARG, "which must be 0,1,2");
+  const bool use_swd = which != 1, use_rf = which != 2;
+  if ((use_swd && !ctx->has_swd) || (use_rf && !ctx->has_rf) || !ctx->has_obs)
+    return fail(ctx, RFS_E_CONFIG, "context not configured (rfs_config_swd/rf/obs)");
+  if (use_swd && use_rf && ctx->n_swd != ctx->n_rf)
+    return fail(ctx, RFS_E_CONFIG, "SWD and RF layer counts differ");
+  if (use_rf && ctx->method != 1)
+    return fail(ctx, RFS_E_UNSUPPORTED, "time-domain (deconit) RF Frechet is not built; use method='freq'");
+  const int n = use_swd ? ctx->n_swd : ctx->n_rf;
+  const int n1 = use_rf ? ctx->nt : 0, nsw = use_swd ? ctx->plan.ndata : 0;
+  const int ndata = n1 + nsw;
+  if ((int)ctx->dobs.size() != ndata) return fail(ctx, RFS_E_CONFIG, "dobs length != ndata");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pm = per_model_bytes(ctx, which);
+  long long Bmax = (long long)std::max<size_t>(1024, ctx->ws_budget / pm);
+  const double *d_dobs = (const double *)ctx->d_dobs.p;
+  double tshift = ctx->tshift;
+  if (ctx->rf_type == 2) tshift = -tshift;  // src/RF/main.cpp:35
+  const double sigma = 1.0 / ctx->dt / ctx->nft * 4.;
+  const double q = ctx->sigma1 / ctx->sigma2;
+  const double wt = (which == 0) ? q * q * n1 / nsw : 1.0;
+  for (long long off = 0; off < B; off += Bmax) {
+    const long long Bc = std::min(Bmax, B - off);
+    int rc;
+    const size_t nB = (size_t)n * Bc;
+    if (use_swd && (rc = ensure(ctx, ctx->w_swd, sizeof(double) * SWD_NF * nB))) return rc;
+    if (use_rf && (rc = ensure(ctx, ctx->w_rfm, sizeof(double) * 4 * nB))) return rc;
+    if ((rc = ensure(ctx, ctx->w_chain, sizeof(double) * 2 * nB))) return rc;
+    LAUNCH(prep_models_kernel, gridFor(Bc * n, 256), 256, 0, st, x + off * 2 * n, Bc, n,
+           use_swd ? (double *)ctx->w_swd.p : nullptr, use_rf ? (double *)ctx->w_rfm.p : nullptr,
+           (double *)ctx->w_chain.p);
+    if (use_rf) {
+      if ((rc = run_rf_spectra(ctx, (const double *)ctx->w_rfm.p, (const double *)ctx->w_chain.p,
+                               nullptr, nullptr, Bc, n, 2, sigma, st)))
+        return rc;
+      if ((rc = ensure(ctx, ctx->w_urf, sizeof(double) * Bc))) return rc;
+      if ((rc = ensure(ctx, ctx->w_grf, sizeof(double) * 2 * nB))) return rc;
+      double *Uo = (which == 1) ? U + off : (double *)ctx->w_urf.p;
+      double *go = (which == 1) ? grad + off * 2 * n : (double *)ctx->w_grf.p;
+      if ((rc = run_rf_decon(ctx, Bc, 2 * n, d_dobs, dsyn + off * ndata, ndata, Uo, go, sigma,
+                             tshift, st)))
+        return rc;
+      if (which == 1) CK(cudaMemsetAsync(flag + off, 1, Bc, st));
+    }
+    if (use_swd) {
+      if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p,
+                        (const double *)ctx->w_swd.p, Bc, n, false, true, st)))
+        return rc;
+      SwdView V;
+      V.croot = (const double *)ctx->w_croot.p;
+      V.ugr = (const double *)ctx->w_ugr.p;
+      V.kern = (const double *)ctx->w_kern.p;
+      V.periods = (const double *)ctx->d_periods.p;
+      V.B = Bc;
+      V.n = n;
+      LAUNCH(joint_assemble_kernel, gridFor(Bc * n, 128), 128, 0, st, ctx->plan, V,
+             (const int *)ctx->w_ierr.p, (const double *)ctx->w_chain.p, ctx->stale, which, n1,
+             d_dobs, (const double *)ctx->w_urf.p, (const double *)ctx->w_grf.p, wt, U + off,
+             grad + off * 2 * n, dsyn + off * ndata, flag + off);
+    }
+  }
+  return RFS_OK;
+}
+
+int rfs_misfit_grad_host(rfs_ctx *ctx, long long B, const double *x, int which, double *U,
+                         double *grad, double *dsyn, unsigned char *flag) {
+  if (!ctx) return RFS_E_ARG;
+  if (B <= 0) return RFS_OK;
+  if (which < 0 || which > 2) return fail(ctx, RFS_E_ARG, "which must be 0,1,2");
+  const bool use_swd = which != 1, use_rf = which != 2;
+  if ((use_swd && !ctx->has_swd) || (use_rf && !ctx->has_rf))
+    return fail(ctx, RFS_E_CONFIG, "context not configured (rfs_config_swd/rf/obs)");
+  const int n = use_swd ? ctx->n_swd : ctx->n_rf;
+  const int ndata = (use_rf ? ctx->nt : 0) + (use_swd ? ctx->plan.ndata : 0);
+  CK(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure(ctx, ctx->io_x, sizeof(double) * B * 2 * n))) return rc;
+  if ((rc = ensure(ctx, ctx->io_U, sizeof(double) * B))) return rc;
+  if ((rc = ensure(ctx, ctx->io_grad, sizeof(double) * B * 2 * n))) return rc;
+  if ((rc = ensure(ctx, ctx->io_dsyn, sizeof(double) * B * ndata))) return rc;
+  if ((rc = ensure(ctx, ctx->io_flag, B))) return rc;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->io_x.p, x, sizeof(double) * B * 2 * n, cudaMemcpyHostToDevice, st));
+  rc = rfs_misfit_grad_dev(ctx, B, (const double *)ctx->io_x.p, which, (double *)ctx->io_U.p,
+                           (double *)ctx->io_grad.p, (double *)ctx->io_dsyn.p,
+                           (unsigned char *)ctx->io_flag.p, st);
+  if (rc) return rc;
+  if (U) CK(cudaMemcpyAsync(U, ctx->io_U.p, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+  if (grad)
+    CK(cudaMemcpyAsync(grad, ctx->io_grad.p, sizeof(double) * B * 2 * n, cudaMemcpyDeviceToHost, st));
+  if (dsyn)
+    CK(cudaMemcpyAsync(dsyn, ctx->io_dsyn.p, sizeof(double) * B * ndata, cudaMemcpyDeviceToHost, st));
+  if (flag) CK(cudaMemcpyAsync(flag, ctx->io_flag.p, B, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RFS_OK;
+}
+
+// ------------------------------------------------------------------------------ libsurf drop-ins
+static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const double *vp,
+                       const double *vs, const double *rho, int nT, const double *period,
+                       int wavetype, int mode, int sphere, int stale, bool want_kernels,
+                       bool all_modes, double *c, double *dcda, double *dcdb, double *dcdr,
+                       double *dcdh, unsigned char *ok) {
+  if (!ctx) return RFS_E_ARG;
+  if (wavetype < 0 || wavetype > 3)
+    return fail(ctx, RFS_E_ARG, "wavetype should be one of [Rc,Rg,Lc,Lg]");
+  if (sphere) return fail(ctx, RFS_E_UNSUPPORTED, "spherical earth (sphere=True) is not built yet");
+  if (B <= 0 || nT <= 0) return RFS_OK;
+  if (n < 2 || nmax_for(n) < 0) return fail(ctx, RFS_E_ARG, "bad layer count");
+  if (mode < 0 || mode > 16) return fail(ctx, RFS_E_ARG, "bad mode");
+  CK(cudaSetDevice(ctx->device));
+  for (long long i = 0; i < B * n; i++)
+    if (!((float)vs[i] > 0.0f))
+      return fail(ctx, RFS_E_UNSUPPORTED, "water layers (vs<=0) are not built yet");
+  SwdPlan P;
+  std::vector<double> periods;
+  int nts[4] = {0, 0, 0, 0};
+  const double *ts[4] = {nullptr, nullptr, nullptr, nullptr};
+  nts[wavetype] = nT;
+  ts[wavetype] = period;
+  int rc = build_plan(ctx, P, periods, nts, ts, mode, want_kernels);
+  if (rc) return rc;
+  const bool group = (wavetype & 1) != 0;
+  const bool want_eigen = want_kernels || group;
+  cudaStream_t st = ctx->stream;
+  // pack the model block on the host: [SWD_NF][n][B] float32-rounded (src/SWD/main.cpp:9,62)
+  std::vector<double> blk((size_t)SWD_NF * n * B);
+  const size_t nB = (size_t)n * B;
+  for (long long b = 0; b < B; b++)
+    for (int m = 0; m < n; m++) {
+      const double d32 = (double)(float)thk[b * n + m], a32 = (double)(float)vp[b * n + m],
+                   b32 = (double)(float)vs[b * n + m], r32 = (double)(float)rho[b * n + m];
+      blk[F_D * nB + (size_t)m * B + b] = d32;
+      blk[F_A * nB + (size_t)m * B + b] = a32;
+      blk[F_B * nB + (size_t)m * B + b] = b32;
+      blk[F_RHO * nB + (size_t)m * B + b] = r32;
+      blk[F_IA * nB + (size_t)m * B + b] = 1.0 / a32;
+      blk[F_IB * nB + (size_t)m * B + b] = 1.0 / b32;
+      blk[F_IRHO * nB + (size_t)m * B + b] = 1.0 / r32;
+    }
+  if ((rc = ensure(ctx, ctx->w_swd, sizeof(double) * blk.size()))) return rc;
+  if ((rc = ensure(ctx, ctx->io_a, sizeof(double) * periods.size()))) return rc;
+  CK(cudaMemcpyAsync(ctx->w_swd.p, blk.data(), sizeof(double) * blk.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->io_a.p, periods.data(), sizeof(double) * periods.size(),
+                     cudaMemcpyHostToDevice, st));
+  if ((rc = run_swd(ctx, P, (const double *)ctx->io_a.p, (const double *)ctx->w_swd.p, B, n,
+                    all_modes, want_eigen, st)))
+    return rc;
+  const int nmo = all_modes ? P.nmode : 1;
+  const size_t nc = (size_t)B * nT, nk = (size_t)B * nT * n;
+  if ((rc = ensure(ctx, ctx->io_b, sizeof(double) * nc))) return rc;
+  if (want_kernels) {
+    if ((rc = ensure(ctx, ctx->io_c, sizeof(double) * nk))) return rc;
+    if ((rc = ensure(ctx, ctx->io_d, sizeof(double) * nk))) return rc;
+    if ((rc = ensure(ctx, ctx->io_e, sizeof(double) * nk))) return rc;
+    if ((rc = ensure(ctx, ctx->io_f, sizeof(double) * nk))) return rc;
+  }
+  for (int mo = 0; mo < nmo; mo++) {
+    SwdView V;
+    V.croot = (const double *)ctx->w_croot.p + (size_t)mo * P.nsolve * B;
+    V.ugr = want_eigen ? (const double *)ctx->w_ugr.p + (size_t)mo * P.nsolve * B : nullptr;
+    V.kern = want_eigen ? (const double *)ctx->w_kern.p + (size_t)mo * P.nsolve * 4 * n * B : nullptr;
+    V.periods = (const double *)ctx->io_a.p;
+    V.B = B;
+    V.n = n;
+    LAUNCH(swd_export_row_kernel, gridFor(B * nT * n, 256), 256, 0, st, P, 0, V, stale,
+           (double *)ctx->io_b.p, want_kernels ? (double *)ctx->io_c.p : nullptr,
+           (double *)ctx->io_d.p, (double *)ctx->io_e.p, (double *)ctx->io_f.p);
+    // outputs are [B][nmo][nT](...) : strided copy per model when nmo > 1
+    if (nmo == 1) {
+      CK(cudaMemcpyAsync(c, ctx->io_b.p, sizeof(double) * nc, cudaMemcpyDeviceToHost, st));
+      if (want_kernels) {
+        CK(cudaMemcpyAsync(dcda, ctx->io_c.p, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(dcdb, ctx->io_d.p, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(dcdr, ctx->io_e.p, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(dcdh, ctx->io_f.p, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      const size_t wc = sizeof(double) * nT, wk = sizeof(double) * nT * n;
+      CK(cudaMemcpy2DAsync(c + (size_t)mo * nT, wc * nmo, ctx->io_b.p, wc, wc, B,
+                           cudaMemcpyDeviceToHost, st));
+      if (want_kernels) {
+        CK(cudaMemcpy2DAsync(dcda + (size_t)mo * nT * n, wk * nmo, ctx->io_c.p, wk, wk, B,
+                             cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpy2DAsync(dcdb + (size_t)mo * nT * n, wk * nmo, ctx->io_d.p, wk, wk, B,
+                             cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpy2DAsync(dcdr + (size_t)mo * nT * n, wk * nmo, ctx->io_e.p, wk, wk, B,
+                             cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpy2DAsync(dcdh + (size_t)mo * nT * n, wk * nmo, ctx->io_f.p, wk, wk, B,
+                             cudaMemcpyDeviceToHost, st));
+      }
+      CK(cudaStreamSynchronize(st));
+    }
+  }
+  std::vector<int> ierr((size_t)P.nseq * B);
+  CK(cudaMemcpyAsync(ierr.data(), ctx->w_ierr.p, sizeof(int) * ierr.size(), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (ok)
+    for (long long b = 0; b < B; b++) {
+      bool good = true;
+      for (int s = 0; s < P.nseq; s++) good = good && ierr[(size_t)s * B + b] == 0;
+      ok[b] = good ? 1 : 0;
+    }
+  return RFS_OK;
+}
+
+int rfs_surf_forward(rfs_ctx *ctx, long long B, int n, const double *thk, const double *vp,
+                     const double *vs, const double *rho, int nT, const double *period,
+                     int wavetype, int mode, int sphere, double *c, unsigned char *ok) {
+  return surf_common(ctx, B, n, thk, vp, vs, rho, nT, period, wavetype, mode, sphere, 1, false,
+                     false, c, nullptr, nullptr, nullptr, nullptr, ok);
+}
+
+int rfs_surf_adjoint_kernel(rfs_ctx *ctx, long long B, int n, const double *thk, const double *vp,
+                            const double *vs, const double *rho, int nT, const double *period,
+                            int wavetype, int mode, int sphere, int stale, double *c, double *dcda,
+                            double *dcdb, double *dcdr, double *dcdh, unsigned char *ok) {
+  return surf_common(ctx, B, n, thk, vp, vs, rho, nT, period, wavetype, mode, sphere, stale, true,
+                     false, c, dcda, dcdb, dcdr, dcdh, ok);
+}
+
+int rfs_surf_adjoint_kernel_modes(rfs_ctx *ctx, long long B, int n, const double *thk,
+                                  const double *vp, const double *vs, const double *rho, int nT,
+                                  const double *period, int wavetype, int mode, int stale,
+                                  double *c, double *dcda, double *dcdb, double *dcdr,
+                                  double *dcdh, unsigned char *ok) {
+  return surf_common(ctx, B, n, thk, vp, vs, rho, nT, period, wavetype, mode, 0, stale, true, true,
+                     c, dcda, dcdb, dcdr, dcdh, ok);
+}
+
+// -------------------------------------------------------------------------------- librf drop-ins
+static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const double *rho,
+                     const double *vp, const double *vs, const double *qa, const double *qb,
+                     double ray_p, int nt, double dt, double gauss, double time_shift, int method,
+                     double water, int rf_type, int par_type, int nq, double *rf, double *drf) {
+  if (!ctx) return RFS_E_ARG;
+  // drop-in calls must not disturb the fused-path configuration: save / restore the RF fields
+  struct RfSave {
+    int n_rf, nt, nft, logn, n2, rf_type, method;
+    double ray_p, dt, gauss, tshift, water;
+  } saved = {ctx->n_rf, ctx->nt, ctx->nft, ctx->logn, ctx->n2, ctx->rf_type, ctx->method,
+             ctx->ray_p, ctx->dt, ctx->gauss, ctx->tshift, ctx->water};
+  int rc = set_rf_cfg(ctx, n, ray_p, nt, dt, gauss, time_shift, water, rf_type, method);
+  auto done = [&](int code) {
+    ctx->n_rf = saved.n_rf;
+    ctx->nt = saved.nt;
+    ctx->nft = saved.nft;
+    ctx->logn = saved.logn;
+    ctx->n2 = saved.n2;
+    ctx->rf_type = saved.rf_type;
+    ctx->method = saved.method;
+    ctx->ray_p = saved.ray_p;
+    ctx->dt = saved.dt;
+    ctx->gauss = saved.gauss;
+    ctx->tshift = saved.tshift;
+    ctx->water = saved.water;
+    return code;
+  };
+  if (rc) return done(rc);
+  if (method != 1)
+    return done(fail(ctx, RFS_E_UNSUPPORTED,
+                     "time-domain (deconit) receiver functions are not built yet; use method='freq'"));
+  if (nq == 1 && (par_type < 1 || par_type > 4))
+    return done(fail(ctx, RFS_E_ARG, "par_type should be one of [vp,vs,rho,thick]"));
+  if (B <= 0) return done(RFS_OK);
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t nB = (size_t)n * B;
+  std::vector<double> blk(6 * nB);
+  for (long long b = 0; b < B; b++)
+    for (int m = 0; m < n; m++) {
+      blk[0 * nB + (size_t)m * B + b] = thk[b * n + m];
+      blk[1 * nB + (size_t)m * B + b] = rho[b * n + m];
+      blk[2 * nB + (size_t)m * B + b] = vp[b * n + m];
+      blk[3 * nB + (size_t)m * B + b] = vs[b * n + m];
+      blk[4 * nB + (size_t)m * B + b] = qa[b * n + m];
+      blk[5 * nB + (size_t)m * B + b] = qb[b * n + m];
+    }
+  if ((rc = ensure(ctx, ctx->w_rfm, sizeof(double) * 6 * nB))) return done(rc);
+  CK(cudaMemcpyAsync(ctx->w_rfm.p, blk.data(), sizeof(double) * 6 * nB, cudaMemcpyHostToDevice, st));
+  const double *d_rfm = (const double *)ctx->w_rfm.p;
+  double tshift = time_shift;
+  if (rf_type == 2) tshift = -tshift;
+  const double sigma = 1.0 / dt / ctx->nft * 4.;
+  if ((rc = run_rf_spectra(ctx, d_rfm, nullptr, d_rfm + 4 * nB, d_rfm + 5 * nB, B, n,
+                           nq > 0 ? 4 : 0, sigma, st)))
+    return done(rc);
+  if ((rc = ensure(ctx, ctx->io_b, sizeof(double) * B * nt))) return done(rc);
+  if ((rc = run_rf_decon(ctx, B, 0, nullptr, (double *)ctx->io_b.p, nt, nullptr, nullptr, sigma,
+                         tshift, st)))
+    return done(rc);
+  CK(cudaMemcpyAsync(rf, ctx->io_b.p, sizeof(double) * B * nt, cudaMemcpyDeviceToHost, st));
+  if (nq > 0) {
+    const int nrow = 4 * n;
+    if ((rc = ensure(ctx, ctx->w_rftr, sizeof(double) * (size_t)B * nrow * nt))) return done(rc);
+    const size_t sm = decon_smem(ctx->nft, ctx->n2);
+    if (sm > 48 * 1024)
+      CK(cudaFuncSetAttribute(rf_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    LAUNCH(rf_trace_kernel, (unsigned)(B * nrow), decon_threads(ctx->nft), sm, st,
+           (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, nt, ctx->nft,
+           ctx->logn, dt, gauss, tshift, water, sigma, (double *)ctx->w_rftr.p);
+    if (nq == 4) {
+      CK(cudaMemcpyAsync(drf, ctx->w_rftr.p, sizeof(double) * (size_t)B * nrow * nt,
+                         cudaMemcpyDeviceToHost, st));
+    } else {
+      const size_t w = sizeof(double) * (size_t)n * nt;
+      CK(cudaMemcpy2DAsync(drf, w, (const double *)ctx->w_rftr.p + (size_t)(par_type - 1) * n * nt,
+                           w * 4, w, B, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  return done(RFS_OK);
+}
+
+int rfs_rf_forward(rfs_ctx *ctx, long long B, int n, const double *thk, const double *rho,
+                   const double *vp, const double *vs, const double *qa, const double *qb,
+                   double ray_p, int nt, double dt, double gauss, double time_shift, int method,
+                   double water, int rf_type, double *rf) {
+  return rf_common(ctx, B, n, thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method,
+                   water, rf_type, 0, 0, rf, nullptr);
+}
+int rfs_rf_kernel(rfs_ctx *ctx, long long B, int n, const double *thk, const double *rho,
+                  const double *vp, const double *vs, const double *qa, const double *qb,
+                  double ray_p, int nt, double dt, double gauss, double time_shift, int method,
+                  double water, int rf_type, int par_type, double *rf, double *drf) {
+  return rf_common(ctx, B, n, thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method,
+                   water, rf_type, par_type, 1, rf, drf);
+}
+int rfs_rf_kernel_all(rfs_ctx *ctx, long long B, int n, const double *thk, const double *rho,
+                      const double *vp, const double *vs, const double *qa, const double *qb,
+                      double ray_p, int nt, double dt, double gauss, double time_shift, int method,
+                      double water, int rf_type, double *rf, double *drf) {
+  return rf_common(ctx, B, n, thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method,
+                   water, rf_type, 0, 4, rf, drf);
+}
+
+}  // extern "C"
+
+#include "hmc_host.inl"

@@ -1,0 +1,183 @@
+// Host driver of the device-resident HMC (included at the end of capi.cu).
+// Replaces HamitonianMC.sample (pyhmc/hmc.py:228-276) and HMCDualAveraging.sample
+// (pyhmc/hmcda.py:280-369) for C chains at once; see hmc_kernels.cuh for the per-chain logic.
+
+namespace {
+
+struct Carver {
+  char *base;
+  size_t off = 0;
+  template <class T>
+  T *take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += sizeof(T) * count;
+    return p;
+  }
+};
+
+void carve_hmc(Carver &cv, HmcDev &D, long long C, int n2, int nd) {
+  D.xcur = cv.take<double>(C * n2);
+  D.xnew = cv.take<double>(C * n2);
+  D.pnew = cv.take<double>(C * n2);
+  D.gcur = cv.take<double>(C * n2);
+  D.dcur = cv.take<double>(C * nd);
+  D.xeval = cv.take<double>(C * n2);
+  D.Ucur = cv.take<double>(C);
+  D.Hcur = cv.take<double>(C);
+  D.dt = cv.take<double>(C);
+  D.dtbar = cv.take<double>(C);
+  D.h0 = cv.take<double>(C);
+  D.fdH = cv.take<double>(C);
+  D.gauss = cv.take<double>(C);
+  D.phase = cv.take<int>(C);
+  D.istep = cv.take<int>(C);
+  D.L = cv.take<int>(C);
+  D.okcur = cv.take<int>(C);
+  D.fd_it = cv.take<int>(C);
+  D.fd_a = cv.take<int>(C);
+  D.status = cv.take<int>(C);
+  D.mti = cv.take<int>(C);
+  D.has_gauss = cv.take<int>(C);
+  D.iacc = cv.take<long long>(C);
+  D.ncount = cv.take<long long>(C);
+  D.nevals = cv.take<long long>(C);
+  D.mt = cv.take<unsigned int>(C * 624);
+  D.n_active = cv.take<int>(4);
+}
+
+}  // namespace
+
+extern "C" {
+
+long long rfs_hmc_last_evals(rfs_ctx *ctx) { return ctx ? ctx->hmc_evals : 0; }
+
+int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_id,
+                const double *bounds, double dt, int Lmin, int Lmax, int L0, double target_ratio,
+                long long seed, int nsamples, int ndraws, long long max_iters, double *samples,
+                double *misfit, double *syn, double *initmodel, long long *n_iter,
+                long long *n_acc, double *dt_final, signed char *accept_seq,
+                long long max_iter_log) {
+  if (!ctx) return RFS_E_ARG;
+  if (sampler != 0 && sampler != 1) return fail(ctx, RFS_E_ARG, "sampler must be 0 or 1");
+  if (C <= 0 || !chain_id || !bounds || nsamples <= 0 || ndraws < 0)
+    return fail(ctx, RFS_E_ARG, "bad HMC arguments");
+  if (!ctx->has_swd || !ctx->has_rf || !ctx->has_obs)
+    return fail(ctx, RFS_E_CONFIG, "joint model not configured (rfs_config_swd/rf/obs)");
+  if (sampler == 0 && (Lmin < 1 || Lmax < Lmin)) return fail(ctx, RFS_E_ARG, "bad Lrange");
+  if (seed + 0 < 0) return fail(ctx, RFS_E_ARG, "Seed must be between 0 and 2**32 - 1");
+  CK(cudaSetDevice(ctx->device));
+  const int n = ctx->n_swd, n2 = 2 * n, nd = ctx->nt + ctx->plan.ndata;
+  cudaStream_t st = ctx->stream;
+  HmcCfg cfg;
+  cfg.n2 = n2;
+  cfg.ndata = nd;
+  cfg.sampler = sampler;
+  cfg.Lmin = Lmin;
+  cfg.Lmax = Lmax;
+  cfg.L0 = L0;
+  cfg.nsamples = nsamples;
+  cfg.ndraws = ndraws;
+  cfg.dt0 = dt;
+  cfg.target = target_ratio;
+  cfg.lambda = L0 * dt;        // hmcda.py:76
+  cfg.mu = log(10 * dt);       // hmcda.py:300 (uses the configured dt)
+  cfg.max_iters = max_iters;
+  cfg.max_log = accept_seq ? max_iter_log : 0;
+
+  HmcDev D;
+  memset(&D, 0, sizeof(D));
+  Carver probe{nullptr};
+  carve_hmc(probe, D, C, n2, nd);
+  int rc;
+  if ((rc = ensure(ctx, ctx->h_state, probe.off + 256))) return rc;
+  Carver cv{(char *)ctx->h_state.p};
+  carve_hmc(cv, D, C, n2, nd);
+  // evaluation outputs
+  if ((rc = ensure(ctx, ctx->io_U, sizeof(double) * C))) return rc;
+  if ((rc = ensure(ctx, ctx->io_grad, sizeof(double) * C * n2))) return rc;
+  if ((rc = ensure(ctx, ctx->io_dsyn, sizeof(double) * C * nd))) return rc;
+  if ((rc = ensure(ctx, ctx->io_flag, C))) return rc;
+  D.Ue = (const double *)ctx->io_U.p;
+  D.ge = (const double *)ctx->io_grad.p;
+  D.de = (const double *)ctx->io_dsyn.p;
+  D.fe = (const unsigned char *)ctx->io_flag.p;
+  // misc inputs: bounds, chain ids
+  if ((rc = ensure(ctx, ctx->h_misc, sizeof(double) * 2 * n2 + sizeof(long long) * C + 512)))
+    return rc;
+  double *d_bounds = (double *)ctx->h_misc.p;
+  long long *d_ids = (long long *)((char *)ctx->h_misc.p + ((sizeof(double) * 2 * n2 + 255) & ~255));
+  CK(cudaMemcpyAsync(d_bounds, bounds, sizeof(double) * 2 * n2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_ids, chain_id, sizeof(long long) * C, cudaMemcpyHostToDevice, st));
+  D.bounds = d_bounds;
+  // outputs
+  size_t ob = 0;
+  const size_t o_mis = ob; ob += misfit ? sizeof(double) * C * nsamples : 0; ob = (ob + 255) & ~(size_t)255;
+  const size_t o_smp = ob; ob += samples ? sizeof(double) * C * nsamples * n2 : 0; ob = (ob + 255) & ~(size_t)255;
+  const size_t o_syn = ob; ob += syn ? sizeof(double) * C * nsamples * nd : 0; ob = (ob + 255) & ~(size_t)255;
+  const size_t o_ini = ob; ob += initmodel ? sizeof(double) * C * n2 : 0; ob = (ob + 255) & ~(size_t)255;
+  const size_t o_log = ob; ob += accept_seq ? (size_t)C * max_iter_log : 0; ob = (ob + 255) & ~(size_t)255;
+  if ((rc = ensure(ctx, ctx->h_out, ob + 256))) return rc;
+  char *ob_base = (char *)ctx->h_out.p;
+  D.misfit = misfit ? (double *)(ob_base + o_mis) : nullptr;
+  D.samples = samples ? (double *)(ob_base + o_smp) : nullptr;
+  D.syn = syn ? (double *)(ob_base + o_syn) : nullptr;
+  D.initmodel = initmodel ? (double *)(ob_base + o_ini) : nullptr;
+  D.alog = accept_seq ? (signed char *)(ob_base + o_log) : nullptr;
+  if (D.misfit) CK(cudaMemsetAsync(D.misfit, 0, sizeof(double) * C * nsamples, st));
+  if (D.samples) CK(cudaMemsetAsync(D.samples, 0, sizeof(double) * C * nsamples * n2, st));
+  if (D.syn) CK(cudaMemsetAsync(D.syn, 0, sizeof(double) * C * nsamples * nd, st));
+  if (D.alog) CK(cudaMemsetAsync(D.alog, 0xff, (size_t)C * max_iter_log, st));
+
+  LAUNCH(hmc_init_kernel, gridFor(C, 64), 64, 0, st, D, cfg, C, (const long long *)d_ids, seed);
+  int h_active = 1;
+  long long steps = 0;
+  const int check_every = 16;
+  while (h_active > 0) {
+    for (int s = 0; s < check_every; s++) {
+      rc = rfs_misfit_grad_dev(ctx, C, D.xeval, 0, (double *)ctx->io_U.p, (double *)ctx->io_grad.p,
+                               (double *)ctx->io_dsyn.p, (unsigned char *)ctx->io_flag.p, st);
+      if (rc) return rc;
+      if (s == check_every - 1) CK(cudaMemsetAsync(D.n_active, 0, sizeof(int), st));
+      LAUNCH(hmc_advance_kernel, gridFor(C, 64), 64, 0, st, D, cfg, C);
+      steps++;
+    }
+    CK(cudaMemcpyAsync(&h_active, D.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  // results
+  std::vector<long long> nev(C);
+  CK(cudaMemcpyAsync(nev.data(), D.nevals, sizeof(long long) * C, cudaMemcpyDeviceToHost, st));
+  if (misfit) CK(cudaMemcpyAsync(misfit, D.misfit, sizeof(double) * C * nsamples, cudaMemcpyDeviceToHost, st));
+  if (samples)
+    CK(cudaMemcpyAsync(samples, D.samples, sizeof(double) * C * nsamples * n2, cudaMemcpyDeviceToHost, st));
+  if (syn) CK(cudaMemcpyAsync(syn, D.syn, sizeof(double) * C * nsamples * nd, cudaMemcpyDeviceToHost, st));
+  if (initmodel) CK(cudaMemcpyAsync(initmodel, D.initmodel, sizeof(double) * C * n2, cudaMemcpyDeviceToHost, st));
+  if (accept_seq) CK(cudaMemcpyAsync(accept_seq, D.alog, (size_t)C * max_iter_log, cudaMemcpyDeviceToHost, st));
+  if (n_iter) CK(cudaMemcpyAsync(n_iter, D.ncount, sizeof(long long) * C, cudaMemcpyDeviceToHost, st));
+  if (n_acc) CK(cudaMemcpyAsync(n_acc, D.iacc, sizeof(long long) * C, cudaMemcpyDeviceToHost, st));
+  if (dt_final) CK(cudaMemcpyAsync(dt_final, D.dt, sizeof(double) * C, cudaMemcpyDeviceToHost, st));
+  std::vector<int> status(C);
+  CK(cudaMemcpyAsync(status.data(), D.status, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  long long tot = 0;
+  for (long long c = 0; c < C; c++) tot += nev[c];
+  ctx->hmc_evals = tot;
+  long long nbad3 = 0, nbad4 = 0;
+  for (long long c = 0; c < C; c++) {
+    if (status[c] == 3) nbad3++;
+    if (status[c] == 4) nbad4++;
+  }
+  if (nbad3 || nbad4) {
+    char msg[256];
+    snprintf(msg, sizeof(msg),
+             "%lld chain(s) stuck at a state whose forward model fails (reference would loop "
+             "forever), %lld chain(s) failed inside _find_initial_dt (reference: exit(1))",
+             nbad3, nbad4);
+    ctx->err = msg;
+    return 1;  // positive: completed with per-chain failures (outputs are valid for the others)
+  }
+  return RFS_OK;
+}
+
+}  // extern "C"

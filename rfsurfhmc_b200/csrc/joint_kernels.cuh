@@ -1,0 +1,86 @@
+// Fused L2 glue on the device: SWD residuals/gradient contraction and the joint weighting.
+//
+// Replaces the NumPy glue of
+//   /root/reference/model/model_surf.py:155-228          (SurfWD.misfit_and_grad)
+//   /root/reference/model/model_rf.py:137-197            (ReceiverFunc.misfit_and_grad; its
+//                                                          contraction is done inside rf_decon_kernel)
+//   /root/reference/model/model_rf_swd_vs_thk.py:66-86   (Joint_RF_SWD.misfit_and_grad)
+// The Jacobians are contracted with the residuals on the fly; K = dcdb + dcda*dadb + dcdr*drda*dadb
+// (model_surf.py:184) is applied per layer.
+#pragma once
+#include "swd_kernels.cuh"
+
+namespace rfs {
+
+// which: 0 joint, 1 RF only, 2 SWD only
+// One thread per (model, layer).  Layout of outputs (row-major per model, as the Python API):
+//   U[B], grad[B][2n] (vs then thk), dsyn[B][ndata] with ndata = nt_rf + nsw (joint),
+//   flag[B] (1 ok, 0 failed SWD root search)
+__global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__restrict__ ierr,
+                                      const double *__restrict__ chain, int stale, int which,
+                                      int nt_rf, const double *__restrict__ dobs,
+                                      const double *__restrict__ U_rf,
+                                      const double *__restrict__ g_rf, double wt,
+                                      double *__restrict__ U, double *__restrict__ grad,
+                                      double *__restrict__ dsyn, unsigned char *__restrict__ flag) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long B = V.B;
+  const int n = V.n;
+  if (i >= B * n) return;
+  const long long b = i % B;
+  const int m = (int)(i / B);
+  const long long nB = (long long)n * B;
+  const int nsw = (which == 1) ? 0 : plan.ndata;
+  const int n1 = (which == 2) ? 0 : nt_rf;
+  const int ndata = n1 + nsw;
+  bool ok = true;
+  if (which != 1)
+    for (int s = 0; s < plan.nseq; s++) ok = ok && (ierr[(long long)s * B + b] == 0);
+  double gv = 0.0, gh = 0.0, us = 0.0;
+  if (which != 1 && ok) {
+    const double dadb = chain[0 * nB + m * B + b], drda = chain[1 * nB + m * B + b];
+    for (int r = 0; r < plan.nrow; r++) {
+      const SwdRow rw = plan.row[r];
+      for (int k = 0; k < rw.nper; k++) {
+        const double d = swd_row_value(plan, V, rw, k, b);
+        const double res = d - dobs[n1 + rw.d_off + k];
+        double K[4];
+        swd_row_kernels(plan, V, rw, k, m, b, stale, K);
+        const double kv = K[1] + K[0] * dadb + K[2] * drda * dadb;
+        gv += res * kv;
+        gh += res * K[3];
+        if (m == 0) {
+          us += res * res;
+          dsyn[b * ndata + n1 + rw.d_off + k] = d;
+        }
+      }
+    }
+  }
+  if (ok) {
+    const double w = (which == 0) ? wt : 1.0;
+    double g0 = w * gv, g1 = w * gh;
+    if (which != 2) {
+      g0 += g_rf[b * 2 * n + m];
+      g1 += g_rf[b * 2 * n + n + m];
+    }
+    grad[b * 2 * n + m] = g0;
+    grad[b * 2 * n + n + m] = g1;
+    if (m == 0) {
+      double u = w * 0.5 * us;
+      if (which != 2) u += U_rf[b];
+      U[b] = u;
+      flag[b] = 1;
+    }
+  } else {
+    // model_rf_swd_vs_thk.py:73-74: (0.0, zeros, dobs, False)
+    grad[b * 2 * n + m] = 0.0;
+    grad[b * 2 * n + n + m] = 0.0;
+    for (int j = m; j < ndata; j += n) dsyn[b * ndata + j] = (which == 2) ? 0.0 : dobs[j];
+    if (m == 0) {
+      U[b] = 0.0;
+      flag[b] = 0;
+    }
+  }
+}
+
+}  // namespace rfs

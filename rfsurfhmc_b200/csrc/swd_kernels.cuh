@@ -1,0 +1,218 @@
+// __global__ kernels of the SWD path and the host-side "plan" that maps the reference's four
+// wave types (Rc, Rg, Lc, Lg; /root/reference/src/SWD/surfdisp.cpp:190-297) onto unique
+// period sequences and eigen solves.
+#pragma once
+#include "swd_love.cuh"
+#include "swd_rayleigh.cuh"
+#include "swd_roots.cuh"
+
+namespace rfs {
+
+#define RFS_MAX_SEQ 12
+#define RFS_MAX_ROWS 4
+
+// one requested data block ("row"): a wave type on a period list
+struct SwdRow {
+  int type;      // 0 Rc, 1 Rg, 2 Lc, 3 Lg
+  int nper;      // periods
+  int per_off;   // offset of its period list in the period table
+  int s0, s1, s2;  // sequences: T, 1.05 T, 0.95 T (s1,s2 = -1 for phase velocity)
+  int d_off;     // offset of this row in the concatenated data vector
+};
+
+struct SwdPlan {
+  int nseq, nrow;
+  int nsolve;  // total (sequence, period) pairs == total periods over sequences
+  int ndata;   // total data count over rows
+  int nmode;   // modes solved (mode+1); the last one is reported
+  SwdSeq seq[RFS_MAX_SEQ];
+  SwdRow row[RFS_MAX_ROWS];
+};
+
+// ---- model preparation: x=[vs(n),thk(n)] -> Brocher vp/rho (+derivatives) and the two model
+// blocks.  Follows model/model_surf.py:47-79 and model/model_rf.py:52-77 (same polynomials) and
+// the float32 cast at the SWD boundary (src/SWD/main.cpp:7-9).
+// swd  : [SWD_NF][n][B]  float32-rounded values stored as double
+// rfm  : [4][n][B]       thk, rho, vp, vs in float64 (RF argument order)
+// chain: [2][n][B]       dadb, drda
+__global__ void prep_models_kernel(const double *__restrict__ x, long long B, int n,
+                                   double *__restrict__ swd, double *__restrict__ rfm,
+                                   double *__restrict__ chain) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const long long b = i % B;
+  const int m = (int)(i / B);
+  const double vs = x[b * 2 * n + m], thk = x[b * 2 * n + n + m];
+  const double vp = 0.9409 + 2.0947 * vs - 0.8206 * (vs * vs) + 0.2683 * (vs * vs * vs) -
+                    0.0251 * (vs * vs * vs * vs);
+  const double rho = 1.6612 * vp - 0.4721 * (vp * vp) + 0.0671 * (vp * vp * vp) -
+                     0.0043 * (vp * vp * vp * vp) + 0.000106 * (vp * vp * vp * vp * vp);
+  const double drda = 1.6612 - 0.4721 * 2 * vp + 0.0671 * 3 * (vp * vp) -
+                      0.0043 * 4 * (vp * vp * vp) + 0.000106 * 5 * (vp * vp * vp * vp);
+  const double dadb = 2.0947 - 0.8206 * 2 * vs + 0.2683 * 3 * (vs * vs) - 0.0251 * 4 * (vs * vs * vs);
+  const long long nb = (long long)n * B;
+  if (swd) {
+    const double d32 = (double)(float)thk, a32 = (double)(float)vp, b32 = (double)(float)vs,
+                 r32 = (double)(float)rho;
+    swd[F_D * nb + m * B + b] = d32;
+    swd[F_A * nb + m * B + b] = a32;
+    swd[F_B * nb + m * B + b] = b32;
+    swd[F_RHO * nb + m * B + b] = r32;
+    swd[F_IA * nb + m * B + b] = 1.0 / a32;
+    swd[F_IB * nb + m * B + b] = 1.0 / b32;
+    swd[F_IRHO * nb + m * B + b] = 1.0 / r32;
+  }
+  if (rfm) {
+    rfm[0 * nb + m * B + b] = thk;
+    rfm[1 * nb + m * B + b] = rho;
+    rfm[2 * nb + m * B + b] = vp;
+    rfm[3 * nb + m * B + b] = vs;
+  }
+  if (chain) {
+    chain[0 * nb + m * B + b] = dadb;
+    chain[1 * nb + m * B + b] = drda;
+  }
+}
+
+// explicit (thk,vp,vs,rho) -> SWD block, for the libsurf drop-in (float32 cast of main.cpp:9,62)
+__global__ void pack_swd_kernel(const double *__restrict__ thk, const double *__restrict__ vp,
+                                const double *__restrict__ vs, const double *__restrict__ rho,
+                                long long B, int n, double *__restrict__ swd) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const long long b = i % B;
+  const int m = (int)(i / B);
+  const long long nb = (long long)n * B;
+  const double d32 = (double)(float)thk[b * n + m], a32 = (double)(float)vp[b * n + m],
+               b32 = (double)(float)vs[b * n + m], r32 = (double)(float)rho[b * n + m];
+  swd[F_D * nb + m * B + b] = d32;
+  swd[F_A * nb + m * B + b] = a32;
+  swd[F_B * nb + m * B + b] = b32;
+  swd[F_RHO * nb + m * B + b] = r32;
+  swd[F_IA * nb + m * B + b] = 1.0 / a32;
+  swd[F_IB * nb + m * B + b] = 1.0 / b32;
+  swd[F_IRHO * nb + m * B + b] = 1.0 / r32;
+}
+
+// ---- K1: one thread per (model, sequence)
+// croot : [nmode_out][nsolve][B]   cwork : [nsolve][B] (only touched when nmode > 1)
+// ierr  : [nseq][B] int
+__global__ void __launch_bounds__(128)
+    swd_roots_kernel(SwdPlan plan, const double *__restrict__ swd, long long B, int n,
+                     const double *__restrict__ periods, int all_modes,
+                     double *__restrict__ croot, double *__restrict__ cwork,
+                     int *__restrict__ ierr) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * plan.nseq) return;
+  const long long b = i % B;
+  const int s = (int)(i / B);
+  SwdModel M{swd, B, n};
+  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+                                   (long long)plan.nsolve * B, cwork, B);
+  ierr[(long long)s * B + b] = e;
+}
+
+// ---- K2: one thread per (model, solve=(sequence,period)[, mode])
+// ugr  : [nmode_out][nsolve][B]     kern : [nmode_out][nsolve][4][n][B]
+template <int NMAX>
+__global__ void __launch_bounds__(128)
+    swd_eigen_kernel(SwdPlan plan, const double *__restrict__ swd, long long B, int n,
+                     const double *__restrict__ periods, int nmode_out,
+                     const double *__restrict__ croot, double *__restrict__ ugr,
+                     double *__restrict__ kern) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long tot = B * plan.nsolve * nmode_out;
+  if (i >= tot) return;
+  const long long b = i % B;
+  const long long sv = i / B;  // mode * nsolve + solve
+  const int solve = (int)(sv % plan.nsolve);
+  // find the sequence of this solve
+  int s = 0;
+  for (int q = 0; q < plan.nseq; q++)
+    if (solve >= plan.seq[q].out_off && solve < plan.seq[q].out_off + plan.seq[q].nper) s = q;
+  const SwdSeq sq = plan.seq[s];
+  const int k = solve - sq.out_off;
+  const double T = __ldg(periods + sq.per_off + k) * sq.scale;
+  const double c = croot[sv * B + b];
+  double *kp = kern + sv * 4 * (long long)n * B + b;
+  SwdModel M{swd, B, n};
+  double u;
+  if (!(c > 0.0)) {
+    // mode does not exist at this period (reference: c = 0 -> NaN kernels downstream)
+    const double qnan = nan("");
+    for (int j = 0; j < 4 * n; j++) kp[(long long)j * B] = qnan;
+    u = qnan;
+  } else if (sq.ifunc == 2) {
+    rayleigh_solve<NMAX>(M, b, T, c, &u, kp, B);
+  } else {
+    love_solve<NMAX>(M, b, T, c, &u, kp, B);
+  }
+  ugr[sv * B + b] = u;
+}
+
+// value + 4 kernels of data row `r`, period k, layer m for model b (drop-in adjoint_kernel
+// semantics, surfdisp.cpp:209-294 + sregnpu/slegnpu combination sregn96.f90:1839-1844).
+// Returns the datum (phase or group velocity); K[0..3] = d/d(vp,vs,rho,thk).
+struct SwdView {
+  const double *croot, *ugr, *kern;  // already offset to the reported mode
+  const double *periods;
+  long long B;
+  int n;
+};
+RFS_DEVINL double swd_row_value(const SwdPlan &plan, const SwdView &V, const SwdRow &rw, int k,
+                                long long b) {
+  const int sv0 = plan.seq[rw.s0].out_off + k;
+  if (rw.type == 0 || rw.type == 2) return V.croot[(long long)sv0 * V.B + b];
+  return V.ugr[(long long)sv0 * V.B + b];
+}
+RFS_DEVINL void swd_row_kernels(const SwdPlan &plan, const SwdView &V, const SwdRow &rw, int k,
+                                int m, long long b, int stale, double K[4]) {
+  const long long nB = (long long)V.n * V.B;
+  const int sv0 = plan.seq[rw.s0].out_off + k;
+  const double *k0 = V.kern + (long long)sv0 * 4 * nB + (long long)m * V.B + b;
+  if (rw.type == 0 || rw.type == 2) {
+    for (int p = 0; p < 4; p++) K[p] = k0[p * nB];
+    return;
+  }
+  const int sv1 = plan.seq[rw.s1].out_off + k, sv2 = plan.seq[rw.s2].out_off + k;
+  const double *k1 = V.kern + (long long)sv1 * 4 * nB + (long long)m * V.B + b;
+  const double *k2 = V.kern + (long long)sv2 * 4 * nB + (long long)m * V.B + b;
+  const double t = V.periods[rw.per_off + k];
+  const double t1 = t * (1.0 + 0.05), t2 = t * (1.0 - 0.05);
+  const double cp = V.croot[(long long)sv0 * V.B + b];
+  const double cg = V.ugr[(long long)sv0 * V.B + b];
+  const double uc1 = cg / cp;
+  for (int p = 0; p < 4; p++) {
+    const double first = stale ? k2[p * nB] : k0[p * nB];
+    K[p] = uc1 * (2.0 - uc1) * first - uc1 * uc1 * t * (k2[p * nB] - k1[p * nB]) / (t2 - t1);
+  }
+  if (rw.type == 3) K[0] = 0.0;
+}
+
+// Materialise the drop-in outputs of libsurf.adjoint_kernel for one row:
+//   c[B][nper], dcda/dcdb/dcdr/dcdh [B][nper][n]  (row-major per model, as the pybind returns)
+__global__ void swd_export_row_kernel(SwdPlan plan, int r, SwdView V, int stale,
+                                      double *__restrict__ c, double *__restrict__ dcda,
+                                      double *__restrict__ dcdb, double *__restrict__ dcdr,
+                                      double *__restrict__ dcdh) {
+  const SwdRow rw = plan.row[r];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long tot = V.B * rw.nper * V.n;
+  if (i >= tot) return;
+  const long long b = i % V.B;
+  const long long km = i / V.B;
+  const int m = (int)(km % V.n);
+  const int k = (int)(km / V.n);
+  if (m == 0) c[b * rw.nper + k] = swd_row_value(plan, V, rw, k, b);
+  if (dcda) {
+    double K[4];
+    swd_row_kernels(plan, V, rw, k, m, b, stale, K);
+    const long long o = (b * rw.nper + k) * V.n + m;
+    dcda[o] = K[0];
+    dcdb[o] = K[1];
+    dcdr[o] = K[2];
+    dcdh[o] = K[3];
+  }
+}
+
+}  // namespace rfs

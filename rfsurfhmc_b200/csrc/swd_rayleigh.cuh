@@ -1,0 +1,428 @@
+// K2 (Rayleigh) — eigenfunctions, energy integrals, group velocity and phase-velocity Frechet
+// kernels for one (model, period, c), one thread each.
+//
+// Replaces /root/reference/src/SWD/sregn96.f90: svfunc :196-402, up :404-492, dnka :494-650,
+// evalg :652-829, varsv :831-915, hska :917-991, down :993-1063, energy :1065-1201,
+// intijr :1203-1323, ffunc..h2func :1325-1403, getdcdh :1436-1535, getmat :1537-1589 and the
+// suffix-sum of sregn96 :1727-1731.
+//
+// Re-design (same mathematics, different schedule):
+//  * ONE up-sweep stores the normalised Dunkin vectors cd(m,1:5)+exe(m) in thread-local memory
+//    (6 doubles/layer); the down-sweep is fused with the eigenfunction assembly, the per-layer
+//    energy integrals and the boundary terms of dc/dh, so the Haskell vectors vv(m,:) and the
+//    eigenfunctions are never stored (reference: 25 heap arrays per call).
+//  * the six intijr integrals of a layer are ONE symmetric bilinear form a_i^T W a_j in the
+//    potentials; evalg (E, E^-1) is evaluated once per layer (reference: 6x).
+//  * vertical wavenumbers are real or purely imaginary, so varsv is done in real arithmetic.
+// Solid layers only (water layers: INTEGRATION.md "not yet").
+#pragma once
+#include "common.cuh"
+#include "swd_roots.cuh"
+
+namespace rfs {
+
+// varsv (:831-915) for one wavenumber: s = wvno^2 - xk^2 (real)
+struct VSV {
+  double c, rs, sr, ex;  // cos-like, r*sinh-like, sinh-like/r, exponent
+  bool imag;             // vertical wavenumber purely imaginary (oscillatory)
+  double r;              // |nu|
+};
+RFS_DEVINL VSV varsv_half(double s, double zd) {
+  VSV o;
+  const double small = (double)1.0e-5f;
+  if (s >= 0.0) {
+    o.imag = false;
+    o.r = sqrt(s);
+    const double pr = o.r * zd;
+    const double pfac = (pr < 30.0) ? exp(-2.0 * pr) : 0.0;
+    o.c = 0.5 + pfac * 0.5;
+    const double sinp = 0.5 - pfac * 0.5;
+    o.rs = o.r * sinp;
+    o.sr = (fabs(pr) < small && o.r < small) ? zd : sinp / o.r;
+    o.ex = pr;
+  } else {
+    o.imag = true;
+    o.r = sqrt(-s);
+    const double pi_ = o.r * zd;
+    double sn, cs;
+    sincos(pi_, &sn, &cs);
+    o.c = cs;
+    o.rs = -o.r * sn;
+    o.sr = (o.r < small) ? zd : sn / o.r;
+    o.ex = 0.0;
+  }
+  return o;
+}
+
+// sregn96.f90 dnka (:494-650), elastic branch: reduced 5x5 compound matrix, unique entries
+struct Dnk {
+  double c11, c12, c13, c14, c15, c21, c22, c23, c24, c31, c32, c33, c41, c42, c51;
+};
+RFS_DEVINL Dnk dnka_r(const VSV &P, const VSV &S, double rho, double b, double exa, double wvno,
+                      double wvno2, double om2) {
+  Dnk o;
+  const double a0 = (exa < 60.0) ? exp(-exa) : 0.0;
+  const double cpcq = P.c * S.c, cpy = P.c * S.sr, cpz = P.c * S.rs, cqw = S.c * P.sr,
+               cqx = S.c * P.rs, xy = P.rs * S.sr, xz = P.rs * S.rs, wy = P.sr * S.sr,
+               wz = P.sr * S.rs;
+  const float bf = (float)b, rf = (float)rho;
+  const double rho2 = (double)__fmul_rn(rf, rf);                        // REAL*4 rho*rho
+  const double gam = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 / om2;  // 2.0*b*b in REAL*4
+  const double gam2 = gam * gam, gamm1 = gam - 1.0, gamm2 = gamm1 * gamm1;
+  const double cqww2 = cqw * wvno2, cqxw2 = cqx / wvno2, gg1 = gam * gamm1;
+  const double a0c = 2.0 * (a0 - cpcq);
+  const double xz2 = xz / wvno2, gxz2 = gam * xz2, g2xz2 = gam2 * xz2;
+  const double a0cgg1 = a0c * (gam + gamm1);
+  const double wy2 = wy * wvno2, g2wy2 = gamm2 * wy2, g1wy2 = gamm1 * wy2;
+  const double rom2 = rho * om2;
+  double temp = a0c * gg1 + g2xz2 + g2wy2;
+  o.c33 = a0 + temp + temp;
+  o.c11 = cpcq - temp;
+  o.c12 = (-cqx + wvno2 * cpy) / rom2;
+  temp = 0.5 * a0cgg1 + gxz2 + g1wy2;
+  o.c13 = wvno * temp / rom2;
+  o.c14 = (-cqww2 + cpz) / rom2;
+  temp = wvno2 * (a0c + wy2) + xz;
+  o.c15 = -temp / (rho2 * om2 * om2);
+  o.c21 = (-gamm2 * cqw + gam2 * cpz / wvno2) * rho * om2;
+  o.c22 = cpcq;
+  o.c23 = (gamm1 * cqww2 - gam * cpz) / wvno;
+  o.c24 = -wz;
+  temp = 0.5 * a0cgg1 * gg1 + gam2 * gxz2 + gamm2 * g1wy2;
+  o.c31 = -2.0 * temp * rho * om2 / wvno;
+  o.c32 = -wvno * (gam * cqxw2 - gamm1 * cpy) * 2.0;
+  o.c41 = (-gam2 * cqxw2 + gamm2 * cpy) * rho * om2;
+  o.c42 = -xy;
+  temp = gamm2 * (a0c * gam2 + g2wy2) + gam2 * g2xz2;
+  o.c51 = -rho2 * om2 * om2 * temp / wvno2;
+  return o;
+}
+
+RFS_DEVINL cd mk(bool imag, double r) { return imag ? cd(0.0, r) : cd(r, 0.0); }
+
+// ffunc/gfunc/h1func/h2func (:1325-1403)
+RFS_DEVINL cd ffunc_d(cd nub, double dm) {
+  if (cabs(nub) < 1.0e-08) return cd(dm);
+  const cd arg = nub * dm;
+  cd exqq = (arg.x < 40.0) ? cexp(-2.0 * arg) : cd(0.0);
+  return (1.0 - exqq) / (2.0 * nub);
+}
+RFS_DEVINL cd gfunc_d(cd nub, double dm) {
+  const cd arg = nub * dm;
+  if (arg.x < 75.0) return cexp(-arg) * dm;
+  return cd(0.0);
+}
+RFS_DEVINL cd h1func_d(cd nua, cd nub, double dm) {
+  if (cabs(nub + nua) < 1.0e-08) return cd(dm);
+  const cd arg = (nua + nub) * dm;
+  cd exqq = (arg.x < 40.0) ? cexp(-arg) : cd(0.0);
+  return (1.0 - exqq) / (nub + nua);
+}
+RFS_DEVINL cd h2func_d(cd nua, cd nub, double dm) {
+  if (cabs(nub - nua) < 1.0e-08) return cd(dm);
+  cd arg = nua * dm;
+  cd exqp = (arg.x < 40.0) ? cexp(-arg) : cd(0.0);
+  arg = nub * dm;
+  cd exqq = (arg.x < 40.0) ? cexp(-arg) : cd(0.0);
+  return (exqq - exqp) / (nua - nub);
+}
+
+struct Eig4 {
+  double ur, uz, tz, tr;
+};
+
+// Output of one Rayleigh solve.  kern points at [4][n] doubles with element stride `ks`
+// (order: dcda, dcdb, dcdr, dcdh), dcdh already converted to d/d(thickness) (suffix sums).
+template <int NMAX>
+RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double c, double *ugr_out,
+                               double *__restrict__ kern, long long ks) {
+  const int mmax = M.n;
+  const double omega = (2.0 * RFS_PI32) / T;
+  const double wvno = omega / c;
+  const double wvno2 = wvno * wvno, om2 = omega * omega;
+  double cdl[NMAX * 6];  // [m][0..4] = cd, [m][5] = exe   (thread-local, L1-backed)
+
+  // ---------------- up-sweep (:404-492): half-space vector from evalg (:736-768)
+  {
+    const int m = mmax - 1;
+    const double za = M.ld(F_A, m, b), zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b);
+    const double xka = omega / za, xkb = omega / zb;
+    const double sa = wvno2 - xka * xka, sb = wvno2 - xkb * xkb;
+    const cd ra = mk(sa < 0.0, sqrt(fabs(sa))), rb = mk(sb < 0.0, sqrt(fabs(sb)));
+    double gam = zb * wvno / omega;
+    gam = 2.0 * (gam * gam);
+    const double gamm1 = gam - 1.0;
+    const cd rarb = ra * rb;
+    cd g1 = (zr * zr) * om2 * om2 * (wvno2 * gamm1 * gamm1 - (gam * gam) * rarb);
+    cd g2 = -zr * (wvno2 * ra) * om2;
+    cd g3 = -zr * (wvno2 * gamm1 - gam * rarb) * om2 * wvno;
+    cd g4 = zr * (wvno2 * rb) * om2;
+    cd g5 = wvno2 * (wvno2 - rarb);
+    const cd den = (-zr * zr * om2 * om2 * wvno2) * rarb;
+    const cd q = 0.25 * cinv(den);
+    cdl[m * 6 + 0] = (g1 * q).x;
+    cdl[m * 6 + 1] = (g2 * q).x;
+    cdl[m * 6 + 2] = (g3 * q).x;
+    cdl[m * 6 + 3] = (g4 * q).x;
+    cdl[m * 6 + 4] = (g5 * q).x;
+    cdl[m * 6 + 5] = 0.0;
+  }
+  double exsum = 0.0;
+  for (int m = mmax - 2; m >= 0; m--) {
+    const double za = M.ld(F_A, m, b), zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b),
+                 zd = M.ld(F_D, m, b);
+    const double xka = omega / za, xkb = omega / zb;
+    const VSV P = varsv_half(wvno2 - xka * xka, zd);
+    const VSV S = varsv_half(wvno2 - xkb * xkb, zd);
+    const Dnk A = dnka_r(P, S, zr, zb, P.ex + S.ex, wvno, wvno2, om2);
+    const double d0 = cdl[(m + 1) * 6 + 0], d1 = cdl[(m + 1) * 6 + 1], d2 = cdl[(m + 1) * 6 + 2],
+                 d3 = cdl[(m + 1) * 6 + 3], d4 = cdl[(m + 1) * 6 + 4];
+    // ee(i) = sum_j cd(m+1,j) ca(j,i); symmetric fill-ins of :620-645
+    //   ca(2,5)=c14 ca(3,4)=-2 c23 ca(3,5)=-2 c13 ca(4,3)=-c32/2 ca(4,4)=c22 ca(4,5)=c12
+    //   ca(5,2)=c41 ca(5,3)=-c31/2 ca(5,4)=c21 ca(5,5)=c11
+    double n0 = d0 * A.c11 + d1 * A.c21 + d2 * A.c31 + d3 * A.c41 + d4 * A.c51;
+    double n1 = d0 * A.c12 + d1 * A.c22 + d2 * A.c32 + d3 * A.c42 + d4 * A.c41;
+    double n2 = d0 * A.c13 + d1 * A.c23 + d2 * A.c33 + d3 * (-A.c32 / 2.0) + d4 * (-A.c31 / 2.0);
+    double n3 = d0 * A.c14 + d1 * A.c24 + d2 * (-2.0 * A.c23) + d3 * A.c22 + d4 * A.c21;
+    double n4 = d0 * A.c15 + d1 * A.c14 + d2 * (-2.0 * A.c13) + d3 * A.c12 + d4 * A.c11;
+    double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
+    if (t1 < 1.e-40) t1 = 1.0;
+    exsum = exsum + P.ex + S.ex + log(t1);
+    cdl[m * 6 + 0] = n0 / t1;
+    cdl[m * 6 + 1] = n1 / t1;
+    cdl[m * 6 + 2] = n2 / t1;
+    cdl[m * 6 + 3] = n3 / t1;
+    cdl[m * 6 + 4] = n4 / t1;
+    cdl[m * 6 + 5] = exsum;
+  }
+
+  // ---------------- fused down-sweep / eigenfunctions / energy integrals
+  const double f1213 = -cdl[1];
+  const double exe1 = cdl[5];
+  Eig4 et;  // eigenfunction at the top of the current layer
+  et.ur = cdl[2] / cdl[1];
+  et.uz = 1.0;
+  et.tz = 0.0;
+  et.tr = 0.0;
+  double v0 = 1.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // vv(m,1:4)
+  double exa_sum = 0.0;
+  double sumi0 = 0.0, sumi1 = 0.0, sumi2 = 0.0, sumi3 = 0.0;
+  const double cph = omega / wvno;
+  double zr_prev = 0.0, xmu_prev = 0.0, xlam_prev = 0.0;
+  for (int m = 0; m < mmax; m++) {
+    const bool half = (m == mmax - 1);
+    const double za = M.ld(F_A, m, b), zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b),
+                 zd = M.ld(F_D, m, b);
+    const double xmu = zr * zb * zb;
+    const double xlam = zr * za * za - 2 * xmu;
+    const double xka = omega / za, xkb = omega / zb;
+    const double sa = wvno2 - xka * xka, sb = wvno2 - xkb * xkb;
+
+    // ---- boundary term of dc/dh at the top of layer m (getdcdh :1436-1535, solid branches)
+    double gsum;
+    {
+      const double tur = et.ur, tuz = et.uz, ttz = et.tz, ttr = et.tr;
+      const double xl2mp = xlam + xmu + xmu;
+      const double duzdzp = (ttz + wvno * xlam * tur) / xl2mp;
+      const double durdzp = (ttr / xmu) - wvno * tuz;
+      if (m == 0) {
+        const double drho = zr, dmu = xmu, dl2mu = xlam + dmu + dmu;
+        gsum = om2 * drho * tuz * tuz + om2 * (tur * tur * drho) - wvno2 * dmu * tuz * tuz -
+               wvno2 * (tur * tur * dl2mu) + (xl2mp * duzdzp * duzdzp) + (xmu * durdzp * durdzp);
+      } else {
+        const double drho = zr - zr_prev, dmu = xmu - xmu_prev, dlm = xlam - xlam_prev;
+        const double dl2mu = dlm + dmu + dmu;
+        const double xl2mm = xlam_prev + xmu_prev + xmu_prev;
+        const double durdzm = (ttr / xmu_prev) - wvno * tuz;
+        const double duzdzm = (ttz + wvno * xlam_prev * tur) / xl2mm;
+        gsum = om2 * drho * tuz * tuz + om2 * (tur * tur * drho) - wvno2 * dmu * tuz * tuz -
+               wvno2 * (tur * tur * dl2mu) + (xl2mp * duzdzp * duzdzp - xl2mm * duzdzm * duzdzm) +
+               (xmu * durdzp * durdzp - xmu_prev * durdzm * durdzm);
+      }
+    }
+    kern[(3LL * mmax + m) * ks] = gsum;  // scaled by `fac` in the epilogue
+
+    // ---- E, E^-1 of this layer (evalg :736-768)
+    const cd ra = mk(sa < 0.0, sqrt(fabs(sa))), rb = mk(sb < 0.0, sqrt(fabs(sb)));
+    double gam = zb * wvno / omega;
+    gam = 2.0 * (gam * gam);
+    const double gamm1 = gam - 1.0;
+    const double rom2 = zr * om2;
+    const cd ira = cinv(ra), irb = cinv(rb);
+    // EINV rows (acting on [ur, uz, tz, tr])
+    const double ei11 = 0.5 * gam / wvno, ei13 = -0.5 / rom2;
+    const cd ei12 = (-0.5 * gamm1) * ira, ei14 = (0.5 * wvno / rom2) * ira;
+    const cd ei21 = (-0.5 * gamm1) * irb, ei23 = (0.5 * wvno / rom2) * irb;
+    // rows 3,4: EINV(3,:) = [ei11, -ei12, ei13, -ei14]; EINV(4,:) = [-ei21, ei11, -ei23, ei13]
+
+    Eig4 eb = et;  // eigenfunction at the bottom of the layer (top of m+1)
+    VSV P, S;
+    if (!half) {
+      // ---- Haskell step (hska :917-991, down :993-1063)
+      P = varsv_half(sa, zd);
+      S = varsv_half(sb, zd);
+      const double dfac = ((P.ex - S.ex) > 70.0) ? 0.0 : exp(S.ex - P.ex);
+      const double cosp = P.c, rsinp = P.rs, sinpr = P.sr;
+      const double cossv = dfac * S.c, rsinsv = dfac * S.rs, sinsvr = dfac * S.sr;
+      const float bf = (float)zb;
+      const double gmh = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 / om2;
+      const double gmh1 = gmh - 1.0;
+      const double a11 = cossv + gmh * (cosp - cossv);
+      const double a12 = -wvno * gmh1 * sinpr + gmh * rsinsv / wvno;
+      const double a13 = -wvno * (cosp - cossv) / rom2;
+      const double a14 = (wvno2 * sinpr - rsinsv) / rom2;
+      const double a21 = gmh * rsinp / wvno - wvno * gmh1 * sinsvr;
+      const double a22 = cosp - gmh * (cosp - cossv);
+      const double a23 = (-rsinp + wvno2 * sinsvr) / rom2;
+      const double a24 = -a13;
+      const double a31 = rom2 * gmh * gmh1 * (cosp - cossv) / wvno;
+      const double a32 = rom2 * (-gmh1 * gmh1 * sinpr + gmh * gmh * rsinsv / wvno2);
+      const double a33 = a22, a34 = -a12;
+      const double a41 = rom2 * (gmh * gmh * rsinp / wvno2 - gmh1 * gmh1 * sinsvr);
+      const double a42 = -a31, a43 = -a21, a44 = a11;
+      double w0 = a11 * v0 + a12 * v1 + a13 * v2 + a14 * v3;
+      double w1 = a21 * v0 + a22 * v1 + a23 * v2 + a24 * v3;
+      double w2 = a31 * v0 + a32 * v1 + a33 * v2 + a34 * v3;
+      double w3 = a41 * v0 + a42 * v1 + a43 * v2 + a44 * v3;
+      double t1 = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
+      if (t1 < 1.e-40) t1 = 1.0;
+      v0 = w0 / t1;
+      v1 = w1 / t1;
+      v2 = w2 / t1;
+      v3 = w3 / t1;
+      exa_sum = exa_sum + P.ex + log(t1);
+      // ---- eigenfunction at the top of layer m+1 (svfunc :268-315)
+      const int i = m + 1;
+      const double cd1 = cdl[i * 6 + 0], cd2 = cdl[i * 6 + 1], cd3 = cdl[i * 6 + 2], cd4 = -cd3,
+                   cd5 = cdl[i * 6 + 3], cd6 = cdl[i * 6 + 4];
+      const double tz1 = -v3, tz2 = -v2, tz3 = v1, tz4 = v0;
+      const double uu1 = tz2 * cd6 - tz3 * cd5 + tz4 * cd4;
+      const double uu2 = -tz1 * cd6 + tz3 * cd3 - tz4 * cd2;
+      const double uu3 = tz1 * cd5 - tz2 * cd3 + tz4 * cd1;
+      const double uu4 = -tz1 * cd4 + tz2 * cd2 - tz3 * cd1;
+      const double ext = exa_sum + cdl[i * 6 + 5] - exe1;
+      if (ext > -80.0 && ext < 80.0) {
+        const double fact = exp(ext);
+        eb.ur = uu1 * fact / f1213;
+        eb.uz = uu2 * fact / f1213;
+        eb.tz = uu3 * fact / f1213;
+        eb.tr = uu4 * fact / f1213;
+      } else {
+        eb.ur = eb.uz = eb.tz = eb.tr = 0.0;
+      }
+    }
+
+    // ---- potentials (intijr :1203-1323)
+    // downward coefficients at the top of the layer (rows 3,4 of E^-1), upward at the bottom
+    const cd km1pd = ei11 * et.ur - ei12 * et.uz + ei13 * et.tz - ei14 * et.tr;
+    const cd km1sd = -1.0 * (ei21 * et.ur) + ei11 * et.uz - ei23 * et.tz + ei13 * et.tr;
+    // E columns: E(:,1)=[k, ra, r g1, r g ra/k]  E(:,2)=[rb, k, r g rb/k, r g1]
+    //            E(:,3)=[k,-ra, r g1,-r g ra/k]  E(:,4)=[-rb, k,-r g rb/k, r g1]     (r = rho om^2)
+    const double rg1 = rom2 * gamm1;
+    const cd e41 = (rom2 * gam / wvno) * ra, e32 = (rom2 * gam / wvno) * rb;
+    cd a3[4], a4[4];  // a_i3 = E(i,3) km1pd, a_i4 = E(i,4) km1sd
+    a3[0] = wvno * km1pd;
+    a3[1] = -1.0 * (ra * km1pd);
+    a3[2] = rg1 * km1pd;
+    a3[3] = -1.0 * (e41 * km1pd);
+    a4[0] = -1.0 * (rb * km1sd);
+    a4[1] = wvno * km1sd;
+    a4[2] = -1.0 * (e32 * km1sd);
+    a4[3] = rg1 * km1sd;
+    double I11, I13, I22, I24, I33, I44;
+    if (half) {
+      const cd qa = 0.5 * ira, qb = 0.5 * irb, qab = cinv(ra + rb);
+#define RFS_HS(i, j) \
+  ((a3[i] * a3[j]) * qa + (a3[i] * a4[j] + a4[i] * a3[j]) * qab + (a4[i] * a4[j]) * qb).x
+      I11 = RFS_HS(0, 0);
+      I13 = RFS_HS(0, 2);
+      I22 = RFS_HS(1, 1);
+      I24 = RFS_HS(1, 3);
+      I33 = RFS_HS(2, 2);
+      I44 = RFS_HS(3, 3);
+#undef RFS_HS
+    } else {
+      const cd kmpu = ei11 * eb.ur + ei12 * eb.uz + ei13 * eb.tz + ei14 * eb.tr;
+      const cd kmsu = ei21 * eb.ur + ei11 * eb.uz + ei23 * eb.tz + ei13 * eb.tr;
+      cd a1[4], a2[4];
+      a1[0] = wvno * kmpu;
+      a1[1] = ra * kmpu;
+      a1[2] = rg1 * kmpu;
+      a1[3] = e41 * kmpu;
+      a2[0] = rb * kmsu;
+      a2[1] = wvno * kmsu;
+      a2[2] = e32 * kmsu;
+      a2[3] = rg1 * kmsu;
+      const cd FA = ffunc_d(ra, zd), GA = gfunc_d(ra, zd), FB = ffunc_d(rb, zd),
+               GB = gfunc_d(rb, zd), H1 = h1func_d(ra, rb, zd), H2 = h2func_d(ra, rb, zd);
+      // INT_ij = a_i^T W a_j,  W = [[FA,H1,GA,H2],[H1,FB,H2,GB],[GA,H2,FA,H1],[H2,GB,H1,FB]]
+#define RFS_WJ(j, b1, b2, b3, b4)                                     \
+  const cd b1 = FA * a1[j] + H1 * a2[j] + GA * a3[j] + H2 * a4[j];   \
+  const cd b2 = H1 * a1[j] + FB * a2[j] + H2 * a3[j] + GB * a4[j];   \
+  const cd b3 = GA * a1[j] + H2 * a2[j] + FA * a3[j] + H1 * a4[j];   \
+  const cd b4 = H2 * a1[j] + GB * a2[j] + H1 * a3[j] + FB * a4[j];
+#define RFS_DOT(i, b1, b2, b3, b4) (a1[i] * b1 + a2[i] * b2 + a3[i] * b3 + a4[i] * b4).x
+      {
+        RFS_WJ(0, p1, p2, p3, p4) I11 = RFS_DOT(0, p1, p2, p3, p4);
+      }
+      {
+        RFS_WJ(1, p1, p2, p3, p4) I22 = RFS_DOT(1, p1, p2, p3, p4);
+      }
+      {
+        RFS_WJ(2, p1, p2, p3, p4) I13 = RFS_DOT(0, p1, p2, p3, p4);
+        I33 = RFS_DOT(2, p1, p2, p3, p4);
+      }
+      {
+        RFS_WJ(3, p1, p2, p3, p4) I24 = RFS_DOT(1, p1, p2, p3, p4);
+        I44 = RFS_DOT(3, p1, p2, p3, p4);
+      }
+#undef RFS_WJ
+#undef RFS_DOT
+    }
+
+    // ---- energy integrals and un-normalised partials (energy :1065-1201, getmat :1537-1589)
+    {
+      const double TL = zr * zb * zb, TC = zr * za * za, TA = TC, TF = TA - 2. * TL;
+      const double a12 = -wvno, a14 = 1.0 / TL, a21 = wvno * TF / TC, a23 = 1.0 / TC;
+      const double URUR = I11, UZUZ = I22;
+      const double DURDUR = a12 * a12 * I22 + 2. * a12 * a14 * I24 + a14 * a14 * I44;
+      const double DUZDUZ = a21 * a21 * I11 + 2. * a21 * a23 * I13 + a23 * a23 * I33;
+      const double URDUZ = a21 * I11 + a23 * I13;
+      const double UZDUR = a12 * I22 + a14 * I24;
+      sumi0 += zr * (URUR + UZUZ);
+      sumi1 += TL * UZUZ + TA * URUR;
+      sumi2 += TL * UZDUR - TF * URDUZ;
+      sumi3 += TL * DURDUR + TC * DUZDUZ;
+      const double facah = zr * za * (URUR - 2. * URDUZ / wvno);
+      const double facav = zr * za * DUZDUZ / wvno2;
+      const double facbv = zr * zb * (UZUZ + 2. * UZDUR / wvno + DURDUR / wvno2 + 4. * URDUZ / wvno);
+      const double facr = -0.5 * cph * cph * (URUR + UZUZ);
+      kern[(0LL * mmax + m) * ks] = facah + facav;
+      kern[(1LL * mmax + m) * ks] = facbv;
+      kern[(2LL * mmax + m) * ks] = 0.5 * (za * facav + za * facah + zb * facbv) / zr + facr;
+    }
+    et = eb;
+    zr_prev = zr;
+    xmu_prev = xmu;
+    xlam_prev = xlam;
+  }
+  (void)sumi3;
+  // ---------------- epilogue: U, normalisation, boundary -> thickness suffix sums
+  const double ugr = (wvno * sumi1 + sumi2) / (omega * sumi0);
+  const double are = wvno / (2.0 * omega * ugr * sumi0);
+  const double fac = are * cph / wvno2;
+  const double nrm = ugr * sumi0;
+  double suffix = 0.0;
+  for (int m = mmax - 1; m >= 0; m--) {
+    kern[(0LL * mmax + m) * ks] = kern[(0LL * mmax + m) * ks] / nrm;
+    kern[(1LL * mmax + m) * ks] = kern[(1LL * mmax + m) * ks] / nrm;
+    kern[(2LL * mmax + m) * ks] = kern[(2LL * mmax + m) * ks] / nrm;
+    double dfac = fac * kern[(3LL * mmax + m) * ks];
+    if (fabs(dfac) < 1.0e-38) dfac = 0.0;
+    kern[(3LL * mmax + m) * ks] = suffix;  // dcdh(i) = sum_{j>i} raw(j); dcdh(mmax) = 0
+    suffix += dfac;
+  }
+  *ugr_out = ugr;
+}
+
+}  // namespace rfs

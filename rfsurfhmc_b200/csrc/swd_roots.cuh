@@ -1,0 +1,489 @@
+// K1 — batched phase-velocity root search (one thread per (model, period-sequence)).
+//
+// Replaces /root/reference/src/SWD/surfdisp96.f (surfdisp96 :54-368, getsol :398-491,
+// nevill :568-687, half :689-701, dltar1 :727-787, dltar4 :791-891, var :894-1011,
+// dnka :1044-1088) and the retry loop of /root/reference/src/SWD/surfdisp.cpp:93-100.
+//
+// B200 design: the reference's recursion getsol -> nevill -> dltar is flattened into ONE
+// per-thread state machine whose loop body contains exactly one secular-function evaluation, so
+// the 32 lanes of a warp (32 different models, same sequence) stay converged on the expensive
+// Dunkin/Haskell layer sweep no matter where each lane is in its own scan / bisection / Neville
+// step.  The scan grid (dc = float32 0.005), the period-to-period and mode-to-mode chaining, the
+// `del1st` sign memory and the hybrid `nevill` refinement are reproduced exactly, because the
+// returned root depends on them at the 1e-6 level (SURVEY.md §7 hard part 1).
+// Model arrays live in HBM as [field][layer][model] (model fastest => coalesced, L1-resident).
+#pragma once
+#include "common.cuh"
+
+namespace rfs {
+
+// field indices of the SWD model block (all values are float32-rounded, stored as double)
+enum { F_D = 0, F_A = 1, F_B = 2, F_RHO = 3, F_IA = 4, F_IB = 5, F_IRHO = 6, SWD_NF = 7 };
+
+struct SwdModel {
+  const double *p;   // [SWD_NF][n][stride]
+  long long stride;  // models in the batch (B)
+  int n;             // layers (last = half-space)
+  RFS_DEVINL double ld(int f, int m, long long b) const {
+    return __ldg(p + ((long long)f * n + m) * stride + b);
+  }
+};
+
+// ---- Love secular function: Haskell 2-vector from the half-space up (surfdisp96.f:727-787)
+RFS_DEVINL double dltar1_dev(double wvno, double omega, const SwdModel &M, long long b, int llw) {
+  const int mmax = M.n;
+  double beta1 = M.ld(F_B, mmax - 1, b);
+  double rho1 = M.ld(F_RHO, mmax - 1, b);
+  double xkb = omega / beta1;
+  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  double e1 = rho1 * rb;
+  double e2 = 1.0 / (beta1 * beta1);
+  for (int m = mmax - 2; m >= llw - 1; m--) {
+    beta1 = M.ld(F_B, m, b);
+    rho1 = M.ld(F_RHO, m, b);
+    const double dm = M.ld(F_D, m, b);
+    const double xmu = rho1 * beta1 * beta1;
+    xkb = omega / beta1;
+    rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    const double q = dm * rb;
+    double y, z, cosq;
+    if (wvno < xkb) {
+      double sinq;
+      sincos(q, &sinq, &cosq);
+      y = sinq / rb;
+      z = -rb * sinq;
+    } else if (wvno == xkb) {
+      cosq = 1.0;
+      y = dm;
+      z = 0.0;
+    } else {
+      double fac = 0.0;
+      if (q < 16.0) fac = exp(-2.0 * q);
+      cosq = (1.0 + fac) * 0.5;
+      const double sinq = (1.0 - fac) * 0.5;
+      y = sinq / rb;
+      z = rb * sinq;
+    }
+    const double e10 = e1 * cosq + e2 * xmu * z;
+    const double e20 = e1 * y / xmu + e2 * cosq;
+    double xnor = fmax(fabs(e10), fabs(e20));
+    if (xnor < 1.e-40) xnor = 1.0;
+    e1 = e10 / xnor;
+    e2 = e20 / xnor;
+  }
+  return e1;
+}
+
+// hyperbolic / circular layer functions of surfdisp96.f `var` (:894-1011) for one wave type
+struct VarHalf {
+  double c, w, x, ex;  // cos-like, sin/r, (+-)r*sin, exponent
+};
+RFS_DEVINL VarHalf var_half(double wvno, double xk, double r, double pq, double dpth) {
+  VarHalf o;
+  o.ex = 0.0;
+  if (wvno < xk) {
+    double s;
+    sincos(pq, &s, &o.c);
+    o.w = s / r;
+    o.x = -r * s;
+  } else if (wvno == xk) {
+    o.c = 1.0;
+    o.w = dpth;
+    o.x = 0.0;
+  } else {
+    o.ex = pq;
+    double fac = 0.0;
+    if (pq < 16.0) fac = exp(-2.0 * pq);
+    o.c = (1.0 + fac) * 0.5;
+    const double s = (1.0 - fac) * 0.5;
+    o.w = s / r;
+    o.x = r * s;
+  }
+  return o;
+}
+
+// ---- Rayleigh secular function: Dunkin 5-vector compound matrix (surfdisp96.f:791-891)
+RFS_DEVINL double dltar4_dev(double wvno, double omga, const SwdModel &M, long long b, int llw) {
+  const int mmax = M.n;
+  double omega = omga;
+  if (omega < 1.0e-4) omega = 1.0e-4;
+  const double wvno2 = wvno * wvno;
+  double e0, e1, e2, e3, e4;
+  {
+    const double am = M.ld(F_A, mmax - 1, b), bm = M.ld(F_B, mmax - 1, b);
+    const double rho1 = M.ld(F_RHO, mmax - 1, b);
+    const double xka = omega / am, xkb = omega / bm;
+    const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    const double t = bm / omega;
+    const double gammk = 2.0 * t * t;
+    const double gam = gammk * wvno2;
+    const double gamm1 = gam - 1.0;
+    e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
+    e1 = -rho1 * ra;
+    e2 = rho1 * (gamm1 - gammk * ra * rb);
+    e3 = rho1 * rb;
+    e4 = wvno2 - ra * rb;
+  }
+  for (int m = mmax - 2; m >= llw - 1; m--) {
+    const double am = M.ld(F_A, m, b), bm = M.ld(F_B, m, b);
+    const double dpth = M.ld(F_D, m, b), rho = M.ld(F_RHO, m, b);
+    const double xka = omega / am, xkb = omega / bm;
+    const double t = bm / omega;
+    const double gammk = 2.0 * t * t;
+    const double gam = gammk * wvno2;
+    const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+    const VarHalf P = var_half(wvno, xka, ra, ra * dpth, dpth);
+    const VarHalf S = var_half(wvno, xkb, rb, rb * dpth, dpth);
+    const double exa = P.ex + S.ex;
+    double a0 = 0.0;
+    if (exa < 60.0) a0 = exp(-exa);
+    const double cpcq = P.c * S.c, cpy = P.c * S.w, cpz = P.c * S.x, cqw = S.c * P.w,
+                 cqx = S.c * P.x, xy = P.x * S.w, xz = P.x * S.x, wy = P.w * S.w, wz = P.w * S.x;
+    // Dunkin matrix (dnka :1044-1088), unique entries only
+    const double gamm1 = gam - 1.0, twgm1 = gam + gamm1, gmgmk = gam * gammk, gmgm1 = gam * gamm1,
+                 gm1sq = gamm1 * gamm1, rho2 = rho * rho, a0pq = a0 - cpcq;
+    const double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
+    const double c12 = (wvno2 * cpy - cqx) / rho;
+    const double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) / rho;
+    const double c14 = (cpz - wvno2 * cqw) / rho;
+    const double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) / rho2;
+    const double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
+    const double c22 = cpcq;
+    const double c23 = gammk * cpz - gamm1 * cqw;
+    const double c24 = -wz;
+    const double c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
+    const double c42 = -xy;
+    const double c43 = gamm1 * cpy - gammk * cqx;
+    const double c51 =
+        -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
+    const double c53 =
+        -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
+    const double tt = -2.0 * wvno2;
+    const double c31 = tt * c53, c32 = tt * c43, c33 = a0 + 2.0 * (cpcq - c11), c34 = tt * c23,
+                 c35 = tt * c13;
+    // ee(i) = sum_j e(j) ca(j,i), with ca(2,5)=c14 ca(4,4)=c22 ca(4,5)=c12 ca(5,2)=c41
+    // ca(5,4)=c21 ca(5,5)=c11   (same left-to-right summation order as the reference)
+    double n0 = e0 * c11 + e1 * c21 + e2 * c31 + e3 * c41 + e4 * c51;
+    double n1 = e0 * c12 + e1 * c22 + e2 * c32 + e3 * c42 + e4 * c41;
+    double n2 = e0 * c13 + e1 * c23 + e2 * c33 + e3 * c43 + e4 * c53;
+    double n3 = e0 * c14 + e1 * c24 + e2 * c34 + e3 * c22 + e4 * c21;
+    double n4 = e0 * c15 + e1 * c14 + e2 * c35 + e3 * c12 + e4 * c11;
+    double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
+    if (t1 < 1.e-40) t1 = 1.0;
+    e0 = n0 / t1;
+    e1 = n1 / t1;
+    e2 = n2 / t1;
+    e3 = n3 / t1;
+    e4 = n4 / t1;
+  }
+  if (llw != 1) {
+    // water layer on top (surfdisp96.f:870-886)
+    const double am = M.ld(F_A, 0, b), dpth = M.ld(F_D, 0, b), rho1 = M.ld(F_RHO, 0, b);
+    const double xka = omega / am;
+    const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+    const VarHalf P = var_half(wvno, xka, ra, ra * dpth, dpth);
+    const double w0 = -rho1 * P.w;
+    return P.c * e0 + w0 * e1;
+  }
+  return e0;
+}
+
+// One sequence = one wave family on one period list (optionally scaled: 1.05 T / 0.95 T for the
+// group-velocity kernels, surfdisp.cpp:234-241).
+struct SwdSeq {
+  int ifunc;      // 1 Love, 2 Rayleigh
+  int per_off;    // offset into the period table
+  int nper;       // periods in this sequence (ascending)
+  int out_off;    // offset (in periods) of this sequence in the output block
+  double scale;   // period multiplier
+};
+
+// float32 Newton start value (gtsolh, surfdisp96.f:375-396) — all REAL*4
+RFS_DEVINL float gtsolh_dev(float a, float b) {
+  float c = __fmul_rn(0.95f, b);
+  for (int i = 0; i < 5; i++) {
+    float gamma = __fdiv_rn(b, a);
+    float kappa = __fdiv_rn(c, b);
+    float k2 = __fmul_rn(kappa, kappa);
+    float gk = __fmul_rn(gamma, kappa);
+    float gk2 = __fmul_rn(gk, gk);
+    float fac1 = __fsqrt_rn(__fsub_rn(1.0f, gk2));
+    float fac2 = __fsqrt_rn(__fsub_rn(1.0f, k2));
+    float tk = __fsub_rn(2.0f, k2);
+    float fr = __fsub_rn(__fmul_rn(tk, tk), __fmul_rn(__fmul_rn(4.0f, fac1), fac2));
+    float t1 = __fmul_rn(__fmul_rn(-4.0f, tk), kappa);
+    float t2 = __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(4.0f, fac2), gamma), gamma), kappa), fac1);
+    float t3 = __fdiv_rn(__fmul_rn(__fmul_rn(4.0f, fac1), kappa), fac2);
+    float frp = __fadd_rn(__fadd_rn(t1, t2), t3);
+    frp = __fdiv_rn(frp, b);
+    c = __fsub_rn(c, __fdiv_rn(fr, frp));
+  }
+  return c;
+}
+
+// phases of the flattened getsol/nevill state machine
+enum { PH_START = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE };
+
+// Solve all modes 1..nmode of sequence `sq` for model b.
+//  cout  : [nmode_out][nper][stride] float32-rounded roots (0 where a mode does not exist)
+//  cwork : [nper][stride] unrounded roots of the running mode (chain state), may alias nothing
+// returns ierr (1 = fundamental mode not found, even after the per-period retry).
+RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &sq,
+                                  const double *__restrict__ periods, int nmode, int all_modes,
+                                  double *__restrict__ cout, long long cout_mode_stride,
+                                  double *__restrict__ cwork, long long stride) {
+  const int mmax = M.n;
+  const int ifunc = sq.ifunc;
+  const int kmax = sq.nper;
+  // ---- prologue of surfdisp96 (:128-220): extremal velocities and float32 start value
+  const int llw = (M.ld(F_B, 0, b) <= 0.0) ? 2 : 1;
+  int jmn = 0, jsol = 1;
+  float betmx = -1.e20f, betmn = 1.e20f;
+  for (int i = 0; i < mmax; i++) {
+    const float bi = (float)M.ld(F_B, i, b), ai = (float)M.ld(F_A, i, b);
+    if (bi > 0.01f && bi < betmn) {
+      betmn = bi;
+      jmn = i;
+      jsol = 1;
+    } else if (bi <= 0.01f && ai < betmn) {
+      betmn = ai;
+      jmn = i;
+      jsol = 0;
+    }
+    if (bi > betmx) betmx = bi;
+  }
+  float cc1;
+  if (jsol == 0)
+    cc1 = betmn;
+  else
+    cc1 = gtsolh_dev((float)M.ld(F_A, jmn, b), (float)M.ld(F_B, jmn, b));
+  cc1 = __fmul_rn(0.95f, cc1);
+  cc1 = __fmul_rn(0.90f, cc1);
+  const double cc = (double)cc1;
+  const double dc = (double)0.005f;
+  const double one = 1.0e-2, onea = 1.5;
+  const double cm = cc;
+  const double betmxd = (double)betmx;
+  const double twopi = 2.0 * RFS_PI64;
+
+  int ierr = 0;
+  // job 0: the whole sequence; jobs 1.. : per-period retries (surfdisp.cpp:93-100)
+  int kb = 0, ke = kmax;  // [kb,ke) periods of the current job
+  int retry_k = -1;
+  for (;;) {
+    const int jk = ke - kb;  // kmax of this job
+    int ift = 999;
+    int job_ierr = 0;
+    double del1st = 0.0;
+    for (int iq = 1; iq <= nmode; iq++) {
+      double *cq = cout + (all_modes ? (long long)(iq - 1) * cout_mode_stride : 0);
+      int k = 0;
+      bool failed = false;
+      double cprev = 0.0;  // c(k-1) of the present mode
+      for (k = 0; k < jk; k++) {
+        if (k + 1 >= ift) {
+          failed = true;
+          break;
+        }
+        const double t1 = __ldg(periods + sq.per_off + kb + k) * sq.scale;
+        const double omega = twopi / t1;
+        // ---- start values (surfdisp96.f:257-276)
+        double c1, clow;
+        int ifirst;
+        if (k == 0 && iq == 1) {
+          c1 = cc;
+          clow = cc;
+          ifirst = 1;
+        } else if (k == 0 && iq > 1) {
+          c1 = cwork[(long long)(kb + 0) * stride + b] + one * dc;
+          clow = c1;
+          ifirst = 1;
+        } else if (k > 0 && iq > 1) {
+          ifirst = 0;
+          clow = cwork[(long long)(kb + k) * stride + b] + one * dc;
+          c1 = cprev;
+          if (c1 < clow) c1 = clow;
+        } else {
+          ifirst = 0;
+          c1 = cprev - onea * dc;
+          clow = cm;
+        }
+        // ---- flattened getsol + nevill: one secular evaluation per loop trip
+        double c2 = 0.0, del1 = 0.0, del2 = 0.0, c3 = 0.0, del3 = 0.0;
+        double xs[12], ys[12];
+        int idir = 1, nev = 1, nctrl = 1, mm = 1;
+        int phase = PH_G_FIRST;
+        double ceval = c1;
+        int iret = 0;  // 0 running, 1 ok, -1 fail
+        while (iret == 0) {
+          const double wv = omega / ceval;
+          const double val = (ifunc == 1) ? dltar1_dev(wv, omega, M, b, llw)
+                                          : dltar4_dev(wv, omega, M, b, llw);
+          bool body = false;
+          if (phase == PH_G_FIRST) {
+            del1 = val;
+            if (ifirst == 1) del1st = del1;
+            const double plmn = sgn1(del1st) * sgn1(del1);
+            idir = (ifirst == 1 || plmn >= 0.0) ? +1 : -1;
+            // first c2 (label 1000, :457-470)
+            for (;;) {
+              c2 = (idir > 0) ? c1 + dc : c1 - dc;
+              if (c2 <= clow) {
+                idir = +1;
+                c1 = clow;
+                continue;
+              }
+              break;
+            }
+            ceval = c2;
+            phase = PH_G_SCAN;
+          } else if (phase == PH_G_SCAN) {
+            del2 = val;
+            if (sgn1(del1) != sgn1(del2)) {
+              // bracketed -> nevill: initial half
+              c3 = 0.5 * (c1 + c2);
+              ceval = c3;
+              nev = 1;
+              nctrl = 1;
+              phase = PH_N_TOP;
+            } else {
+              c1 = c2;
+              del1 = del2;
+              if (c1 < cm || c1 >= (betmxd + dc)) {
+                iret = -1;
+              } else {
+                for (;;) {
+                  c2 = (idir > 0) ? c1 + dc : c1 - dc;
+                  if (c2 <= clow) {
+                    idir = +1;
+                    c1 = clow;
+                    continue;
+                  }
+                  break;
+                }
+                ceval = c2;
+              }
+            }
+          } else if (phase == PH_N_TOP) {
+            del3 = val;
+            nctrl = nctrl + 1;
+            if (nctrl >= 100) {
+              iret = 2;  // nevill exit by iteration cap -> cc = c3
+            } else if (c3 < fmin(c1, c2) || c3 > fmax(c1, c2)) {
+              nev = 0;
+              c3 = 0.5 * (c1 + c2);
+              ceval = c3;
+              phase = PH_N_OUTSIDE;
+            } else {
+              body = true;
+            }
+          } else {  // PH_N_OUTSIDE
+            del3 = val;
+            body = true;
+          }
+          if (body) {
+            const double s13 = del1 - del3;
+            const double s32 = del3 - del2;
+            if (sgn1(del3) * sgn1(del1) < 0.0) {
+              c2 = c3;
+              del2 = del3;
+            } else {
+              c1 = c3;
+              del1 = del3;
+            }
+            if (fabs(c1 - c2) <= 1.e-6 * c1) {
+              iret = 2;
+            } else {
+              if (sgn1(s13) != sgn1(s32)) nev = 0;
+              const double ss1 = fabs(del1), ss2 = fabs(del2);
+              const double s1 = (double)0.01f * ss1, s2 = (double)0.01f * ss2;
+              bool do_half = (s1 > ss2 || s2 > ss1 || nev == 0);
+              if (!do_half) {
+                if (nev == 2) {
+                  xs[mm] = c3;
+                  ys[mm] = del3;
+                } else {
+                  xs[0] = c1;
+                  ys[0] = del1;
+                  xs[1] = c2;
+                  ys[1] = del2;
+                  mm = 1;
+                }
+                bool bad = false;
+                for (int kk = 1; kk <= mm; kk++) {
+                  const int j = mm - kk;  // 0-based index of x(j)
+                  const double denom = ys[mm] - ys[j];
+                  if (fabs(denom) < 1.0e-10 * fabs(ys[mm])) {
+                    bad = true;
+                    break;
+                  }
+                  xs[j] = (-ys[j] * xs[j + 1] + ys[mm] * xs[j]) / denom;
+                }
+                if (!bad) {
+                  c3 = xs[0];
+                  nev = 2;
+                  mm = mm + 1;
+                  if (mm > 10) mm = 10;
+                } else {
+                  do_half = true;
+                }
+              }
+              if (do_half) {
+                c3 = 0.5 * (c1 + c2);
+                nev = 1;
+                mm = 1;
+              }
+              ceval = c3;
+              phase = PH_N_TOP;
+            }
+          }
+        }
+        if (iret == 2) {
+          // back in getsol (:483-487)
+          c1 = c3;
+          iret = (c1 > betmxd) ? -1 : 1;
+        }
+        if (iret == -1) {
+          failed = true;
+          break;
+        }
+        cprev = c1;
+        if (nmode > 1) cwork[(long long)(kb + k) * stride + b] = c1;
+        cq[(long long)(sq.out_off + kb + k) * stride + b] = (double)(float)c1;  // cg(k)=sngl(c(k))
+      }
+      if (!failed) continue;
+      if (iq <= 1) job_ierr = 1;
+      ift = k + 1;
+      for (int i = k; i < jk; i++) cq[(long long)(sq.out_off + kb + i) * stride + b] = 0.0;
+    }
+    // ---- job bookkeeping: emulate _surfdisp's retry of zero periods when ierr != 0
+    if (retry_k < 0) {
+      if (job_ierr == 0) break;  // main pass fine (missing higher modes are zeros with ierr 0)
+      ierr = 1;
+      retry_k = 0;
+    } else {
+      // we just retried period retry_k-1 as a single-period job
+      ierr = job_ierr;
+      if (job_ierr != 0) break;  // `if(ierr !=0) return ierr;`
+    }
+    // find next period whose (last-mode) output is zero / NaN
+    const double *clast = cout + (all_modes ? (long long)(nmode - 1) * cout_mode_stride : 0);
+    int kn = -1;
+    for (int i = retry_k; i < kmax; i++) {
+      const double v = clast[(long long)(sq.out_off + i) * stride + b];
+      if (v == 0.0 || isnan(v)) {
+        kn = i;
+        break;
+      }
+    }
+    if (kn < 0) break;
+    kb = kn;
+    ke = kn + 1;
+    retry_k = kn + 1;
+  }
+  return ierr;
+}
+
+}  // namespace rfs
