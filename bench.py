@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — joint RF+SWD forward+gradient evaluations/s on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            (our arm: sm_100a CUDA through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU arm: oracle restatement of the
+                                                              reference, all host threads)
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, chains sharded)
+
+One "step" = one batched Joint_RF_SWD.misfit_and_grad over `--chains` chain states per GPU at the
+C1/C4 sizes of SURVEY.md §8 (n=7 layers, 36 Rc + 36 Rg periods, RF nt=125 -> nft=128; reference
+param.yaml), i.e. the evaluation every leapfrog step of every chain performs.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# frozen algorithmic-work constants (hand counts of SURVEY.md §8d)
+F_R = 375.0      # flop per Rayleigh secular-function layer step (dltar4 body)
+N_LAYERS = 7
+
+
+def workload(nchains, seed):
+    from rfsurfhmc_b200.fixtures import f1_config, f1_true_model, driver_bounds, sorted_uniform_models
+    cfg = f1_config()
+    x0 = f1_true_model()
+    X = sorted_uniform_models(driver_bounds(x0), nchains, seed)
+    return cfg, x0, X
+
+
+def make_dobs(cfg, x0):
+    """Observations = synthetics of the true model (main_base.py:49-56), computed by the oracle
+    on the CPU (test infrastructure used as data generator, not on the timed path)."""
+    from oracle.oracle import Oracle
+    O = Oracle()
+    nd = cfg["nt"] + len(cfg["tRc"]) + len(cfg["tRg"])
+    _, _, d, _ = O.joint_batch(x0[None, :], np.zeros(nd), cfg)
+    return d[0]
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev = dev
+        self.rows = []
+        self.stop = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons}
+
+
+def cpu_arm(cfg, dobs, X, seconds, nthreads):
+    """Oracle restatement (-O3 build) timed on the host cores: evaluations/s."""
+    from oracle.oracle import Oracle
+    O = Oracle(fast=True)
+    chunk = max(64, 16 * nthreads)
+    done = 0
+    t0 = time.perf_counter()
+    i = 0
+    while True:
+        xb = X[(i * chunk) % len(X):][:chunk]
+        if len(xb) < chunk:
+            xb = X[:chunk]
+        O.joint_batch(xb, dobs, cfg, nthreads=nthreads)
+        done += len(xb)
+        i += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=16384, help="chain states per GPU (C4: 16384)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    config = {"workload": "C4/C1 joint RF+SWD misfit_and_grad: n=7 layers, 36 Rc + 36 Rg periods (5-40 s), "
+                          "RF nt=125 (nft=128) freq-domain P, %d chain states per GPU" % args.chains,
+              "chains_per_gpu": args.chains, "parallelism": "chains sharded, no data-path collective",
+              "l2": "inputs rotated over 4 batches + 256 MiB L2 flush between steps (inside the timed region)"}
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cfg, x0, X = workload(4096, 1234)
+        dobs = make_dobs(cfg, x0)
+        per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
+        for _ in range(min(args.warmup, 1)):
+            cpu_arm(cfg, dobs, X, 0.5, ncores)
+        tot, tt = 0, 0.0
+        for _ in range(args.steps):
+            v, done, dt = cpu_arm(cfg, dobs, X, per_step, ncores)
+            tot += done
+            tt += dt
+        val = tot / tt
+        print(json.dumps({
+            "impl": "reference", "metric": "joint RF+SWD forward+gradient evaluations/s",
+            "value": val, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": ncores, "kind": "port",
+                             "sample": "%d evaluations in %.1f s (oracle restatement of the reference CPU "
+                                       "path, g++ -O3, %d threads; reference itself not buildable: no "
+                                       "gfortran/FFTW3)" % (tot, tt, ncores)},
+            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from rfsurfhmc_b200._lib import Context
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (rfsurfhmc_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.chains
+    cfg, x0, _ = workload(1, 0)
+    dobs = make_dobs(cfg, x0)
+    nd = dobs.size
+    ctx = Context(local_rank)
+    ctx.config_swd(N_LAYERS, tRc=cfg["tRc"], tRg=cfg["tRg"])
+    ctx.config_rf(N_LAYERS, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"],
+                  cfg["water"], cfg["rf_type"], cfg["method"])
+    ctx.config_obs(dobs)
+    nrot = 4
+    Xs = [workload(B, 1000 + 97 * rank + i)[2] for i in range(nrot)]
+    xd = [torch.from_numpy(x).to(dev) for x in Xs]
+    U = torch.empty(B, dtype=torch.float64, device=dev)
+    G = torch.empty(B, 2 * N_LAYERS, dtype=torch.float64, device=dev)
+    D = torch.empty(B, nd, dtype=torch.float64, device=dev)
+    Fl = torch.empty(B, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        flush.zero_()
+        ctx.misfit_grad_dev(B, xd[i % nrot].data_ptr(), 0, U.data_ptr(), G.data_ptr(), D.data_ptr(),
+                            Fl.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    fp64_peak = ctx.measure_fp64_peak()
+    ctx.count_evals(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    nev = ctx.read_evals()
+    ctx.count_evals(False)
+    sampler.stop = True
+    n_fail = int((Fl == 0).sum().item())
+
+    # kernel-level timing of the dominant kernel (swd_roots) with CUDA events on the same stream:
+    # re-run the SWD-only path where the roots kernel is >70 % of the time is not exact, so time the
+    # full step with the flush excluded instead and attribute by the ncu share (profiles/).
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for i in range(5):
+        ctx.misfit_grad_dev(B, xd[i % nrot].data_ptr(), 0, U.data_ptr(), G.data_ptr(), D.data_ptr(),
+                            Fl.data_ptr(), stream.cuda_stream)
+    ev[1].record(stream)
+    torch.cuda.synchronize()
+    ms_noflush = ev[0].elapsed_time(ev[1]) / 5
+
+    # ---- e2e: host (pinned) buffers, H2D of x and D2H of U, grad, dsyn, flag inside the timed region
+    xh = [torch.from_numpy(x).pin_memory() for x in Xs]
+    Uh = torch.empty(B, dtype=torch.float64).pin_memory()
+    Gh = torch.empty(B, 2 * N_LAYERS, dtype=torch.float64).pin_memory()
+    Dh = torch.empty(B, nd, dtype=torch.float64).pin_memory()
+    Fh = torch.empty(B, dtype=torch.uint8).pin_memory()
+    xin = torch.empty(B, 2 * N_LAYERS, dtype=torch.float64, device=dev)
+
+    def step_e2e(i):
+        xin.copy_(xh[i % nrot], non_blocking=True)
+        ctx.misfit_grad_dev(B, xin.data_ptr(), 0, U.data_ptr(), G.data_ptr(), D.data_ptr(), Fl.data_ptr(),
+                            stream.cuda_stream)
+        Uh.copy_(U, non_blocking=True)
+        Gh.copy_(G, non_blocking=True)
+        Dh.copy_(D, non_blocking=True)
+        Fh.copy_(Fl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(Uh[0])
+
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # max over ranks
+    tt = torch.tensor([ms, t_e2e * 1e3, ms_noflush], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, ms_noflush = [float(v) for v in tt.tolist()]
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (swd_roots_kernel, FP64-pipe bound)
+        share = None
+        prof = os.path.join(ROOT, "profiles", "r01_launch_shares.json")
+        if os.path.exists(prof):
+            try:
+                share = json.load(open(prof)).get("swd_roots_kernel")
+            except Exception:
+                share = None
+        evals_per_launch = nev / max(1, args.steps)
+        flop_per_launch = evals_per_launch * (N_LAYERS - 1) * F_R
+        t_kernel = (ms_noflush * 1e-3) * (share if share else 1.0)
+        achieved = flop_per_launch / t_kernel / 1e12
+        roofline = {"bound": "fp64", "kernel": "swd_roots_kernel", "achieved": achieved, "peak": fp64_peak,
+                    "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                    "note": "peak = DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
+                            "figure); achieved = secular evaluations counted on device x (n-1) layer steps x "
+                            "F_R=375 flop / (step time without flush x ncu share %s)" %
+                            ("%.3f" % share if share else "unknown -> 1.0, lower bound"),
+                    "secular_evals_per_launch": evals_per_launch, "step_ms_no_flush": ms_noflush}
+        tr = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tr):
+            try:
+                roofline["traffic"] = json.load(open(tr)).get("swd_roots_kernel_dram_bytes_per_launch")
+            except Exception:
+                pass
+        cpu = None
+        if not args.no_cpu_baseline:
+            cfg2, _, Xc = workload(4096, 4321)
+            v, done, dtc = cpu_arm(cfg2, dobs, Xc, args.cpu_seconds, ncores)
+            cpu = {"value": v, "unit": "evals/s", "cores": ncores, "kind": "port",
+                   "sample": "%d evaluations of the same workload in %.1f s (oracle restatement, g++ -O3, "
+                             "%d threads)" % (done, dtc, ncores)}
+        out = {"metric": "joint RF+SWD forward+gradient evaluations/s", "value": value, "unit": "evals/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": config, "clocks": sampler.summary(),
+               "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": B * 2 * N_LAYERS * 8,
+                       "d2h_bytes_per_step": B * (1 + 2 * N_LAYERS + nd) * 8 + B},
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+               "failed_models_last_step": n_fail}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

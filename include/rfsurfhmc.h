@@ -120,6 +120,14 @@ int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_i
 /* number of misfit_and_grad evaluations performed by the last rfs_hmc_run */
 long long rfs_hmc_last_evals(rfs_ctx *ctx);
 
+/* ---- measurement helpers (no reference counterpart; used by bench.py) --------------------------
+ * rfs_count_evals(ctx,1) zeroes and enables a device counter of secular-function evaluations
+ * (the algorithmic work of the root-search kernel); rfs_read_evals synchronises and reads it.
+ * rfs_measure_fp64_peak runs a DFMA micro-benchmark: the roofline denominator of the FP64 path. */
+int rfs_count_evals(rfs_ctx *ctx, int enable);
+long long rfs_read_evals(rfs_ctx *ctx);
+int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,7 +68,7 @@ int love_group(const float *thk, const float *vs, const float *rho, int nlayer, 
   int iflsph = sphere ? 1 : 0;
   std::vector<float> vp(nlayer);
   std::vector<double> cp(kmax), uu(nlayer), tt(nlayer), dcdh(nlayer), dcdr(nlayer), dcdb(nlayer);
-  for (int i = 0; i < nlayer; i++) vp[i] = 1.732f * vs[i];
+  for (int i = 0; i < nlayer; i++) vp[i] = (float)(1.732 * (double)vs[i]);  // double literal, float store
   int ierr = surfdisp(thk, vp.data(), vs, rho, nlayer, t, cp.data(), kmax, "Lc", mode, sphere, true);
   if (ierr == 1) return ierr;
   for (int i = 0; i < kmax; i++) {

@@ -80,6 +80,12 @@ def load_library():
                                   _llp, _llp, _dp, _i8p, C.c_longlong]
         L.rfs_hmc_last_evals.restype = C.c_longlong
         L.rfs_hmc_last_evals.argtypes = [_vp]
+        L.rfs_count_evals.restype = C.c_int
+        L.rfs_count_evals.argtypes = [_vp, C.c_int]
+        L.rfs_read_evals.restype = C.c_longlong
+        L.rfs_read_evals.argtypes = [_vp]
+        L.rfs_measure_fp64_peak.restype = C.c_int
+        L.rfs_measure_fp64_peak.argtypes = [_vp, _dp]
         _lib = L
         return _lib
 
@@ -90,7 +96,8 @@ def exported_symbols():
             "rfs_config_swd", "rfs_config_rf", "rfs_config_obs", "rfs_misfit_grad_dev",
             "rfs_misfit_grad_host", "rfs_surf_forward", "rfs_surf_adjoint_kernel",
             "rfs_surf_adjoint_kernel_modes", "rfs_rf_forward", "rfs_rf_kernel", "rfs_rf_kernel_all",
-            "rfs_hmc_run", "rfs_hmc_last_evals"]
+            "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
+            "rfs_measure_fp64_peak"]
 
 
 def _f64(a):
@@ -138,6 +145,17 @@ class Context:
     @property
     def launches(self):
         return int(self.L.rfs_launch_count(self.h))
+
+    def count_evals(self, enable=True):
+        self._ck(self.L.rfs_count_evals(self.h, int(bool(enable))))
+
+    def read_evals(self):
+        return int(self.L.rfs_read_evals(self.h))
+
+    def measure_fp64_peak(self):
+        v = C.c_double(0.0)
+        self._ck(self.L.rfs_measure_fp64_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     # ---- configuration
     def config_swd(self, nlayer, tRc=None, tRg=None, tLc=None, tLg=None, mode=0, sphere=False, stale=True):

@@ -55,6 +55,8 @@ struct rfs_ctx {
   long long hmc_evals = 0;
   Buf h_state, h_rng, h_misc, h_x, h_p, h_out;
   size_t ws_budget = (size_t)24 << 30;  // workspace budget per chunk (bytes)
+  Buf d_counter;                 // [0] secular-function evaluations (algorithmic-work counter)
+  bool count_evals = false;
 };
 
 namespace {
@@ -185,7 +187,8 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const doubl
   if ((rc = ensure(ctx, ctx->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
   LAUNCH(swd_roots_kernel, gridFor(B * P.nseq, 128), 128, 0, st, P, d_swd, B, n, d_periods,
          all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
-         (int *)ctx->w_ierr.p);
+         (int *)ctx->w_ierr.p,
+         ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr);
   if (!want_eigen) return RFS_OK;
   if ((rc = ensure(ctx, ctx->w_ugr, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_kern, sizeof(double) * (size_t)nmo * P.nsolve * 4 * n * B)))
@@ -332,7 +335,7 @@ void rfs_destroy(rfs_ctx *ctx) {
                 &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
                 &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state, &ctx->h_rng,
-                &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out};
+                &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out,  &ctx->d_counter};
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -516,14 +519,19 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
   if (rc) return rc;
   const bool group = (wavetype & 1) != 0;
   const bool want_eigen = want_kernels || group;
+  // libsurf.forward(...,"Lg") goes through _LoveGroup, which replaces vp by 1.732*vs
+  // (surfdisp.cpp:127,132); only the float32 start value of the root search sees it.
+  const bool love_group_vp = (wavetype == 3) && !want_kernels;
   cudaStream_t st = ctx->stream;
   // pack the model block on the host: [SWD_NF][n][B] float32-rounded (src/SWD/main.cpp:9,62)
   std::vector<double> blk((size_t)SWD_NF * n * B);
   const size_t nB = (size_t)n * B;
   for (long long b = 0; b < B; b++)
     for (int m = 0; m < n; m++) {
-      const double d32 = (double)(float)thk[b * n + m], a32 = (double)(float)vp[b * n + m],
-                   b32 = (double)(float)vs[b * n + m], r32 = (double)(float)rho[b * n + m];
+      const double d32 = (double)(float)thk[b * n + m], b32 = (double)(float)vs[b * n + m],
+                   r32 = (double)(float)rho[b * n + m];
+      const double a32 = love_group_vp ? (double)(float)(1.732 * (double)(float)vs[b * n + m])
+                                       : (double)(float)vp[b * n + m];
       blk[F_D * nB + (size_t)m * B + b] = d32;
       blk[F_A * nB + (size_t)m * B + b] = a32;
       blk[F_B * nB + (size_t)m * B + b] = b32;
@@ -726,6 +734,73 @@ int rfs_rf_kernel_all(rfs_ctx *ctx, long long B, int n, const double *thk, const
                       double water, int rf_type, double *rf, double *drf) {
   return rf_common(ctx, B, n, thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method,
                    water, rf_type, 0, 4, rf, drf);
+}
+
+
+// ---- measurement helpers (bench.py) ---------------------------------------------------------
+int rfs_count_evals(rfs_ctx *ctx, int enable) {
+  if (!ctx) return RFS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure(ctx, ctx->d_counter, 64);
+  if (rc) return rc;
+  CK(cudaMemset(ctx->d_counter.p, 0, 64));
+  ctx->count_evals = enable != 0;
+  return RFS_OK;
+}
+long long rfs_read_evals(rfs_ctx *ctx) {
+  if (!ctx || !ctx->d_counter.p) return -1;
+  unsigned long long v = 0;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(&v, ctx->d_counter.p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (long long)v;
+}
+
+__global__ void dfma_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c);
+    a1 = fma(a1, m, c);
+    a2 = fma(a2, m, c);
+    a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c);
+    a5 = fma(a5, m, c);
+    a6 = fma(a6, m, c);
+    a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// Measured FP64 FMA peak of this GPU in TFLOP/s (1 FMA = 2 flop): the roofline denominator for
+// the FP64-pipe-bound kernels (MEASURED_PEAKS.json carries no FP64 figure).
+int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return RFS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  int rc = ensure(ctx, ctx->io_a, sizeof(double) * (size_t)blocks * threads);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CK(cudaEventRecord(e0, ctx->stream));
+    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double *)ctx->io_a.p, iters);
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return RFS_OK;
 }
 
 }  // extern "C"

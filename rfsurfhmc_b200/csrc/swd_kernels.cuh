@@ -101,15 +101,22 @@ __global__ void __launch_bounds__(128)
     swd_roots_kernel(SwdPlan plan, const double *__restrict__ swd, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
-                     int *__restrict__ ierr) {
+                     int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= B * plan.nseq) return;
   const long long b = i % B;
   const int s = (int)(i / B);
   SwdModel M{swd, B, n};
+  unsigned int nev = 0;
   const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                   (long long)plan.nsolve * B, cwork, B);
+                                   (long long)plan.nsolve * B, cwork, B, nev);
   ierr[(long long)s * B + b] = e;
+  if (neval_total) {
+    // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
+    unsigned int w = nev;
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(__activemask(), w, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
+  }
 }
 
 // ---- K2: one thread per (model, solve=(sequence,period)[, mode])

@@ -233,7 +233,8 @@ enum { PH_START = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE };
 RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &sq,
                                   const double *__restrict__ periods, int nmode, int all_modes,
                                   double *__restrict__ cout, long long cout_mode_stride,
-                                  double *__restrict__ cwork, long long stride) {
+                                  double *__restrict__ cwork, long long stride,
+                                  unsigned int &n_evals) {
   const int mmax = M.n;
   const int ifunc = sq.ifunc;
   const int kmax = sq.nper;
@@ -319,6 +320,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
         int iret = 0;  // 0 running, 1 ok, -1 fail
         while (iret == 0) {
           const double wv = omega / ceval;
+          n_evals++;
           const double val = (ifunc == 1) ? dltar1_dev(wv, omega, M, b, llw)
                                           : dltar4_dev(wv, omega, M, b, llw);
           bool body = false;
