@@ -5,7 +5,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librfsurf_b200.so")
+LIB_PATH = os.environ.get("RFS_LIB") or os.path.join(_HERE, "lib", "librfsurf_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_ubyte)

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -32,6 +33,9 @@ struct rfs_ctx {
   std::string err;
   long long launches = 0;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
+  cudaStream_t stream2 = nullptr; // RF branch of the joint evaluation runs concurrently with SWD
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = true;
   // ---- SWD configuration
   bool has_swd = false;
   int n_swd = 0, mode = 0, stale = 1;
@@ -319,10 +323,14 @@ int rfs_create(rfs_ctx **out, int device) {
   if (cudaSetDevice(device) != cudaSuccess) return RFS_E_CUDA;
   rfs_ctx *ctx = new rfs_ctx();
   ctx->device = device;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return RFS_E_CUDA;
   }
+  if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
   *out = ctx;
   return RFS_OK;
 }
@@ -339,6 +347,9 @@ void rfs_destroy(rfs_ctx *ctx) {
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 
@@ -427,17 +438,26 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
            use_swd ? (double *)ctx->w_swd.p : nullptr, use_rf ? (double *)ctx->w_rfm.p : nullptr,
            (double *)ctx->w_chain.p);
     if (use_rf) {
+      // the RF branch is independent of the SWD branch: run it on a second stream so that its
+      // kernels fill the SMs the (latency-bound, < 1 wave) root-search kernel leaves idle
+      cudaStream_t sr = st;
+      if (use_swd && ctx->overlap) {
+        sr = ctx->stream2;
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(sr, ctx->ev_fork, 0));
+      }
       if ((rc = run_rf_spectra(ctx, (const double *)ctx->w_rfm.p, (const double *)ctx->w_chain.p,
-                               nullptr, nullptr, Bc, n, 2, sigma, st)))
+                               nullptr, nullptr, Bc, n, 2, sigma, sr)))
         return rc;
       if ((rc = ensure(ctx, ctx->w_urf, sizeof(double) * Bc))) return rc;
       if ((rc = ensure(ctx, ctx->w_grf, sizeof(double) * 2 * nB))) return rc;
       double *Uo = (which == 1) ? U + off : (double *)ctx->w_urf.p;
       double *go = (which == 1) ? grad + off * 2 * n : (double *)ctx->w_grf.p;
       if ((rc = run_rf_decon(ctx, Bc, 2 * n, d_dobs, dsyn + off * ndata, ndata, Uo, go, sigma,
-                             tshift, st)))
+                             tshift, sr)))
         return rc;
-      if (which == 1) CK(cudaMemsetAsync(flag + off, 1, Bc, st));
+      if (which == 1) CK(cudaMemsetAsync(flag + off, 1, Bc, sr));
+      if (sr != st) CK(cudaEventRecord(ctx->ev_join, sr));
     }
     if (use_swd) {
       if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p,
@@ -450,6 +470,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       V.periods = (const double *)ctx->d_periods.p;
       V.B = Bc;
       V.n = n;
+      if (use_rf && ctx->overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
       LAUNCH(joint_assemble_kernel, gridFor(Bc * n, 128), 128, 0, st, ctx->plan, V,
              (const int *)ctx->w_ierr.p, (const double *)ctx->w_chain.p, ctx->stale, which, n1,
              d_dobs, (const double *)ctx->w_urf.p, (const double *)ctx->w_grf.p, wt, U + off,

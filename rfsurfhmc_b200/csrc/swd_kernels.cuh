@@ -97,7 +97,10 @@ __global__ void pack_swd_kernel(const double *__restrict__ thk, const double *__
 // ---- K1: one thread per (model, sequence)
 // croot : [nmode_out][nsolve][B]   cwork : [nsolve][B] (only touched when nmode > 1)
 // ierr  : [nseq][B] int
-__global__ void __launch_bounds__(128)
+#ifndef RFS_ROOTS_MINBLOCKS
+#define RFS_ROOTS_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, RFS_ROOTS_MINBLOCKS)
     swd_roots_kernel(SwdPlan plan, const double *__restrict__ swd, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,

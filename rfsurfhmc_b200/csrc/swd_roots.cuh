@@ -74,17 +74,24 @@ RFS_DEVINL double dltar1_dev(double wvno, double omega, const SwdModel &M, long 
   return e1;
 }
 
-// hyperbolic / circular layer functions of surfdisp96.f `var` (:894-1011) for one wave type
+// hyperbolic / circular layer functions of surfdisp96.f `var` (:894-1011) for one wave type.
+// x2 = (wvno+xk)*|wvno-xk| = r^2.  Division-free: r = x2*rsqrt(x2), 1/r = rsqrt(x2); the
+// evanescent branch returns e = exp(-r d) so that exp(-2 r d) = e*e and a0 = e_p*e_q need no
+// further exponentials (<= 2 ulp away from the reference's expressions).
 struct VarHalf {
-  double c, w, x, ex;  // cos-like, sin/r, (+-)r*sin, exponent
+  double c, w, x, ex, e;  // cos-like, sin/r, (+-)r*sin, exponent, exp(-ex)
 };
-RFS_DEVINL VarHalf var_half(double wvno, double xk, double r, double pq, double dpth) {
+RFS_DEVINL VarHalf var_half(double wvno, double xk, double x2, double dpth) {
   VarHalf o;
+  const double ri = (x2 > 0.0) ? rsqrt(x2) : 0.0;
+  const double r = x2 * ri;
+  const double pq = r * dpth;
   o.ex = 0.0;
+  o.e = 1.0;
   if (wvno < xk) {
     double s;
     sincos(pq, &s, &o.c);
-    o.w = s / r;
+    o.w = s * ri;
     o.x = -r * s;
   } else if (wvno == xk) {
     o.c = 1.0;
@@ -92,30 +99,36 @@ RFS_DEVINL VarHalf var_half(double wvno, double xk, double r, double pq, double 
     o.x = 0.0;
   } else {
     o.ex = pq;
-    double fac = 0.0;
-    if (pq < 16.0) fac = exp(-2.0 * pq);
+    o.e = exp(-pq);
+    const double fac = (pq < 16.0) ? o.e * o.e : 0.0;
     o.c = (1.0 + fac) * 0.5;
     const double s = (1.0 - fac) * 0.5;
-    o.w = s / r;
+    o.w = s * ri;
     o.x = r * s;
   }
   return o;
 }
 
-// ---- Rayleigh secular function: Dunkin 5-vector compound matrix (surfdisp96.f:791-891)
-RFS_DEVINL double dltar4_dev(double wvno, double omga, const SwdModel &M, long long b, int llw) {
+// ---- Rayleigh secular function: Dunkin 5-vector compound matrix (surfdisp96.f:791-891).
+// iom = 1/omega (hoisted per period); per-layer reciprocals 1/a, 1/b, 1/rho come from the model
+// block.  Same formulas as dltar4/var/dnka/normc; divisions replaced by reciprocal multiplies.
+RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const SwdModel &M,
+                             long long b, int llw) {
   const int mmax = M.n;
-  double omega = omga;
-  if (omega < 1.0e-4) omega = 1.0e-4;
+  double omega = omga, iom = iomga;
+  if (omega < 1.0e-4) {
+    omega = 1.0e-4;
+    iom = 1.0e4;
+  }
   const double wvno2 = wvno * wvno;
   double e0, e1, e2, e3, e4;
   {
-    const double am = M.ld(F_A, mmax - 1, b), bm = M.ld(F_B, mmax - 1, b);
+    const double bm = M.ld(F_B, mmax - 1, b);
     const double rho1 = M.ld(F_RHO, mmax - 1, b);
-    const double xka = omega / am, xkb = omega / bm;
+    const double xka = omega * M.ld(F_IA, mmax - 1, b), xkb = omega * M.ld(F_IB, mmax - 1, b);
     const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
     const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const double t = bm / omega;
+    const double t = bm * iom;
     const double gammk = 2.0 * t * t;
     const double gam = gammk * wvno2;
     const double gamm1 = gam - 1.0;
@@ -126,29 +139,26 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, const SwdModel &M, long l
     e4 = wvno2 - ra * rb;
   }
   for (int m = mmax - 2; m >= llw - 1; m--) {
-    const double am = M.ld(F_A, m, b), bm = M.ld(F_B, m, b);
-    const double dpth = M.ld(F_D, m, b), rho = M.ld(F_RHO, m, b);
-    const double xka = omega / am, xkb = omega / bm;
-    const double t = bm / omega;
+    const double bm = M.ld(F_B, m, b);
+    const double dpth = M.ld(F_D, m, b), rho = M.ld(F_RHO, m, b), irho = M.ld(F_IRHO, m, b);
+    const double xka = omega * M.ld(F_IA, m, b), xkb = omega * M.ld(F_IB, m, b);
+    const double t = bm * iom;
     const double gammk = 2.0 * t * t;
     const double gam = gammk * wvno2;
-    const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-    const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const VarHalf P = var_half(wvno, xka, ra, ra * dpth, dpth);
-    const VarHalf S = var_half(wvno, xkb, rb, rb * dpth, dpth);
+    const VarHalf P = var_half(wvno, xka, (wvno + xka) * fabs(wvno - xka), dpth);
+    const VarHalf S = var_half(wvno, xkb, (wvno + xkb) * fabs(wvno - xkb), dpth);
     const double exa = P.ex + S.ex;
-    double a0 = 0.0;
-    if (exa < 60.0) a0 = exp(-exa);
+    const double a0 = (exa < 60.0) ? P.e * S.e : 0.0;
     const double cpcq = P.c * S.c, cpy = P.c * S.w, cpz = P.c * S.x, cqw = S.c * P.w,
                  cqx = S.c * P.x, xy = P.x * S.w, xz = P.x * S.x, wy = P.w * S.w, wz = P.w * S.x;
     // Dunkin matrix (dnka :1044-1088), unique entries only
     const double gamm1 = gam - 1.0, twgm1 = gam + gamm1, gmgmk = gam * gammk, gmgm1 = gam * gamm1,
-                 gm1sq = gamm1 * gamm1, rho2 = rho * rho, a0pq = a0 - cpcq;
+                 gm1sq = gamm1 * gamm1, rho2 = rho * rho, irho2 = irho * irho, a0pq = a0 - cpcq;
     const double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
-    const double c12 = (wvno2 * cpy - cqx) / rho;
-    const double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) / rho;
-    const double c14 = (cpz - wvno2 * cqw) / rho;
-    const double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) / rho2;
+    const double c12 = (wvno2 * cpy - cqx) * irho;
+    const double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * irho;
+    const double c14 = (cpz - wvno2 * cqw) * irho;
+    const double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * irho2;
     const double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
     const double c22 = cpcq;
     const double c23 = gammk * cpz - gamm1 * cqw;
@@ -164,26 +174,26 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, const SwdModel &M, long l
     const double c31 = tt * c53, c32 = tt * c43, c33 = a0 + 2.0 * (cpcq - c11), c34 = tt * c23,
                  c35 = tt * c13;
     // ee(i) = sum_j e(j) ca(j,i), with ca(2,5)=c14 ca(4,4)=c22 ca(4,5)=c12 ca(5,2)=c41
-    // ca(5,4)=c21 ca(5,5)=c11   (same left-to-right summation order as the reference)
-    double n0 = e0 * c11 + e1 * c21 + e2 * c31 + e3 * c41 + e4 * c51;
-    double n1 = e0 * c12 + e1 * c22 + e2 * c32 + e3 * c42 + e4 * c41;
-    double n2 = e0 * c13 + e1 * c23 + e2 * c33 + e3 * c43 + e4 * c53;
-    double n3 = e0 * c14 + e1 * c24 + e2 * c34 + e3 * c22 + e4 * c21;
-    double n4 = e0 * c15 + e1 * c14 + e2 * c35 + e3 * c12 + e4 * c11;
+    // ca(5,4)=c21 ca(5,5)=c11; two partial sums per component shorten the dependent chain
+    const double n0 = (e0 * c11 + e1 * c21) + (e2 * c31 + e3 * c41) + e4 * c51;
+    const double n1 = (e0 * c12 + e1 * c22) + (e2 * c32 + e3 * c42) + e4 * c41;
+    const double n2 = (e0 * c13 + e1 * c23) + (e2 * c33 + e3 * c43) + e4 * c53;
+    const double n3 = (e0 * c14 + e1 * c24) + (e2 * c34 + e3 * c22) + e4 * c21;
+    const double n4 = (e0 * c15 + e1 * c14) + (e2 * c35 + e3 * c12) + e4 * c11;
     double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
     if (t1 < 1.e-40) t1 = 1.0;
-    e0 = n0 / t1;
-    e1 = n1 / t1;
-    e2 = n2 / t1;
-    e3 = n3 / t1;
-    e4 = n4 / t1;
+    const double it1 = 1.0 / t1;
+    e0 = n0 * it1;
+    e1 = n1 * it1;
+    e2 = n2 * it1;
+    e3 = n3 * it1;
+    e4 = n4 * it1;
   }
   if (llw != 1) {
     // water layer on top (surfdisp96.f:870-886)
-    const double am = M.ld(F_A, 0, b), dpth = M.ld(F_D, 0, b), rho1 = M.ld(F_RHO, 0, b);
-    const double xka = omega / am;
-    const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-    const VarHalf P = var_half(wvno, xka, ra, ra * dpth, dpth);
+    const double dpth = M.ld(F_D, 0, b), rho1 = M.ld(F_RHO, 0, b);
+    const double xka = omega * M.ld(F_IA, 0, b);
+    const VarHalf P = var_half(wvno, xka, (wvno + xka) * fabs(wvno - xka), dpth);
     const double w0 = -rho1 * P.w;
     return P.c * e0 + w0 * e1;
   }
@@ -224,12 +234,16 @@ RFS_DEVINL float gtsolh_dev(float a, float b) {
 }
 
 // phases of the flattened getsol/nevill state machine
-enum { PH_START = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE };
+enum { PH_SETUP = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE, PH_DONE };
 
 // Solve all modes 1..nmode of sequence `sq` for model b.
 //  cout  : [nmode_out][nper][stride] float32-rounded roots (0 where a mode does not exist)
-//  cwork : [nper][stride] unrounded roots of the running mode (chain state), may alias nothing
+//  cwork : [nper][stride] unrounded roots of the running mode (chain state), used when nmode > 1
 // returns ierr (1 = fundamental mode not found, even after the per-period retry).
+//
+// The job loop (main pass + per-period retries of surfdisp.cpp:93-100), the mode loop, the period
+// loop, getsol and nevill are ONE loop whose body performs exactly one secular evaluation:
+// lanes never wait for each other at period or mode boundaries.
 RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &sq,
                                   const double *__restrict__ periods, int nmode, int all_modes,
                                   double *__restrict__ cout, long long cout_mode_stride,
@@ -269,30 +283,81 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
   const double betmxd = (double)betmx;
   const double twopi = 2.0 * RFS_PI64;
 
+  // ---- loop-nest state (job / mode / period)
   int ierr = 0;
-  // job 0: the whole sequence; jobs 1.. : per-period retries (surfdisp.cpp:93-100)
-  int kb = 0, ke = kmax;  // [kb,ke) periods of the current job
-  int retry_k = -1;
+  int kb = 0, jk = kmax;  // current job covers periods [kb, kb+jk)
+  int retry_k = -1;       // <0: main pass; else next period index to examine for a retry
+  int iq = 1, k = 0, ift = 999, job_ierr = 0;
+  double cprev = 0.0, del1st = 0.0;
+  // ---- root-search state (getsol / nevill)
+  double c1 = 0.0, c2 = 0.0, clow = 0.0, del1 = 0.0, del2 = 0.0, c3 = 0.0, del3 = 0.0, omega = 0.0,
+         iomega = 0.0;
+  double xs[12], ys[12];
+  int idir = 1, nev = 1, nctrl = 1, mm = 1, ifirst = 0;
+  int phase = PH_SETUP;
+  double ceval = 0.0;
+
   for (;;) {
-    const int jk = ke - kb;  // kmax of this job
-    int ift = 999;
-    int job_ierr = 0;
-    double del1st = 0.0;
-    for (int iq = 1; iq <= nmode; iq++) {
-      double *cq = cout + (all_modes ? (long long)(iq - 1) * cout_mode_stride : 0);
-      int k = 0;
-      bool failed = false;
-      double cprev = 0.0;  // c(k-1) of the present mode
-      for (k = 0; k < jk; k++) {
-        if (k + 1 >= ift) {
-          failed = true;
-          break;
+    if (phase == PH_SETUP) {
+      // ---- advance the (job, mode, period) nest until a root search starts or all is done
+      for (;;) {
+        if (iq <= nmode && k < jk && (k + 1 >= ift)) {
+          // label 1700/1750 reached through `if(k.ge.ift)`: this mode is cut off from k on
+          double *cq = cout + (all_modes ? (long long)(iq - 1) * cout_mode_stride : 0);
+          if (iq <= 1) job_ierr = 1;
+          ift = k + 1;
+          for (int i = k; i < jk; i++) cq[(long long)(sq.out_off + kb + i) * stride + b] = 0.0;
+          iq++;
+          k = 0;
+          continue;
         }
+        if (iq <= nmode && k >= jk) {  // mode finished normally
+          iq++;
+          k = 0;
+          continue;
+        }
+        if (iq > nmode) {
+          // ---- job finished: emulate _surfdisp's retry of zero periods when ierr != 0
+          bool stop = false;
+          if (retry_k < 0) {
+            if (job_ierr == 0) {
+              stop = true;
+            } else {
+              ierr = 1;
+              retry_k = 0;
+            }
+          } else {
+            ierr = job_ierr;
+            if (job_ierr != 0) stop = true;  // `if(ierr !=0) return ierr;`
+          }
+          int kn = -1;
+          if (!stop) {
+            const double *clast = cout + (all_modes ? (long long)(nmode - 1) * cout_mode_stride : 0);
+            for (int i = retry_k; i < kmax; i++) {
+              const double v = clast[(long long)(sq.out_off + i) * stride + b];
+              if (v == 0.0 || isnan(v)) {
+                kn = i;
+                break;
+              }
+            }
+          }
+          if (stop || kn < 0) {
+            phase = PH_DONE;
+            break;
+          }
+          kb = kn;
+          jk = 1;
+          retry_k = kn + 1;
+          iq = 1;
+          k = 0;
+          ift = 999;
+          job_ierr = 0;
+          continue;
+        }
+        // ---- start values of (iq, k) (surfdisp96.f:257-276)
         const double t1 = __ldg(periods + sq.per_off + kb + k) * sq.scale;
-        const double omega = twopi / t1;
-        // ---- start values (surfdisp96.f:257-276)
-        double c1, clow;
-        int ifirst;
+        omega = twopi / t1;
+        iomega = 1.0 / omega;
         if (k == 0 && iq == 1) {
           c1 = cc;
           clow = cc;
@@ -311,179 +376,156 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
           c1 = cprev - onea * dc;
           clow = cm;
         }
-        // ---- flattened getsol + nevill: one secular evaluation per loop trip
-        double c2 = 0.0, del1 = 0.0, del2 = 0.0, c3 = 0.0, del3 = 0.0;
-        double xs[12], ys[12];
-        int idir = 1, nev = 1, nctrl = 1, mm = 1;
-        int phase = PH_G_FIRST;
-        double ceval = c1;
-        int iret = 0;  // 0 running, 1 ok, -1 fail
-        while (iret == 0) {
-          const double wv = omega / ceval;
-          n_evals++;
-          const double val = (ifunc == 1) ? dltar1_dev(wv, omega, M, b, llw)
-                                          : dltar4_dev(wv, omega, M, b, llw);
-          bool body = false;
-          if (phase == PH_G_FIRST) {
-            del1 = val;
-            if (ifirst == 1) del1st = del1;
-            const double plmn = sgn1(del1st) * sgn1(del1);
-            idir = (ifirst == 1 || plmn >= 0.0) ? +1 : -1;
-            // first c2 (label 1000, :457-470)
-            for (;;) {
-              c2 = (idir > 0) ? c1 + dc : c1 - dc;
-              if (c2 <= clow) {
-                idir = +1;
-                c1 = clow;
-                continue;
-              }
+        ceval = c1;
+        phase = PH_G_FIRST;
+        break;
+      }
+      if (phase == PH_DONE) break;
+    }
+
+    // ---- the single secular-function evaluation site
+    const double wv = omega / ceval;
+    n_evals++;
+    const double val =
+        (ifunc == 1) ? dltar1_dev(wv, omega, M, b, llw) : dltar4_dev(wv, omega, iomega, M, b, llw);
+
+    int iret = 0;  // 0 running, 1 root accepted, -1 failed
+    bool body = false;
+    if (phase == PH_G_FIRST) {
+      del1 = val;
+      if (ifirst == 1) del1st = del1;
+      const double plmn = sgn1(del1st) * sgn1(del1);
+      idir = (ifirst == 1 || plmn >= 0.0) ? +1 : -1;
+      for (;;) {  // label 1000 (:457-470)
+        c2 = (idir > 0) ? c1 + dc : c1 - dc;
+        if (c2 <= clow) {
+          idir = +1;
+          c1 = clow;
+          continue;
+        }
+        break;
+      }
+      ceval = c2;
+      phase = PH_G_SCAN;
+    } else if (phase == PH_G_SCAN) {
+      del2 = val;
+      if (sgn1(del1) != sgn1(del2)) {
+        c3 = 0.5 * (c1 + c2);  // bracketed -> nevill: initial half
+        ceval = c3;
+        nev = 1;
+        nctrl = 1;
+        phase = PH_N_TOP;
+      } else {
+        c1 = c2;
+        del1 = del2;
+        if (c1 < cm || c1 >= (betmxd + dc)) {
+          iret = -1;
+        } else {
+          for (;;) {
+            c2 = (idir > 0) ? c1 + dc : c1 - dc;
+            if (c2 <= clow) {
+              idir = +1;
+              c1 = clow;
+              continue;
+            }
+            break;
+          }
+          ceval = c2;
+        }
+      }
+    } else if (phase == PH_N_TOP) {
+      del3 = val;
+      nctrl = nctrl + 1;
+      if (nctrl >= 100) {
+        iret = 2;  // nevill exit by iteration cap -> cc = c3
+      } else if (c3 < fmin(c1, c2) || c3 > fmax(c1, c2)) {
+        nev = 0;
+        c3 = 0.5 * (c1 + c2);
+        ceval = c3;
+        phase = PH_N_OUTSIDE;
+      } else {
+        body = true;
+      }
+    } else {  // PH_N_OUTSIDE
+      del3 = val;
+      body = true;
+    }
+    if (body) {
+      const double s13 = del1 - del3;
+      const double s32 = del3 - del2;
+      if (sgn1(del3) * sgn1(del1) < 0.0) {
+        c2 = c3;
+        del2 = del3;
+      } else {
+        c1 = c3;
+        del1 = del3;
+      }
+      if (fabs(c1 - c2) <= 1.e-6 * c1) {
+        iret = 2;
+      } else {
+        if (sgn1(s13) != sgn1(s32)) nev = 0;
+        const double ss1 = fabs(del1), ss2 = fabs(del2);
+        const double s1 = (double)0.01f * ss1, s2 = (double)0.01f * ss2;
+        bool do_half = (s1 > ss2 || s2 > ss1 || nev == 0);
+        if (!do_half) {
+          if (nev == 2) {
+            xs[mm] = c3;
+            ys[mm] = del3;
+          } else {
+            xs[0] = c1;
+            ys[0] = del1;
+            xs[1] = c2;
+            ys[1] = del2;
+            mm = 1;
+          }
+          bool bad = false;
+          for (int kk = 1; kk <= mm; kk++) {
+            const int j = mm - kk;  // 0-based index of x(j)
+            const double denom = ys[mm] - ys[j];
+            if (fabs(denom) < 1.0e-10 * fabs(ys[mm])) {
+              bad = true;
               break;
             }
-            ceval = c2;
-            phase = PH_G_SCAN;
-          } else if (phase == PH_G_SCAN) {
-            del2 = val;
-            if (sgn1(del1) != sgn1(del2)) {
-              // bracketed -> nevill: initial half
-              c3 = 0.5 * (c1 + c2);
-              ceval = c3;
-              nev = 1;
-              nctrl = 1;
-              phase = PH_N_TOP;
-            } else {
-              c1 = c2;
-              del1 = del2;
-              if (c1 < cm || c1 >= (betmxd + dc)) {
-                iret = -1;
-              } else {
-                for (;;) {
-                  c2 = (idir > 0) ? c1 + dc : c1 - dc;
-                  if (c2 <= clow) {
-                    idir = +1;
-                    c1 = clow;
-                    continue;
-                  }
-                  break;
-                }
-                ceval = c2;
-              }
-            }
-          } else if (phase == PH_N_TOP) {
-            del3 = val;
-            nctrl = nctrl + 1;
-            if (nctrl >= 100) {
-              iret = 2;  // nevill exit by iteration cap -> cc = c3
-            } else if (c3 < fmin(c1, c2) || c3 > fmax(c1, c2)) {
-              nev = 0;
-              c3 = 0.5 * (c1 + c2);
-              ceval = c3;
-              phase = PH_N_OUTSIDE;
-            } else {
-              body = true;
-            }
-          } else {  // PH_N_OUTSIDE
-            del3 = val;
-            body = true;
+            xs[j] = (-ys[j] * xs[j + 1] + ys[mm] * xs[j]) / denom;
           }
-          if (body) {
-            const double s13 = del1 - del3;
-            const double s32 = del3 - del2;
-            if (sgn1(del3) * sgn1(del1) < 0.0) {
-              c2 = c3;
-              del2 = del3;
-            } else {
-              c1 = c3;
-              del1 = del3;
-            }
-            if (fabs(c1 - c2) <= 1.e-6 * c1) {
-              iret = 2;
-            } else {
-              if (sgn1(s13) != sgn1(s32)) nev = 0;
-              const double ss1 = fabs(del1), ss2 = fabs(del2);
-              const double s1 = (double)0.01f * ss1, s2 = (double)0.01f * ss2;
-              bool do_half = (s1 > ss2 || s2 > ss1 || nev == 0);
-              if (!do_half) {
-                if (nev == 2) {
-                  xs[mm] = c3;
-                  ys[mm] = del3;
-                } else {
-                  xs[0] = c1;
-                  ys[0] = del1;
-                  xs[1] = c2;
-                  ys[1] = del2;
-                  mm = 1;
-                }
-                bool bad = false;
-                for (int kk = 1; kk <= mm; kk++) {
-                  const int j = mm - kk;  // 0-based index of x(j)
-                  const double denom = ys[mm] - ys[j];
-                  if (fabs(denom) < 1.0e-10 * fabs(ys[mm])) {
-                    bad = true;
-                    break;
-                  }
-                  xs[j] = (-ys[j] * xs[j + 1] + ys[mm] * xs[j]) / denom;
-                }
-                if (!bad) {
-                  c3 = xs[0];
-                  nev = 2;
-                  mm = mm + 1;
-                  if (mm > 10) mm = 10;
-                } else {
-                  do_half = true;
-                }
-              }
-              if (do_half) {
-                c3 = 0.5 * (c1 + c2);
-                nev = 1;
-                mm = 1;
-              }
-              ceval = c3;
-              phase = PH_N_TOP;
-            }
+          if (!bad) {
+            c3 = xs[0];
+            nev = 2;
+            mm = mm + 1;
+            if (mm > 10) mm = 10;
+          } else {
+            do_half = true;
           }
         }
-        if (iret == 2) {
-          // back in getsol (:483-487)
-          c1 = c3;
-          iret = (c1 > betmxd) ? -1 : 1;
+        if (do_half) {
+          c3 = 0.5 * (c1 + c2);
+          nev = 1;
+          mm = 1;
         }
-        if (iret == -1) {
-          failed = true;
-          break;
-        }
-        cprev = c1;
-        if (nmode > 1) cwork[(long long)(kb + k) * stride + b] = c1;
-        cq[(long long)(sq.out_off + kb + k) * stride + b] = (double)(float)c1;  // cg(k)=sngl(c(k))
+        ceval = c3;
+        phase = PH_N_TOP;
       }
-      if (!failed) continue;
+    }
+    if (iret == 2) {
+      c1 = c3;  // back in getsol (:483-487)
+      iret = (c1 > betmxd) ? -1 : 1;
+    }
+    if (iret == 1) {
+      double *cq = cout + (all_modes ? (long long)(iq - 1) * cout_mode_stride : 0);
+      cprev = c1;
+      if (nmode > 1) cwork[(long long)(kb + k) * stride + b] = c1;
+      cq[(long long)(sq.out_off + kb + k) * stride + b] = (double)(float)c1;  // cg(k)=sngl(c(k))
+      k++;
+      phase = PH_SETUP;
+    } else if (iret == -1) {
+      double *cq = cout + (all_modes ? (long long)(iq - 1) * cout_mode_stride : 0);
       if (iq <= 1) job_ierr = 1;
       ift = k + 1;
       for (int i = k; i < jk; i++) cq[(long long)(sq.out_off + kb + i) * stride + b] = 0.0;
+      iq++;
+      k = 0;
+      phase = PH_SETUP;
     }
-    // ---- job bookkeeping: emulate _surfdisp's retry of zero periods when ierr != 0
-    if (retry_k < 0) {
-      if (job_ierr == 0) break;  // main pass fine (missing higher modes are zeros with ierr 0)
-      ierr = 1;
-      retry_k = 0;
-    } else {
-      // we just retried period retry_k-1 as a single-period job
-      ierr = job_ierr;
-      if (job_ierr != 0) break;  // `if(ierr !=0) return ierr;`
-    }
-    // find next period whose (last-mode) output is zero / NaN
-    const double *clast = cout + (all_modes ? (long long)(nmode - 1) * cout_mode_stride : 0);
-    int kn = -1;
-    for (int i = retry_k; i < kmax; i++) {
-      const double v = clast[(long long)(sq.out_off + i) * stride + b];
-      if (v == 0.0 || isnan(v)) {
-        kn = i;
-        break;
-      }
-    }
-    if (kn < 0) break;
-    kb = kn;
-    ke = kn + 1;
-    retry_k = kn + 1;
   }
   return ierr;
 }
