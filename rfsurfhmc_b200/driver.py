@@ -1,0 +1,83 @@
+"""Drivers with the behaviour of /root/reference/main_base.py:14-93 and main_DA.py:12-91:
+read param.yaml, synthesise observations from `true_model`, build the search box, run the chains,
+write `real_syn.npy`, per-chain result files and `misfit.npy [nchains, nsamples]`.
+
+    python -m rfsurfhmc_b200.driver --param param.yaml --sampler base --chains 4
+    torchrun --nproc-per-node 8 -m rfsurfhmc_b200.driver --sampler da --chains 16384
+
+`mpiexec -n N` of the reference becomes `--chains N`: all chains of a rank run at once on its GPU."""
+import argparse
+import os
+import time
+import numpy as np
+import yaml
+
+from .model.model_rf import ReceiverFunc
+from .model.model_surf import SurfWD
+from .model.model_rf_swd_vs_thk import Joint_RF_SWD
+from .pyhmc.hmc import HamitonianMC
+from .pyhmc.hmcda import HMCDualAveraging
+from .fixtures import driver_bounds
+from . import distributed as D
+
+
+def run(param, sampler="base", nchains=4, save_chains=True):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if ws > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model_swd = SurfWD.init(**param['swd'])
+    model_rf = ReceiverFunc.init(**param['rf'])
+    thk = np.asarray(param['true_model']['thk'], dtype=np.float64)
+    vs = np.asarray(param['true_model']['vs'], dtype=np.float64)
+    model_swd.set_thk(thk)
+    model_rf.set_thk(thk)
+    model = Joint_RF_SWD(1.0, 1.0, model_rf, model_swd)
+    model.set_device(local)
+    outdir = param['hmc']['OUTPUT_DIR']
+    os.makedirs(outdir, exist_ok=True)
+    x = np.hstack((vs, thk))
+    dobs = np.zeros(model.ndata)
+    if rank == 0:
+        drsyn, dssyn, _ = model.forward(x)
+        dobs[:model.rfmodel.nt] = drsyn
+        dobs[model.rfmodel.nt:] = dssyn
+        np.save(f"{outdir}/real_syn.npy", dobs)
+    dobs = D.bcast_array(dobs)
+    nt = model.rfmodel.nt
+    model.set_obsdata(dobs[:nt], dobs[nt:])
+    boundaries = driver_bounds(x)
+    cls = HamitonianMC if sampler == "base" else HMCDualAveraging
+    chain = cls.init(model, boundaries, 0, **param['hmc'])
+    ids = D.shard_chains(nchains)
+    out = chain.sample_chains(ids, want_syn=save_chains, save=save_chains)
+    misfit = D.gather_chains(out["misfit"], nchains)
+    n_iter = D.gather_chains(out["n_iter"], nchains)
+    if rank == 0:
+        np.save(f"{outdir}/misfit.npy", misfit)
+    return misfit, n_iter, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--param", default="param.yaml")
+    ap.add_argument("--sampler", default="base", choices=["base", "da"])
+    ap.add_argument("--chains", type=int, default=4)
+    ap.add_argument("--no-chain-files", action="store_true")
+    a = ap.parse_args()
+    with open(a.param, "r") as f:
+        param = yaml.safe_load(f)
+    tic = time.time()
+    misfit, n_iter, _ = run(param, a.sampler, a.chains, not a.no_chain_files)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("chains %d, accepted samples %d, mean accept ratio %.3f" %
+              (misfit.shape[0], misfit.size, (misfit.shape[1] + param['hmc']['ndraws']) / n_iter.mean()))
+        print("time elapse: {}".format(time.time() - tic))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,62 @@
+"""HamitonianMC — front end with the constructor / `init` / `sample` surface of
+/root/reference/pyhmc/hmc.py (class HamitonianMC :9-276), backed by the device-resident sampler
+(include/rfsurfhmc.h: rfs_hmc_run, sampler=0).
+
+The leapfrog loop, reflections, Metropolis step and the NumPy-legacy random stream all live in
+hmc_kernels.cuh; chain `myrank` is seeded with `seed + myrank` exactly like one MPI rank of the
+reference (hmc.py:43,61), so `sample()` reproduces that rank's accept/reject sequence, and
+`sample_chains(ids)` runs any number of ranks at once on one GPU."""
+import numpy as np
+from ._common import write_chain_file, best_mean_model, require_device_model
+
+
+class HamitonianMC:
+    def __init__(self, UserDefinedModel, boundaries, dt, Lrange, nbest_model, seed, nsamples, ndraws,
+                 myrank=0, name="mychain", outdir="./"):
+        self.myrank = myrank
+        self.seed = seed + myrank
+        self._base_seed = seed
+        self.boundaries = np.asarray(boundaries, dtype=np.float64)
+        self.Lrange = Lrange
+        self.dt = dt
+        self.model = require_device_model(UserDefinedModel)
+        self.nbest_model = nbest_model
+        self.nsamples = nsamples
+        self.ndraws = ndraws
+        self.name = name
+        self.outdir = outdir
+        self.max_iters = 0
+        self.last = None
+
+    @classmethod
+    def init(self, UserDefinedModel, boundaries, rank, **kargs):
+        return HamitonianMC(UserDefinedModel, boundaries, kargs['dt'], kargs['Lrange'], kargs['nbest'],
+                            kargs['seed'], kargs['nsamples'], kargs['ndraws'], rank, kargs['name'],
+                            kargs['OUTPUT_DIR'])
+
+    def sample_chains(self, chain_ids, want_syn=True, log_accepts=0, save=False):
+        """Run the chains `chain_ids` (the reference's MPI ranks) at once; returns the result dict of
+        Context.hmc_run (misfit [C,nsamples], samples, syn, initmodel, n_iter, n_acc, ...)."""
+        n = self.boundaries.shape[0] // 2
+        ctx = self.model.device_context(n)
+        out = ctx.hmc_run(0, chain_ids, self.boundaries, self.dt, Lrange=self.Lrange, seed=self._base_seed,
+                          nsamples=self.nsamples, ndraws=self.ndraws, max_iters=self.max_iters,
+                          want_samples=True, want_syn=want_syn, log_accepts=log_accepts)
+        if save:
+            for i, cid in enumerate(np.atleast_1d(chain_ids)):
+                self._save(out, i, int(cid))
+        self.last = out
+        return out
+
+    def _save(self, out, i, cid):
+        xmean = best_mean_model(out["misfit"][i], out["samples"][i], self.nbest_model)
+        _, _, dsyn, _ = self.model.misfit_and_grad(xmean)
+        syn = out["syn"][i] if out["syn"] is not None else np.zeros((self.nsamples, 0))
+        write_chain_file(f"{self.outdir}/{self.name}.{cid}.npz", out["initmodel"][i], self.model.dobs,
+                         xmean, dsyn, out["samples"][i], syn)
+
+    def sample(self):
+        """One chain (this rank), as the reference: returns misfit[nsamples] and writes
+        {outdir}/{name}.{myrank}.npz."""
+        out = self.sample_chains([self.myrank], want_syn=True, save=True)
+        return out["misfit"][0]

@@ -1,0 +1,145 @@
+"""Oracle vs committed golden vectors, the C ABI surface, host-side logic (no GPU needed)."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+from oracle.oracle import brocher
+from rfsurfhmc_b200.fixtures import f1_config, f1_true_model, driver_bounds, sorted_uniform_models
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_oracle_reproduces_dropin_golden(oracle):
+    g = np.load(os.path.join(G, "f1_dropin.npz"))
+    thk, vs, vp, rho, T = g["thk"], g["vs"], g["vp"], g["rho"], g["T"]
+    for wt in ("Rc", "Rg", "Lc", "Lg"):
+        for mode in (0, 1, 2):
+            c, ok = oracle.surf_forward(thk, vp, vs, rho, T, wt, mode=mode)
+            assert ok == bool(g[f"fwd_{wt}_{mode}_ok"])
+            assert np.allclose(c, g[f"fwd_{wt}_{mode}"], rtol=1e-12, atol=0, equal_nan=True)
+        r = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, wt)
+        for arr, key in zip(r[:5], ("c", "da", "db", "dr", "dh")):
+            assert np.allclose(arr, g[f"ker_{wt}_{key}"], rtol=1e-10, atol=1e-14)
+    q = thk * 0 + 9999.
+    for rft in ("P", "S"):
+        rf, kl = oracle.rf_kernel_all(thk, rho, vp, vs, q, q, 0.045, 125, 0.4, 1.5, 5.0, "freq", 0.001, rft)
+        assert np.allclose(rf, g[f"rf_{rft}"], rtol=1e-10, atol=1e-13)
+        assert np.allclose(kl, g[f"rf_{rft}_kl"], rtol=1e-9, atol=1e-12)
+
+
+def test_oracle_reproduces_joint_golden(oracle):
+    g = np.load(os.path.join(G, "f1_joint.npz"))
+    U, gr, d, f = oracle.joint_batch(g["X"][:16], g["dobs"], f1_config(), nthreads=4)
+    assert np.array_equal(f, g["flag"][:16])
+    assert np.allclose(U, g["U"][:16], rtol=1e-10)
+    assert np.allclose(gr, g["grad"][:16], rtol=1e-8, atol=1e-10)
+
+
+def test_joint_glue_matches_numpy_restatement(oracle):
+    """Joint_RF_SWD.misfit_and_grad assembled in NumPy from the drop-in calls
+    (model_rf.py:182-193, model_surf.py:175-224, model_rf_swd_vs_thk.py:66-86) == oracle batch glue."""
+    cfg = f1_config()
+    x0 = f1_true_model()
+    _, _, dd, _ = oracle.joint_batch(x0[None, :], np.zeros(197), cfg)
+    dobs = dd[0]
+    x = sorted_uniform_models(driver_bounds(x0), 1, seed=5)[0]
+    vs, thk = x[:7], x[7:]
+    vp, rho = brocher(vs)
+    drda = 1.6612 - 0.4721 * 2 * vp + 0.0671 * 3 * vp**2 - 0.0043 * 4 * vp**3 + 0.000106 * 5 * vp**4
+    dadb = 2.0947 - 0.8206 * 2 * vs + 0.2683 * 3 * vs**2 - 0.0251 * 4 * vs**3
+    q = thk * 0 + 9999.
+    d, kl = oracle.rf_kernel_all(thk, rho, vp, vs, q, q, 0.045, 125, 0.4, 1.5, 5.0, "freq", 0.001, "P")
+    K = kl[2] + dadb[:, None] * kl[1] + (drda * dadb)[:, None] * kl[0]
+    r = d - dobs[:125]
+    g_rf = np.hstack((K @ r, kl[3] @ r))
+    U_rf = 0.5 * np.sum(r**2)
+    ds = np.zeros(72); Kv = np.zeros((72, 7)); Kh = np.zeros((72, 7))
+    for i, wt in enumerate(("Rc", "Rg")):
+        c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(thk, vp, vs, rho, cfg["tRc"], wt)
+        assert ok
+        ds[36 * i:36 * i + 36] = c
+        Kv[36 * i:36 * i + 36] = db + da * dadb + dr * drda * dadb
+        Kh[36 * i:36 * i + 36] = dh
+    rs = ds - dobs[125:]
+    g_sw = np.hstack((rs @ Kv, rs @ Kh))
+    wt = 125 / 72
+    U, g, dsyn, f = oracle.joint_batch(x[None, :], dobs, cfg)
+    assert f[0]
+    assert np.isclose(U[0], U_rf + wt * 0.5 * np.sum(rs**2), rtol=1e-12)
+    assert np.allclose(g[0], g_rf + wt * g_sw, rtol=1e-10, atol=1e-12)
+    assert np.allclose(dsyn[0], np.hstack((d, ds)), rtol=1e-13)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rfsurfhmc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rfs_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    from rfsurfhmc_b200 import _lib
+    assert set(_lib.exported_symbols()) == declared
+    lib = ctypes.CDLL(_lib.LIB_PATH)  # loads without a GPU (no compute calls here)
+    for s in declared:
+        assert hasattr(lib, s), s
+    lib.rfs_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.rfs_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rfsurfhmc_b200._lib import Context, RfsError
+    with pytest.raises(RfsError):
+        Context(0)
+    from rfsurfhmc_b200.model.lib import libsurf
+    with pytest.raises(RfsError):
+        libsurf.forward([1., 0.], [5., 6.], [3., 3.5], [2.5, 2.8], [5.], "Rc")
+    with pytest.raises(ValueError):
+        libsurf.forward([1., 0.], [5., 6.], [3., 3.5], [2.5, 2.8], [5.], "Zz")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "rfsurfhmc_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), os.path.join(dp, f)
+
+
+def test_driver_bounds_and_initial_model_distribution():
+    x0 = f1_true_model()
+    b = driver_bounds(x0)
+    assert b.shape == (14, 2)
+    assert np.all(b[:7, 0] >= 1.5) and np.all(b[:7, 1] <= 5.0)
+    assert tuple(b[-1]) == (0.0, 2.0)
+    assert np.allclose(b[7:13, 0], x0[7:13] * 0.8) and np.allclose(b[7:13, 1], x0[7:13] * 1.2)
+    X = sorted_uniform_models(b, 100, 0)
+    assert np.all(np.diff(X[:, :7], axis=1) >= 0)
+
+
+def test_hmc_reference_restatement_on_quadratic_model():
+    """hmc_ref (the checker of the device sampler) samples a Gaussian correctly and its random
+    stream is NumPy's legacy one (first draws equal np.random after the same seed)."""
+    from oracle import hmc_ref
+    n2 = 4
+    bounds = np.tile(np.array([[-5., 5.]]), (n2, 1))
+    f = lambda x: (0.5 * float(x @ x), x.copy(), np.zeros(3), True)
+    R = hmc_ref.run_base(f, bounds, 0.3, (5, 20), 42, nsamples=400, ndraws=100)
+    assert R.n_acc == 500 and len(R.accepts) == R.n_iter
+    # reference quirk Q9: momenta are drawn with variance 0.25 but K = p.p/2 (unit mass), so the
+    # chain equilibrates at an effective temperature of 0.25 -> sample variance ~0.25, not 1
+    assert 0.15 < np.var(R.samples) < 0.40
+    # the random stream is NumPy's legacy global one: the initial model is built from the first
+    # n2 np.random.rand() draws after np.random.seed(seed)
+    np.random.seed(42)
+    u = np.array([np.random.rand() for _ in range(n2)])
+    x = bounds[:, 0] + 10 * u
+    idx = np.argsort(x[:2])
+    expect = np.hstack((x[:2][idx], x[2:][idx]))
+    assert np.allclose(R.initmodel, expect)
+    R2 = hmc_ref.run_da(f, bounds, 0.1, 10, 0.65, 43, nsamples=300, ndraws=100)
+    assert R2.n_acc == 400
+    assert 0.4 < np.mean(R2.accepts[150:]) < 0.9

@@ -1,0 +1,232 @@
+"""GPU parity tests proper: the sm_100a path called through the C ABI vs the CPU oracle and the
+committed golden vectors.  Tolerances are BASELINE.json's: c, U <= 1e-6 relative; RF <= 1e-5 of the
+trace peak; gradients <= 1e-4 relative (to the largest component of that gradient)."""
+import os
+import numpy as np
+import pytest
+from oracle.oracle import brocher
+from rfsurfhmc_b200.fixtures import (f1_config, f1_true_model, driver_bounds, sorted_uniform_models,
+                                     perturbed_models)
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+TOL_C, TOL_RF, TOL_G = 1e-6, 1e-5, 1e-4
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def test_native_library_is_loaded(ctx):
+    # the CUDA extension is the thing that runs: it is mapped into this process
+    maps = open("/proc/self/maps").read()
+    assert "librfsurf_b200.so" in maps
+    l0 = ctx.launches
+    ctx.surf_forward([5., 0.], [5., 6.], [3., 3.5], [2.5, 2.8], [5.], "Rc")
+    assert ctx.launches > l0
+
+
+def test_libsurf_dropin_vs_golden(ctx):
+    g = np.load(os.path.join(G, "f1_dropin.npz"))
+    thk, vs, vp, rho, T = g["thk"], g["vs"], g["vp"], g["rho"], g["T"]
+    from rfsurfhmc_b200.model.lib import libsurf
+    for wt in ("Rc", "Rg", "Lc", "Lg"):
+        for mode in (0, 1, 2):
+            c, ok = libsurf.forward(thk, vp, vs, rho, T, wt, mode)
+            ref = g[f"fwd_{wt}_{mode}"]
+            assert ok == bool(g[f"fwd_{wt}_{mode}_ok"])
+            assert c.shape == (36,) and c.dtype == np.float64
+            # missing higher modes: zeros (phase) / NaN (group) exactly where the reference has them
+            assert np.array_equal(ref == 0, c == 0) and np.array_equal(np.isnan(ref), np.isnan(c))
+            m = np.isfinite(ref) & (ref != 0)
+            assert rel(c[m], ref[m]) <= TOL_C, (wt, mode)
+        c, da, db, dr, dh, ok = libsurf.adjoint_kernel(thk, vp, vs, rho, T, wt)
+        assert ok and da.shape == (36, 7)
+        assert rel(c, g[f"ker_{wt}_c"]) <= TOL_C
+        for got, key in ((da, "da"), (db, "db"), (dr, "dr"), (dh, "dh")):
+            ref = g[f"ker_{wt}_{key}"]
+            s = np.max(np.abs(ref))
+            if s > 0:
+                assert np.max(np.abs(got - ref)) / s <= TOL_G, (wt, key)
+            else:
+                assert np.all(got == 0)
+
+
+def test_librf_dropin_vs_golden(ctx):
+    g = np.load(os.path.join(G, "f1_dropin.npz"))
+    thk, vs, vp, rho = g["thk"], g["vs"], g["vp"], g["rho"]
+    q = thk * 0 + 9999.
+    from rfsurfhmc_b200.model.lib import librf
+    for rft in ("P", "S"):
+        a = (thk, rho, vp, vs, q, q, 0.045, 125, 0.4, 1.5, 5.0, "freq", 0.001, rft)
+        rf = librf.forward(*a)
+        rf2, kl = librf.kernel_all(*a)
+        peak = np.max(np.abs(g[f"rf_{rft}"]))
+        assert rf.shape == (125,) and kl.shape == (4, 7, 125)
+        assert np.max(np.abs(rf - g[f"rf_{rft}"])) <= TOL_RF * peak
+        assert np.max(np.abs(rf2 - g[f"rf_{rft}"])) <= TOL_RF * peak
+        ref = g[f"rf_{rft}_kl"]
+        for ip in range(4):
+            assert np.max(np.abs(kl[ip] - ref[ip])) <= TOL_G * np.max(np.abs(ref[ip]))
+        for ip, nm in enumerate(("rho", "vp", "vs", "h")):
+            _, k1 = librf.kernel(*a, par_type=nm)
+            assert np.max(np.abs(k1 - ref[ip])) <= TOL_G * np.max(np.abs(ref[ip]))
+    # F2 parameter set of the reference's test_forward.py (freq variant; nt=500 -> nft=512)
+    vs2 = g["f2_vs"]
+    vp2, rho2 = brocher(vs2)
+    rf = librf.forward(thk, rho2, vp2, vs2, q, q, 0.045, 500, 0.1, 1.0, 5.0, "freq", 0.001, "P")
+    assert np.max(np.abs(rf - g["f2_rf_freq"])) <= TOL_RF * np.max(np.abs(g["f2_rf_freq"]))
+
+
+def test_error_conventions(ctx):
+    from rfsurfhmc_b200._lib import RfsError
+    from rfsurfhmc_b200.model.lib import libsurf, librf
+    thk, vs = np.array([5., 0.]), np.array([3., 3.5])
+    vp, rho = brocher(vs)
+    q = thk * 0 + 9999.
+    with pytest.raises(ValueError):
+        libsurf.forward(thk, vp, vs, rho, [5.], "Rx")
+    with pytest.raises(ValueError):
+        librf.forward(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "freq", 0.001, "Q")
+    with pytest.raises(ValueError):
+        librf.kernel(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "freq", 0.001, "P", "zz")
+    with pytest.raises(RfsError):  # not built yet: fails loudly instead of falling back
+        libsurf.forward(thk, vp, vs, rho, [5.], "Rc", 0, True)
+    with pytest.raises(RfsError):
+        librf.forward(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "time", 0.001, "P")
+    with pytest.raises(RfsError):  # descending periods are rejected (mode cut-off logic needs ascending)
+        libsurf.forward(thk, vp, vs, rho, [8., 5.], "Rc")
+
+
+def test_root_failure_flag_and_batch_edges(ctx, oracle):
+    # a strong inversion on top of a slow half-space: no fundamental root below betmx at long period
+    thk = np.array([2., 0.]); vs = np.array([4.5, 1.6])
+    vp, rho = brocher(vs)
+    T = np.array([1., 2., 30., 60.])
+    c0, ok0 = oracle.surf_forward(thk, vp, vs, rho, T, "Rc")
+    c1, ok1 = ctx.surf_forward(thk, vp, vs, rho, T, "Rc")
+    assert ok0 == bool(ok1[0])
+    assert np.array_equal(c0 == 0, c1[0] == 0)
+    # ragged batch sizes incl. 1 and a non-multiple of the block size; models are independent
+    x0 = f1_true_model()
+    X = perturbed_models(x0, 131, seed=3)
+    vs_b, thk_b = X[:, :7], X[:, 7:]
+    vp_b, rho_b = brocher(vs_b)
+    Tq = np.array([6., 11., 23.])
+    cb, okb = ctx.surf_forward(thk_b, vp_b, vs_b, rho_b, Tq, "Rc")
+    c1_, _ = ctx.surf_forward(thk_b[77], vp_b[77], vs_b[77], rho_b[77], Tq, "Rc")
+    assert cb.shape == (131, 3) and np.array_equal(cb[77], c1_[0])
+    co, _ = oracle.surf_forward(thk_b[5], vp_b[5], vs_b[5], rho_b[5], Tq, "Rc")
+    assert rel(cb[5], co) <= TOL_C
+
+
+def _joint_ctx(ctx, dobs, cfg):
+    ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"])
+    ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"],
+                  cfg["rf_type"], cfg["method"])
+    ctx.config_obs(dobs)
+
+
+def test_fused_joint_vs_golden(ctx):
+    g = np.load(os.path.join(G, "f1_joint.npz"))
+    cfg = f1_config()
+    _joint_ctx(ctx, g["dobs"], cfg)
+    U, gr, d, f = ctx.misfit_grad_host(g["X"])
+    assert np.array_equal(f, g["flag"])
+    m = f
+    peak = np.max(np.abs(g["dsyn"][m, :125]), axis=1, keepdims=True)
+    assert np.max(np.abs(d[m, :125] - g["dsyn"][m, :125]) / peak) <= TOL_RF
+    assert rel(d[m, 125:], g["dsyn"][m, 125:]) <= TOL_C
+    gs = np.max(np.abs(g["grad"][m]), axis=1, keepdims=True)
+    assert np.max(np.abs(gr[m] - g["grad"][m]) / gs) <= TOL_G
+    assert np.max(np.abs(U[m] - g["U"][m]) / np.maximum(g["U"][m], 1e-12)) <= 1e-5
+
+
+def test_fused_joint_vs_oracle_fresh_models_and_subproblems(ctx, oracle):
+    cfg = f1_config()
+    x0 = f1_true_model()
+    dobs = np.load(os.path.join(G, "f1_joint.npz"))["dobs"]
+    X = np.vstack((sorted_uniform_models(driver_bounds(x0), 160, seed=101),
+                   perturbed_models(x0, 96, seed=102, rel=0.1)))
+    _joint_ctx(ctx, dobs, cfg)
+    U1, g1, d1, f1 = ctx.misfit_grad_host(X)
+    U0, g0, d0, f0 = oracle.joint_batch(X, dobs, cfg, nthreads=8)
+    assert np.array_equal(f0, f1)
+    m = f0
+    e_c = np.max(np.abs(d1[m, 125:] - d0[m, 125:]) / np.abs(d0[m, 125:]), axis=1)
+    e_rf = np.max(np.abs(d1[m, :125] - d0[m, :125]), axis=1) / np.max(np.abs(d0[m, :125]), axis=1)
+    e_g = np.max(np.abs(g1[m] - g0[m]), axis=1) / np.max(np.abs(g0[m]), axis=1)
+    assert e_rf.max() <= TOL_RF
+    # root search is chaotic at the 1e-16 level for a small fraction of strongly inverted models
+    # (DESIGN.md "parity statistics"): every model must be close, >= 99 % within the tolerances
+    assert np.mean(e_c <= TOL_C) >= 0.99 and np.mean(e_g <= TOL_G) >= 0.99
+    assert e_c.max() < 1e-3 and e_g.max() < 1e-2
+    # RF-only and SWD-only objectives (ReceiverFunc / SurfWD misfit_and_grad)
+    for which, sl in ((1, slice(0, 125)), (2, slice(125, 197))):
+        ctx.config_obs(dobs[sl])
+        Ua, ga, da, fa = oracle.joint_batch(X[:64], dobs[sl], cfg, which=which, nthreads=8)
+        Ub, gb, db, fb = ctx.misfit_grad_host(X[:64], which=which)
+        assert np.array_equal(fa, fb)
+        eg = np.max(np.abs(gb[fa] - ga[fa]), axis=1) / np.max(np.abs(ga[fa]), axis=1)
+        assert np.mean(eg <= TOL_G) >= 0.98
+    ctx.config_obs(dobs)
+
+
+def test_reference_shaped_python_api(ctx, oracle):
+    """SurfWD / ReceiverFunc / Joint_RF_SWD driven exactly like the reference drivers do."""
+    import yaml
+    from rfsurfhmc_b200.model.model_rf import ReceiverFunc
+    from rfsurfhmc_b200.model.model_surf import SurfWD
+    from rfsurfhmc_b200.model.model_rf_swd_vs_thk import Joint_RF_SWD
+    param = yaml.safe_load(open(os.path.join(G, "f1_param.yaml")))
+    swd = SurfWD.init(**param["swd"])
+    rfm = ReceiverFunc.init(**param["rf"])
+    x = f1_true_model()
+    model = Joint_RF_SWD(1.0, 1.0, rfm, swd)
+    drf, dsw, flag = model.forward(x)
+    assert flag and drf.shape == (125,) and dsw.shape == (72,)
+    dobs = np.hstack((drf, dsw))
+    model.set_obsdata(dobs[:125], dobs[125:])
+    U, g, d, fl = model.misfit_and_grad(x)
+    assert fl and U < 1e-20 and np.max(np.abs(g)) < 1e-8
+    x2 = x * 1.03
+    U, g, d, fl = model.misfit_and_grad(x2)
+    U0, g0, d0, f0 = oracle.joint_batch(x2[None, :], dobs, f1_config())
+    assert abs(U - U0[0]) <= 1e-6 * U0[0] and np.max(np.abs(g - g0[0])) <= TOL_G * np.max(np.abs(g0[0]))
+    Ur, gr, dr = rfm.misfit_and_grad(x2)
+    Us, gs_, ds, fs = swd.misfit_and_grad(x2)
+    assert np.isclose(U, Ur + (125 / 72) * Us, rtol=1e-9)
+    assert np.allclose(g, gr + (125 / 72) * gs_, rtol=1e-7, atol=1e-12)
+    # finite-difference check of the fused gradient on the RF part (analytic kernels)
+    e = np.zeros(14); e[2] = 1e-5
+    fd = (rfm.misfit_and_grad(x2 + e)[0] - rfm.misfit_and_grad(x2 - e)[0]) / 2e-5
+    assert abs(fd - gr[2]) <= 1e-5 * max(1.0, abs(gr[2]))
+
+
+def test_size_independent_properties_at_scale(ctx):
+    """BASELINE config-2-like sizes (n=40, 60 periods): Euler homogeneity c = sum(vp dc/dvp + vs dc/dvs
+    + h dc/dh) and density invariance for every (model, period), without the oracle."""
+    rng = np.random.default_rng(2)
+    n, B = 40, 512
+    i = np.arange(n - 1)
+    thk = np.hstack((0.5 + 0.1 * i, [0.0]))[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (B, n)))
+    thk[:, -1] = 0.0
+    vs0 = 2.0 + 2.7 * (np.arange(n) / 39.0)**0.7
+    vs = np.clip(vs0[None, :] * (1 + 0.04 * rng.standard_normal((B, n))), 1.5, 5.0)
+    vp, rho = brocher(vs)
+    T = np.geomspace(2, 100, 60)
+    for wt in ("Rc", "Lc"):
+        c, da, db, dr, dh, ok = ctx.surf_adjoint_kernel(thk, vp, vs, rho, T, wt)
+        assert ok.all()
+        v32 = lambda a: a.astype(np.float32).astype(np.float64)
+        euler = ((da * v32(vp)[:, None, :]).sum(2) + (db * v32(vs)[:, None, :]).sum(2) +
+                 (dh * v32(thk)[:, None, :]).sum(2))
+        assert np.max(np.abs(euler - c) / c) < 2e-5, wt
+        assert np.max(np.abs((dr * v32(rho)[:, None, :]).sum(2))) < 1e-4, wt
+    # all modes at once: higher modes are faster, missing ones are zeros at the long-period end
+    c, *_ = ctx.surf_adjoint_kernel(thk[:64], vp[:64], vs[:64], rho[:64], T, "Rc", mode=2, all_modes=True)
+    assert c.shape == (64, 3, 60)
+    both = (c[:, 0] > 0) & (c[:, 1] > 0)
+    assert np.all(c[:, 1][both] > c[:, 0][both])
+    assert np.all((c[:, 2] == 0).sum(1) >= (c[:, 1] == 0).sum(1))

@@ -1,0 +1,89 @@
+"""Pins of the RF oracle: FFT vs NumPy, analytic half-space answer, finite differences, invariance."""
+import numpy as np
+import pytest
+from oracle.oracle import brocher
+from rfsurfhmc_b200.fixtures import f1_true_model
+
+X0 = f1_true_model()
+VS, THK = X0[:7], X0[7:]
+VP, RHO = brocher(VS)
+Q = THK * 0 + 9999.
+ARGS = dict(ray_p=0.045, nt=125, dt=0.4, gauss=1.5, time_shift=5., method="freq", water=0.001, rf_type="P")
+
+
+@pytest.mark.parametrize("n", [2, 8, 128, 1024])
+def test_fft_matches_numpy(oracle, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    X = oracle.rfft(x)
+    assert np.allclose(X, np.fft.rfft(x), rtol=1e-12, atol=1e-12)
+    Y = rng.standard_normal(n // 2 + 1) + 1j * rng.standard_normal(n // 2 + 1)
+    # c2r ignores the imaginary parts of the DC and Nyquist bins (FFTW convention)
+    assert np.allclose(oracle.irfft(Y, n), np.fft.irfft(Y, n), rtol=1e-12, atol=1e-12)
+
+
+def test_halfspace_rf_is_single_gaussian_pulse(oracle):
+    # no interface -> no conversions: the radial/vertical ratio is constant and the RF is one
+    # Gaussian pulse at t = 0 (sample index time_shift/dt)
+    n = 3
+    vs = np.full(n, 3.6); thk = np.array([10., 10., 0.])
+    vp, rho = brocher(vs)
+    q = thk * 0 + 9999.
+    rf = oracle.rf_forward(thk, rho, vp, vs, q, q, 0.06, 256, 0.1, 2.5, 5.0, "freq", 0.001, "P")
+    t = np.arange(256) * 0.1 - 5.0
+    k = np.argmax(np.abs(rf))
+    assert abs(t[k]) < 0.05
+    # time-domain image of exp(-(w/2a)^2) is exp(-a^2 t^2); the complex-frequency trick
+    # (response at w - i sigma, trace times exp(sigma t), RFModule.f90:381-407) turns it into
+    # exp(-a^2 t^2 + sigma t) with sigma = 4/(nft dt)
+    sigma = 4.0 / (256 * 0.1)
+    g = np.exp(-(2.5 * t)**2 + sigma * t)
+    shape = rf / rf[k]
+    assert np.max(np.abs(shape - g / g[k])[np.abs(t) < 1.5]) < 2e-3
+    assert np.max(np.abs(rf[t > 2.0])) < 1e-3 * abs(rf[k])
+
+
+def test_f1_trace_matches_independent_probe(oracle):
+    rf = oracle.rf_forward(THK, RHO, VP, VS, Q, Q, **ARGS)
+    # SURVEY.md Appendix C (independent NumPy scratch restatement)
+    assert abs(rf.sum() - 1.095717149) < 1e-8
+    assert np.argmax(rf) == 12 and abs(rf[12] - 0.222843) < 1e-6
+    assert np.allclose(rf[10:16], [0.024547, 0.106417, 0.222843, 0.218859, 0.090575, 0.018077], atol=1e-6)
+
+
+def test_kernels_finite_difference_and_variants(oracle):
+    rf, kl = oracle.rf_kernel_all(THK, RHO, VP, VS, Q, Q, **ARGS)
+    assert np.allclose(rf, oracle.rf_forward(THK, RHO, VP, VS, Q, Q, **ARGS), rtol=0, atol=1e-13)
+    names = ["rho", "vp", "vs", "h"]
+    arrs = {"rho": RHO, "vp": VP, "vs": VS, "h": THK}
+    for ip, nm in enumerate(names):
+        _, k1 = oracle.rf_kernel(THK, RHO, VP, VS, Q, Q, par_type=nm, **ARGS)
+        assert np.array_equal(k1, kl[ip])
+        for j in range(7):
+            base = {k: v.copy() for k, v in arrs.items()}
+            h = 1e-5
+            base[nm][j] += h
+            fp = oracle.rf_forward(base["h"], base["rho"], base["vp"], base["vs"], Q, Q, **ARGS)
+            base[nm][j] -= 2 * h
+            fm = oracle.rf_forward(base["h"], base["rho"], base["vp"], base["vs"], Q, Q, **ARGS)
+            fd = (fp - fm) / (2 * h)
+            assert np.max(np.abs(fd - kl[ip, j])) < 2e-8 + 1e-6 * np.max(np.abs(kl[ip, j])), (nm, j)
+    # density invariance: sum_j rho_j dRF/drho_j = 0
+    assert np.max(np.abs((RHO[:, None] * kl[0]).sum(0))) < 1e-13
+    # half-space thickness has no influence
+    assert np.all(kl[3, 6] == 0.0)
+
+
+def test_s_type_and_time_method_run(oracle):
+    a = dict(ARGS); a["rf_type"] = "S"
+    rf, kl = oracle.rf_kernel_all(THK, RHO, VP, VS, Q, Q, **a)
+    assert np.all(np.isfinite(rf)) and np.all(np.isfinite(kl))
+    a = dict(ARGS); a["method"] = "time"; a["gauss"] = 1.0
+    rft = oracle.rf_forward(THK, RHO, VP, VS, Q, Q, **a)
+    a["method"] = "freq"
+    rff = oracle.rf_forward(THK, RHO, VP, VS, Q, Q, **a)
+    # iterative and water-level deconvolution agree on the main features
+    assert abs(int(np.argmax(rft)) - int(np.argmax(rff))) <= 1
+    assert np.max(np.abs(rft - rff)) < 0.15 * np.max(np.abs(rff))
+    with pytest.raises(ValueError):
+        oracle.rf_forward(THK, RHO, VP, VS, Q, Q, 0.045, 125, 0.4, 1.5, 5.0, "freq", 0.001, "X")

@@ -1,0 +1,155 @@
+"""Pins of the SWD oracle (no reference test exists): analytic known answers,
+finite differences of its own forward, exact scaling identities, mode bookkeeping."""
+import numpy as np
+import pytest
+from oracle.oracle import brocher
+from rfsurfhmc_b200.fixtures import f1_true_model
+
+X0 = f1_true_model()
+VS, THK = X0[:7], X0[7:]
+VP, RHO = brocher(VS)
+
+
+def rayleigh_halfspace_speed(a, b):
+    """root of (2-k^2)^2 = 4 sqrt(1-g^2 k^2) sqrt(1-k^2), k=c/b, g=b/a (same equation gtsolh iterates,
+    surfdisp96.f:380-394), by bisection in double precision."""
+    g = b / a
+    f = lambda k: (2 - k * k)**2 - 4 * np.sqrt(1 - g * g * k * k) * np.sqrt(1 - k * k)
+    lo, hi = 0.5, 0.999999
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if f(lo) * f(mid) <= 0:
+            hi = mid
+        else:
+            lo = mid
+    return 0.5 * (lo + hi) * b
+
+
+def test_rayleigh_homogeneous_halfspace(oracle):
+    # identical layers == half-space: non-dispersive Rayleigh wave at the analytic speed
+    n = 4
+    vs = np.full(n, 3.5); vp = np.full(n, 6.0); rho = np.full(n, 2.7); thk = np.array([5., 5., 5., 0.])
+    T = np.array([2., 5., 10., 20., 40.])
+    c, ok = oracle.surf_forward(thk, vp, vs, rho, T, "Rc")
+    cr = rayleigh_halfspace_speed(float(np.float32(6.0)), float(np.float32(3.5)))
+    assert ok
+    # nevill's bias (<= ~1e-6 relative, always low) + float32 output rounding
+    assert np.all(np.abs(c - cr) / cr < 1.5e-6)
+    u, ok = oracle.surf_forward(thk, vp, vs, rho, T, "Rg")
+    assert ok and np.all(np.abs(u - cr) / cr < 5e-6)  # U == c without dispersion
+
+
+def test_love_layer_over_halfspace(oracle):
+    # tan(q h) = mu2 nu2 / (mu1 q): residual of the classical dispersion relation at the oracle roots
+    thk = np.array([20., 0.]); vs = np.array([3.0, 4.5]); vp = vs * 1.75; rho = np.array([2.5, 3.2])
+    T = np.array([5., 8., 12., 20., 30.])
+    for mode in (0, 1):
+        c, ok = oracle.surf_forward(thk, vp, vs, rho, T, "Lc", mode=mode)
+        assert ok
+        for t, cc in zip(T, c):
+            if cc == 0.0:
+                continue
+            w = 2 * np.pi / t
+            k = w / cc
+            b1, b2 = float(np.float32(3.0)), float(np.float32(4.5))
+            r1, r2 = float(np.float32(2.5)), float(np.float32(3.2))
+            q = np.sqrt((w / b1)**2 - k * k)
+            nu2 = np.sqrt(k * k - (w / b2)**2)
+            lhs = np.tan(q * 20.0)
+            rhs = (r2 * b2 * b2 * nu2) / (r1 * b1 * b1 * q)
+            # the root is only located to ~1e-6 relative; compare through the phase
+            ph = np.arctan(rhs) + mode * np.pi
+            assert abs(q * 20.0 - ph) < 2e-4, (mode, t, cc, lhs, rhs)
+
+
+def test_f1_values_and_modes(oracle):
+    T = np.arange(5., 41.)
+    c, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Rc")
+    assert ok
+    # independent scratch-probe values of SURVEY.md Appendix C (float32-rounded on output)
+    ref = {5: 2.811252546, 6: 2.802712276, 10: 2.876952767, 20: 3.247148090, 40: 3.882736766}
+    for t, v in ref.items():
+        assert abs(c[int(t) - 5] - v) / v < 1e-7
+    # reversed dispersion below 6 s (low-velocity second layer) exercises the downward search
+    assert c[1] < c[0]
+    # mode 2 does not exist at long periods: zeros with flag True (surfdisp96.f:317,356-362)
+    c2, ok2 = oracle.surf_forward(THK, VP, VS, RHO, np.array([2., 11.]), "Rc", mode=2)
+    assert ok2 and c2[0] > 3.0 and c2[1] == 0.0
+    n_ev = oracle.surfdisp96_evals(THK, VP, VS, RHO, T)
+    assert 700 < n_ev < 1100  # ~125 scan steps once + ~21 per later period
+
+
+@pytest.mark.parametrize("wt", ["Rc", "Lc"])
+def test_phase_kernels_finite_difference(oracle, wt):
+    T = np.array([5., 12., 25., 40.])
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, wt)
+    assert ok
+
+    def roots(thk, vp, vs, rho):
+        # tight-root evaluation through the kernel's own U/c is impossible; use many-period forward
+        return oracle.surf_forward(thk, vp, vs, rho, T, wt)[0]
+    # the forward is float32-quantised (6e-8) and nevill-biased (1e-6), so FD needs big steps:
+    # compare with a relative tolerance that reflects that noise (few %) on the dominant entries
+    for arr, ker in ((VS, db), (THK, dh)):
+        for j in range(6):
+            h = 0.02 * max(arr[j], 1.0)
+            p = arr.copy(); p[j] += h
+            m = arr.copy(); m[j] -= h
+            if arr is VS:
+                fd = (roots(THK, VP, p, RHO) - roots(THK, VP, m, RHO)) / (2 * h)
+            else:
+                fd = (roots(p, VP, VS, RHO) - roots(m, VP, VS, RHO)) / (2 * h)
+            big = np.abs(ker[:, j]) > 0.02
+            if big.any():
+                assert np.max(np.abs(fd[big] - ker[big, j]) / np.abs(ker[big, j])) < 0.03
+
+
+def test_euler_homogeneity_and_density_invariance(oracle):
+    T = np.array([5., 8., 12., 20., 30., 40.])
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, "Rc")
+    euler = (da * VP).sum(1) + (db * VS).sum(1) + (dh * THK).sum(1)
+    assert np.max(np.abs(euler - c) / c) < 5e-6
+    assert np.max(np.abs((dr * RHO).sum(1))) < 2e-5
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, "Lc")
+    euler = (db * VS).sum(1) + (dh * THK).sum(1)
+    assert np.max(np.abs(euler - c) / c) < 5e-6
+    assert np.max(np.abs((dr * RHO).sum(1))) < 2e-5
+    assert np.all(da == 0.0)
+
+
+def test_group_velocity_consistent_with_dispersion(oracle):
+    # U = c / (1 + (T/c) dc/dT): energy-integral U vs numerical differentiation of the phase curve
+    T = np.linspace(8., 36., 15)
+    u, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Rg")
+    h = 0.25
+    cp, _ = oracle.surf_forward(THK, VP, VS, RHO, T + h, "Rc")
+    cm, _ = oracle.surf_forward(THK, VP, VS, RHO, T - h, "Rc")
+    c0, _ = oracle.surf_forward(THK, VP, VS, RHO, T, "Rc")
+    un = c0 / (1 + (T / c0) * (cp - cm) / (2 * h))
+    assert np.max(np.abs(u - un) / u) < 2e-4
+
+
+def test_group_kernel_identity_and_stale_switch(oracle):
+    # dU/dm = (U/c)(2-U/c) dcdm[first] - (U/c)^2 T (dcdm(T2)-dcdm(T1))/(T2-T1)   (sregn96.f90:1839-1844)
+    T = np.array([8., 20., 35.])
+    t1, t2 = T * (1.0 + 0.05), T * (1.0 - 0.05)
+    c0, a0, b0, r0, h0, _ = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, "Rc")
+    c1, a1, b1, r1, h1, _ = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, t1, "Rc")
+    c2, a2, b2, r2, h2, _ = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, t2, "Rc")
+    u, _ = oracle.surf_forward(THK, VP, VS, RHO, T, "Rg")
+    for stale in (True, False):
+        ug, ga, gb, gr, gh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, "Rg", stale=stale)
+        assert ok and np.allclose(ug, u, rtol=1e-12)
+        uc = (u / c0)[:, None]
+        first = b2 if stale else b0
+        expect = uc * (2 - uc) * first - uc**2 * T[:, None] * (b2 - b1) / (t2 - t1)[:, None]
+        assert np.allclose(gb, expect, rtol=1e-9, atol=1e-13)
+    # the two forms differ by percents: the reference's stale form is what parity needs
+    ga_s = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, "Rg", stale=True)[2]
+    ga_f = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, "Rg", stale=False)[2]
+    assert np.max(np.abs(ga_s - ga_f)) / np.max(np.abs(ga_f)) > 5e-3
+
+
+def test_invalid_wavetype_raises(oracle):
+    with pytest.raises(ValueError):
+        oracle.surf_forward(THK, VP, VS, RHO, [5.], "Xx")
