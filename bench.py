@@ -109,6 +109,7 @@ def main():
     ap.add_argument("--chains", type=int, default=16384, help="chain states per GPU (C4: 16384)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hmc", action="store_true", help="skip the short device-resident HMC leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -251,11 +252,37 @@ def main():
     barrier()
     t_e2e = time.perf_counter() - t0
 
+    # ---- secondary metric: device-resident HMC (C4: L=20 leapfrog steps per trajectory)
+    hmc = None
+    if not args.no_hmc:
+        from rfsurfhmc_b200.fixtures import driver_bounds
+        from rfsurfhmc_b200.distributed import shard_chains
+        ids = shard_chains(B * world, rank, world)
+        ntraj = 4
+        barrier()
+        t0 = time.perf_counter()
+        ho = ctx.hmc_run(0, ids, driver_bounds(x0), 0.02, Lrange=(20, 20), seed=991206, nsamples=ntraj,
+                         ndraws=0, max_iters=ntraj, want_samples=False, want_syn=False)
+        barrier()
+        th = time.perf_counter() - t0
+        hmc = [th, float(ho["n_iter"].sum()), float(ho["n_acc"].sum()), float(ho["evals"])]
+
     # max over ranks
     tt = torch.tensor([ms, t_e2e * 1e3, ms_noflush], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_noflush = [float(v) for v in tt.tolist()]
+    if hmc is not None:
+        hv = torch.tensor(hmc, dtype=torch.float64, device=dev)
+        hmax = hv.clone()
+        if world > 1:
+            dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(hv, op=dist.ReduceOp.SUM)
+        th = float(hmax[0])
+        hmc = {"sampler": "HamitonianMC, L=20, dt=0.02, %d chains/GPU, %d trajectories each (initial models, "
+                          "includes chain initialisation and the first evaluation)" % (B, 4),
+               "trajectories_per_s": float(hv[1]) / th, "accepted_samples_per_s": float(hv[2]) / th,
+               "evals_per_s": float(hv[3]) / th, "seconds": th}
     value = world * B * args.steps / (ms * 1e-3)
     e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
 
@@ -299,7 +326,7 @@ def main():
                "data": "synthetic", "config": config, "clocks": sampler.summary(),
                "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": B * 2 * N_LAYERS * 8,
                        "d2h_bytes_per_step": B * (1 + 2 * N_LAYERS + nd) * 8 + B},
-               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+               "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "hmc": hmc,
                "failed_models_last_step": n_fail}
         print(json.dumps(out))
     if world > 1:
