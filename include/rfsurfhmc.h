@@ -126,6 +126,7 @@ long long rfs_hmc_last_evals(rfs_ctx *ctx);
  * rfs_measure_fp64_peak runs a DFMA micro-benchmark: the roofline denominator of the FP64 path. */
 int rfs_count_evals(rfs_ctx *ctx, int enable);
 long long rfs_read_evals(rfs_ctx *ctx);
+int rfs_read_eval_stats(rfs_ctx *ctx, long long *out3); /* total, slowest thread, threads > 2000 */
 int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus

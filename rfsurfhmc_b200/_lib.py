@@ -84,6 +84,8 @@ def load_library():
         L.rfs_count_evals.argtypes = [_vp, C.c_int]
         L.rfs_read_evals.restype = C.c_longlong
         L.rfs_read_evals.argtypes = [_vp]
+        L.rfs_read_eval_stats.restype = C.c_int
+        L.rfs_read_eval_stats.argtypes = [_vp, _llp]
         L.rfs_measure_fp64_peak.restype = C.c_int
         L.rfs_measure_fp64_peak.argtypes = [_vp, _dp]
         _lib = L
@@ -97,7 +99,7 @@ def exported_symbols():
             "rfs_misfit_grad_host", "rfs_surf_forward", "rfs_surf_adjoint_kernel",
             "rfs_surf_adjoint_kernel_modes", "rfs_rf_forward", "rfs_rf_kernel", "rfs_rf_kernel_all",
             "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
-            "rfs_measure_fp64_peak"]
+            "rfs_measure_fp64_peak", "rfs_read_eval_stats"]
 
 
 def _f64(a):
@@ -151,6 +153,11 @@ class Context:
 
     def read_evals(self):
         return int(self.L.rfs_read_evals(self.h))
+
+    def read_eval_stats(self):
+        v = (C.c_longlong * 3)()
+        self._ck(self.L.rfs_read_eval_stats(self.h, v))
+        return int(v[0]), int(v[1]), int(v[2])
 
     def measure_fp64_peak(self):
         v = C.c_double(0.0)

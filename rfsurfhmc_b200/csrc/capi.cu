@@ -776,6 +776,16 @@ long long rfs_read_evals(rfs_ctx *ctx) {
   if (cudaMemcpy(&v, ctx->d_counter.p, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (long long)v;
 }
+// [0] total secular evaluations, [1] evaluations of the slowest thread, [2] threads above 2000
+int rfs_read_eval_stats(rfs_ctx *ctx, long long *out3) {
+  if (!ctx || !ctx->d_counter.p || !out3) return RFS_E_ARG;
+  unsigned long long v[3] = {0, 0, 0};
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(v, ctx->d_counter.p, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 3; i++) out3[i] = (long long)v[i];
+  return RFS_OK;
+}
 
 __global__ void dfma_peak_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,

@@ -105,20 +105,24 @@ __global__ void __launch_bounds__(128, RFS_ROOTS_MINBLOCKS)
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
                      int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
+  __shared__ double wsm_all[4][33];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= B * plan.nseq) return;
-  const long long b = i % B;
-  const int s = (int)(i / B);
+  const bool valid = i < B * plan.nseq;
+  const long long b = valid ? i % B : 0;
+  const int s = valid ? (int)(i / B) : 0;
   SwdModel M{swd, B, n};
   unsigned int nev = 0;
   const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                   (long long)plan.nsolve * B, cwork, B, nev);
-  ierr[(long long)s * B + b] = e;
+                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
+                                   wsm_all[threadIdx.x >> 5]);
+  if (valid) ierr[(long long)s * B + b] = e;
   if (neval_total) {
     // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
     unsigned int w = nev;
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(__activemask(), w, o);
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
     if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
+    atomicMax(neval_total + 1, (unsigned long long)nev);          // slowest thread
+    if (nev > 2000u) atomicAdd(neval_total + 2, 1ull);            // heavy threads (> 2000 evals)
   }
 }
 

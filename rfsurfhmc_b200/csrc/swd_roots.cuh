@@ -244,11 +244,19 @@ enum { PH_SETUP = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE, PH_DONE };
 // The job loop (main pass + per-period retries of surfdisp.cpp:93-100), the mode loop, the period
 // loop, getsol and nevill are ONE loop whose body performs exactly one secular evaluation:
 // lanes never wait for each other at period or mode boundaries.
+//
+// Warp-cooperative tail: rare models need 5-10x more evaluations than the rest (upward scans from
+// the floor velocity in the per-period retries).  All 32 lanes of a warp stay in the loop until
+// the last one is done; lanes that are finished evaluate look-ahead scan points c2+j*dc for one
+// scanning lane (same repeated additions, hence bit-identical grid) and hand the values over
+// through shared memory (`wsm`, 32 doubles per warp).  `valid` = this lane owns a sequence.
 RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &sq,
                                   const double *__restrict__ periods, int nmode, int all_modes,
                                   double *__restrict__ cout, long long cout_mode_stride,
                                   double *__restrict__ cwork, long long stride,
-                                  unsigned int &n_evals) {
+                                  unsigned int &n_evals, bool valid, double *wsm) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const int mmax = M.n;
   const int ifunc = sq.ifunc;
   const int kmax = sq.nper;
@@ -294,7 +302,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
          iomega = 0.0;
   double xs[12], ys[12];
   int idir = 1, nev = 1, nctrl = 1, mm = 1, ifirst = 0;
-  int phase = PH_SETUP;
+  int phase = valid ? PH_SETUP : PH_DONE;
   double ceval = 0.0;
 
   for (;;) {
@@ -380,35 +388,61 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
         phase = PH_G_FIRST;
         break;
       }
-      if (phase == PH_DONE) break;
+    }
+    // ---- warp bookkeeping: who is finished, who is scanning upward
+    const unsigned done_mask = __ballot_sync(FULL, phase == PH_DONE);
+    if (done_mask == FULL) break;
+    const unsigned want_mask = __ballot_sync(FULL, phase == PH_G_SCAN && idir > 0);
+    int nhelp = 0, hsrc = 0, hj = 0;
+    bool helper = false;
+    double e_c = ceval, e_om = omega, e_iom = iomega;
+    long long e_b = b;
+    int e_llw = llw, e_if = ifunc;
+    if (done_mask != 0u && want_mask != 0u) {
+      hsrc = __ffs(want_mask) - 1;
+      nhelp = __popc(done_mask);
+      const double c_h = __shfl_sync(FULL, ceval, hsrc);
+      const double om_h = __shfl_sync(FULL, omega, hsrc);
+      const double iom_h = __shfl_sync(FULL, iomega, hsrc);
+      const long long b_h = __shfl_sync(FULL, b, hsrc);
+      const int llw_h = __shfl_sync(FULL, llw, hsrc);
+      const int if_h = __shfl_sync(FULL, ifunc, hsrc);
+      if (phase == PH_DONE) {
+        helper = true;
+        hj = __popc(done_mask & ((1u << lane) - 1u)) + 1;  // look-ahead index 1..nhelp
+        double c = c_h;
+        for (int t = 0; t < hj; t++) c = c + dc;           // same additions as the scanning lane
+        e_c = c;
+        e_om = om_h;
+        e_iom = iom_h;
+        e_b = b_h;
+        e_llw = llw_h;
+        e_if = if_h;
+      }
     }
 
     // ---- the single secular-function evaluation site
-    const double wv = omega / ceval;
+    double val = 0.0;
+    if (phase != PH_DONE || helper) {
+      const double wv = e_om / e_c;
+      val = (e_if == 1) ? dltar1_dev(wv, e_om, M, e_b, e_llw)
+                        : dltar4_dev(wv, e_om, e_iom, M, e_b, e_llw);
+    }
+    if (nhelp) {
+      if (helper) wsm[hj] = val;
+      __syncwarp();
+    }
+    if (phase == PH_DONE) {
+      if (nhelp) __syncwarp();
+      continue;
+    }
     n_evals++;
-    const double val =
-        (ifunc == 1) ? dltar1_dev(wv, omega, M, b, llw) : dltar4_dev(wv, omega, iomega, M, b, llw);
 
     int iret = 0;  // 0 running, 1 root accepted, -1 failed
     bool body = false;
-    if (phase == PH_G_FIRST) {
-      del1 = val;
-      if (ifirst == 1) del1st = del1;
-      const double plmn = sgn1(del1st) * sgn1(del1);
-      idir = (ifirst == 1 || plmn >= 0.0) ? +1 : -1;
-      for (;;) {  // label 1000 (:457-470)
-        c2 = (idir > 0) ? c1 + dc : c1 - dc;
-        if (c2 <= clow) {
-          idir = +1;
-          c1 = clow;
-          continue;
-        }
-        break;
-      }
-      ceval = c2;
-      phase = PH_G_SCAN;
-    } else if (phase == PH_G_SCAN) {
-      del2 = val;
+    // one upward/downward scan step given Delta(c2) (getsol :457-479)
+    auto scan_step = [&](double v) {
+      del2 = v;
       if (sgn1(del1) != sgn1(del2)) {
         c3 = 0.5 * (c1 + c2);  // bracketed -> nevill: initial half
         ceval = c3;
@@ -431,6 +465,33 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
             break;
           }
           ceval = c2;
+        }
+      }
+    };
+    if (phase == PH_G_FIRST) {
+      del1 = val;
+      if (ifirst == 1) del1st = del1;
+      const double plmn = sgn1(del1st) * sgn1(del1);
+      idir = (ifirst == 1 || plmn >= 0.0) ? +1 : -1;
+      for (;;) {  // label 1000 (:457-470)
+        c2 = (idir > 0) ? c1 + dc : c1 - dc;
+        if (c2 <= clow) {
+          idir = +1;
+          c1 = clow;
+          continue;
+        }
+        break;
+      }
+      ceval = c2;
+      phase = PH_G_SCAN;
+    } else if (phase == PH_G_SCAN) {
+      scan_step(val);
+      if (nhelp && lane == hsrc) {
+        // consume the look-ahead values while the scan simply slides upward
+        for (int j = 1; j <= nhelp; j++) {
+          if (!(phase == PH_G_SCAN && idir > 0 && iret == 0)) break;
+          n_evals++;
+          scan_step(wsm[j]);
         }
       }
     } else if (phase == PH_N_TOP) {
@@ -526,6 +587,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
       k = 0;
       phase = PH_SETUP;
     }
+    if (nhelp) __syncwarp();  // wsm may be rewritten in the next trip
   }
   return ierr;
 }
