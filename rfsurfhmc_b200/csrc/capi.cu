@@ -15,6 +15,7 @@
 #include "hmc_kernels.cuh"
 #include "joint_kernels.cuh"
 #include "rf_kernels.cuh"
+#include "rf_time_kernels.cuh"
 #include "swd_kernels.cuh"
 
 using namespace rfs;
@@ -215,7 +216,8 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const doubl
 // ---- RF pipeline on a prepared model block (freq method)
 // nq: 0 forward only, 2 chain-rule rows (vs, thk), 4 all parameters
 int run_rf_spectra(rfs_ctx *ctx, const double *d_rfm, const double *d_chain, const double *d_qa,
-                   const double *d_qb, long long B, int n, int nq, double sigma, cudaStream_t st) {
+                   const double *d_qb, long long B, int n, int nq, double sigma, cudaStream_t st,
+                   double pi_used = RFS_PI32) {
   int rc;
   const int n2 = ctx->n2;
   if ((rc = ensure(ctx, ctx->w_spec, sizeof(double2) * (size_t)B * 2 * n2))) return rc;
@@ -225,7 +227,7 @@ int run_rf_spectra(rfs_ctx *ctx, const double *d_rfm, const double *d_chain, con
   const long long tot = B * n2;
 #define PROP(NM, NQ)                                                                           \
   LAUNCH((rf_propagate_kernel<NM, NQ>), gridFor(tot, 128), 128, 0, st, d_rfm, d_chain, d_qa,   \
-         d_qb, B, n, n2, ctx->nft, ctx->dt, ctx->ray_p, sigma, ctx->rf_type,                   \
+         d_qb, B, n, n2, ctx->nft, ctx->dt, ctx->ray_p, sigma, pi_used, ctx->rf_type,          \
          (double2 *)ctx->w_spec.p, dsp)
 #define PROPQ(NM)    \
   if (nq == 2) {     \
@@ -261,6 +263,24 @@ int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, doub
   return RFS_OK;
 }
 
+size_t time_smem(int nft, int n2) { return sizeof(double) * (2 * (size_t)nft + 8 * (size_t)n2 + 64); }
+
+// time-domain method: iterative deconvolution of the spectra in w_spec / w_dspec (sigma = 0)
+// nrow = 0 (receiver function only) or 4n (plus all Frechet traces -> w_rftr [B][4n][nt])
+int run_rf_time(rfs_ctx *ctx, long long B, int nrow, double *d_rf, long long ldrf, double tshift,
+                cudaStream_t st) {
+  int rc;
+  if (nrow > 0)
+    if ((rc = ensure(ctx, ctx->w_rftr, sizeof(double) * (size_t)B * nrow * ctx->nt))) return rc;
+  const size_t sm = time_smem(ctx->nft, ctx->n2);
+  if (sm > 48 * 1024)
+    CK(cudaFuncSetAttribute(rf_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  LAUNCH(rf_time_kernel, (unsigned)(B * (nrow + 1)), decon_threads(ctx->nft), sm, st,
+         (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt, ctx->nft,
+         ctx->logn, ctx->dt, ctx->gauss, tshift, d_rf, ldrf, (double *)ctx->w_rftr.p);
+  return RFS_OK;
+}
+
 int set_rf_cfg(rfs_ctx *ctx, int n, double ray_p, int nt, double dt, double gauss,
                double time_shift, double water, int rf_type, int method) {
   if (rf_type != 1 && rf_type != 2) return fail(ctx, RFS_E_ARG, "rf_type should be one of [P,p,S,s]");
@@ -288,7 +308,8 @@ int set_rf_cfg(rfs_ctx *ctx, int n, double ray_p, int nt, double dt, double gaus
   ctx->nft = nft;
   ctx->logn = lg;
   ctx->n2 = nft / 2 + 1;
-  if (decon_smem(nft, ctx->n2) > 200 * 1024) return fail(ctx, RFS_E_ARG, "nt too large (max 8192)");
+  if (std::max(decon_smem(nft, ctx->n2), time_smem(nft, ctx->n2)) > 220 * 1024)
+    return fail(ctx, RFS_E_ARG, "nt too large (max 4096 samples after padding)");
   return RFS_OK;
 }
 
@@ -304,6 +325,9 @@ size_t per_model_bytes(const rfs_ctx *ctx, int which) {
     s += sizeof(double) * (6 * (size_t)ctx->n_rf) +
          sizeof(double2) * ((size_t)2 * ctx->n2 + (size_t)2 * ctx->n_rf * ctx->n2) +
          sizeof(double) * (1 + 2 * (size_t)ctx->n_rf);
+    if (ctx->method == 0)
+      s += sizeof(double2) * ((size_t)2 * ctx->n_rf * ctx->n2) +
+           sizeof(double) * ((size_t)4 * ctx->n_rf * ctx->nt);
   }
   return s + 64;
 }
@@ -411,8 +435,6 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
     return fail(ctx, RFS_E_CONFIG, "context not configured (rfs_config_swd/rf/obs)");
   if (use_swd && use_rf && ctx->n_swd != ctx->n_rf)
     return fail(ctx, RFS_E_CONFIG, "SWD and RF layer counts differ");
-  if (use_rf && ctx->method != 1)
-    return fail(ctx, RFS_E_UNSUPPORTED, "time-domain (deconit) RF Frechet is not built; use method='freq'");
   const int n = use_swd ? ctx->n_swd : ctx->n_rf;
   const int n1 = use_rf ? ctx->nt : 0, nsw = use_swd ? ctx->plan.ndata : 0;
   const int ndata = n1 + nsw;
@@ -424,7 +446,8 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   const double *d_dobs = (const double *)ctx->d_dobs.p;
   double tshift = ctx->tshift;
   if (ctx->rf_type == 2) tshift = -tshift;  // src/RF/main.cpp:35
-  const double sigma = 1.0 / ctx->dt / ctx->nft * 4.;
+  const bool rf_time = use_rf && ctx->method == 0;
+  const double sigma = rf_time ? 0.0 : 1.0 / ctx->dt / ctx->nft * 4.;
   const double q = ctx->sigma1 / ctx->sigma2;
   const double wt = (which == 0) ? q * q * n1 / nsw : 1.0;
   for (long long off = 0; off < B; off += Bmax) {
@@ -447,15 +470,24 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
         CK(cudaStreamWaitEvent(sr, ctx->ev_fork, 0));
       }
       if ((rc = run_rf_spectra(ctx, (const double *)ctx->w_rfm.p, (const double *)ctx->w_chain.p,
-                               nullptr, nullptr, Bc, n, 2, sigma, sr)))
+                               nullptr, nullptr, Bc, n, rf_time ? 4 : 2, sigma, sr,
+                               rf_time ? RFS_PI64 : RFS_PI32)))
         return rc;
       if ((rc = ensure(ctx, ctx->w_urf, sizeof(double) * Bc))) return rc;
       if ((rc = ensure(ctx, ctx->w_grf, sizeof(double) * 2 * nB))) return rc;
       double *Uo = (which == 1) ? U + off : (double *)ctx->w_urf.p;
       double *go = (which == 1) ? grad + off * 2 * n : (double *)ctx->w_grf.p;
-      if ((rc = run_rf_decon(ctx, Bc, 2 * n, d_dobs, dsyn + off * ndata, ndata, Uo, go, sigma,
-                             tshift, sr)))
-        return rc;
+      if (!rf_time) {
+        if ((rc = run_rf_decon(ctx, Bc, 2 * n, d_dobs, dsyn + off * ndata, ndata, Uo, go, sigma,
+                               tshift, sr)))
+          return rc;
+      } else {
+        // deconit is nonlinear (argmax spike picking): no adjoint shortcut, materialise the traces
+        if ((rc = run_rf_time(ctx, Bc, 4 * n, dsyn + off * ndata, ndata, tshift, sr))) return rc;
+        LAUNCH(rf_trace_grad_kernel, gridFor(Bc * n, 128), 128, 0, sr, (const double *)ctx->w_rftr.p,
+               (const double *)ctx->w_chain.p, (const double *)(dsyn + off * ndata), (long long)ndata,
+               d_dobs, Bc, n, ctx->nt, Uo, go);
+      }
       if (which == 1) CK(cudaMemsetAsync(flag + off, 1, Bc, sr));
       if (sr != st) CK(cudaEventRecord(ctx->ev_join, sr));
     }
@@ -680,9 +712,6 @@ static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const 
     return code;
   };
   if (rc) return done(rc);
-  if (method != 1)
-    return done(fail(ctx, RFS_E_UNSUPPORTED,
-                     "time-domain (deconit) receiver functions are not built yet; use method='freq'"));
   if (nq == 1 && (par_type < 1 || par_type > 4))
     return done(fail(ctx, RFS_E_ARG, "par_type should be one of [vp,vs,rho,thick]"));
   if (B <= 0) return done(RFS_OK);
@@ -704,24 +733,32 @@ static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const 
   const double *d_rfm = (const double *)ctx->w_rfm.p;
   double tshift = time_shift;
   if (rf_type == 2) tshift = -tshift;
-  const double sigma = 1.0 / dt / ctx->nft * 4.;
+  const double sigma = (method == 0) ? 0.0 : 1.0 / dt / ctx->nft * 4.;
   if ((rc = run_rf_spectra(ctx, d_rfm, nullptr, d_rfm + 4 * nB, d_rfm + 5 * nB, B, n,
-                           nq > 0 ? 4 : 0, sigma, st)))
+                           nq > 0 ? 4 : 0, sigma, st,
+                           (method == 0 && nq == 4) ? RFS_PI64 : RFS_PI32)))
     return done(rc);
   if ((rc = ensure(ctx, ctx->io_b, sizeof(double) * B * nt))) return done(rc);
-  if ((rc = run_rf_decon(ctx, B, 0, nullptr, (double *)ctx->io_b.p, nt, nullptr, nullptr, sigma,
-                         tshift, st)))
-    return done(rc);
+  const int nrow = 4 * n;
+  if (method == 0) {
+    if ((rc = run_rf_time(ctx, B, nq > 0 ? nrow : 0, (double *)ctx->io_b.p, nt, tshift, st)))
+      return done(rc);
+  } else {
+    if ((rc = run_rf_decon(ctx, B, 0, nullptr, (double *)ctx->io_b.p, nt, nullptr, nullptr, sigma,
+                           tshift, st)))
+      return done(rc);
+  }
   CK(cudaMemcpyAsync(rf, ctx->io_b.p, sizeof(double) * B * nt, cudaMemcpyDeviceToHost, st));
   if (nq > 0) {
-    const int nrow = 4 * n;
-    if ((rc = ensure(ctx, ctx->w_rftr, sizeof(double) * (size_t)B * nrow * nt))) return done(rc);
-    const size_t sm = decon_smem(ctx->nft, ctx->n2);
-    if (sm > 48 * 1024)
-      CK(cudaFuncSetAttribute(rf_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    LAUNCH(rf_trace_kernel, (unsigned)(B * nrow), decon_threads(ctx->nft), sm, st,
-           (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, nt, ctx->nft,
-           ctx->logn, dt, gauss, tshift, water, sigma, (double *)ctx->w_rftr.p);
+    if (method != 0) {
+      if ((rc = ensure(ctx, ctx->w_rftr, sizeof(double) * (size_t)B * nrow * nt))) return done(rc);
+      const size_t sm = decon_smem(ctx->nft, ctx->n2);
+      if (sm > 48 * 1024)
+        CK(cudaFuncSetAttribute(rf_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      LAUNCH(rf_trace_kernel, (unsigned)(B * nrow), decon_threads(ctx->nft), sm, st,
+             (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, nt, ctx->nft,
+             ctx->logn, dt, gauss, tshift, water, sigma, (double *)ctx->w_rftr.p);
+    }
     if (nq == 4) {
       CK(cudaMemcpyAsync(drf, ctx->w_rftr.p, sizeof(double) * (size_t)B * nrow * nt,
                          cudaMemcpyDeviceToHost, st));

@@ -199,13 +199,15 @@ __global__ void __launch_bounds__(128)
     rf_propagate_kernel(const double *__restrict__ rfm, const double *__restrict__ chain,
                         const double *__restrict__ qa, const double *__restrict__ qb, long long B,
                         int n, int n2, int nft, double dt, double ray_p, double sigma,
-                        int rf_type, double2 *__restrict__ spec, double2 *__restrict__ dspec) {
+                        double pi_used, int rf_type, double2 *__restrict__ spec,
+                        double2 *__restrict__ dspec) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= B * n2) return;
   const long long b = i / n2;
   const int kf = (int)(i % n2);
   const long long nB = (long long)n * B;
-  const double w = 1.0 / nft / dt * kf * 2.0 * RFS_PI32;
+  // pi_used: float32 pi everywhere except cal_rf_par_time_all (RFModule.f90:94 uses atan(1.0_dp))
+  const double w = 1.0 / nft / dt * kf * 2.0 * pi_used;
   const cd omega(w, -sigma);
   const double p = ray_p;
   const int row = (rf_type == 1) ? 1 : 0;
