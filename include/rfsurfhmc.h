@@ -34,7 +34,7 @@ extern "C" {
 #define RFS_OK 0
 #define RFS_E_CUDA -1      /* CUDA runtime error (message has the detail) */
 #define RFS_E_ARG -2       /* invalid argument (bad wave type / rf type / sizes) */
-#define RFS_E_UNSUPPORTED -3 /* reference feature not built yet (spherical earth, water layer, time-domain RF Frechet) */
+#define RFS_E_UNSUPPORTED -3 /* reference feature not built yet (water layers) */
 #define RFS_E_CONFIG -4    /* context not configured for this call */
 
 typedef struct rfs_ctx rfs_ctx;
@@ -51,7 +51,7 @@ long long rfs_launch_count(rfs_ctx *ctx);
 /* ---- configuration (replaces SurfWD.__init__, ReceiverFunc.__init__, Joint_RF_SWD.__init__ +
  *      set_obsdata: model/model_surf.py:5-29, model/model_rf.py:5-18,
  *      model/model_rf_swd_vs_thk.py:6-25) -------------------------------------------------------- */
-/* period lists may be empty (n*=0).  mode: 0 fundamental.  sphere must be 0 (RFS_E_UNSUPPORTED).
+/* period lists may be empty (n*=0).  mode: 0 fundamental.  sphere: 1 = earth-flattening transformation.
  * stale_group_kernel=1 reproduces sregnpu/slegnpu's stale first term (sregn96.f90:1841-1844). */
 int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int ntRg,
                    const double *tRg, int ntLc, const double *tLc, int ntLg, const double *tLg,

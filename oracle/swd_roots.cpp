@@ -72,8 +72,12 @@ void sphere(int ifunc, int iflag, Mod32 &M) {
   } else {
     M.d[mmax - 1] = M.dhalf;
     for (int i = 0; i < mmax; i++) {
-      if (ifunc == 1)
-        M.rho[i] = M.rtp[i] * std::pow(M.btp[i], -5.0f);   // btp(i)**(-5), REAL*4
+      if (ifunc == 1) {
+        // btp(i)**(-5): REAL*4 base with an integer exponent = repeated multiplication
+        const float x = M.btp[i];
+        const float x5 = (((x * x) * x) * x) * x;
+        M.rho[i] = M.rtp[i] * (1.0f / x5);
+      }
       else if (ifunc == 2)
         M.rho[i] = M.rtp[i] * std::pow(M.btp[i], -2.275f);  // REAL*4 pow
     }

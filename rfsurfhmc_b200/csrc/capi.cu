@@ -39,7 +39,7 @@ struct rfs_ctx {
   bool overlap = true;
   // ---- SWD configuration
   bool has_swd = false;
-  int n_swd = 0, mode = 0, stale = 1;
+  int n_swd = 0, mode = 0, stale = 1, sphere = 0;
   SwdPlan plan;
   std::vector<double> periods;
   Buf d_periods;
@@ -53,6 +53,7 @@ struct rfs_ctx {
   std::vector<double> dobs;
   Buf d_dobs;
   // ---- workspace (grown on demand, never shrunk)
+  Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
   Buf w_swd, w_rfm, w_chain, w_qa, w_qb, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
       w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
@@ -182,8 +183,28 @@ int build_plan(rfs_ctx *ctx, SwdPlan &P, std::vector<double> &periods, const int
   return RFS_OK;
 }
 
+// flat block -> SwdBlocks (runs the earth-flattening prep when sphere)
+int make_blocks(rfs_ctx *ctx, const double *d_flat, long long B, int n, int sphere, SwdBlocks &blk,
+                cudaStream_t st) {
+  blk.sphere = sphere;
+  if (!sphere) {
+    blk.root[0] = blk.root[1] = blk.eig[0] = blk.eig[1] = d_flat;
+    return RFS_OK;
+  }
+  int rc;
+  for (int i = 0; i < 4; i++)
+    if ((rc = ensure(ctx, ctx->w_sph[i], sizeof(double) * SWD_NF * (size_t)n * B))) return rc;
+  LAUNCH(prep_sphere_kernel, gridFor(B, 128), 128, 0, st, d_flat, B, n, (double *)ctx->w_sph[0].p,
+         (double *)ctx->w_sph[1].p, (double *)ctx->w_sph[2].p, (double *)ctx->w_sph[3].p);
+  blk.root[0] = (const double *)ctx->w_sph[0].p;
+  blk.root[1] = (const double *)ctx->w_sph[1].p;
+  blk.eig[0] = (const double *)ctx->w_sph[2].p;
+  blk.eig[1] = (const double *)ctx->w_sph[3].p;
+  return RFS_OK;
+}
+
 // ---- SWD pipeline on a prepared model block: roots + eigen solves
-int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const double *d_swd,
+int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
             long long B, int n, bool all_modes, bool want_eigen, cudaStream_t st) {
   const int nmo = all_modes ? P.nmode : 1;
   int rc;
@@ -367,7 +388,8 @@ void rfs_destroy(rfs_ctx *ctx) {
                 &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
                 &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state, &ctx->h_rng,
-                &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out,  &ctx->d_counter};
+                &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out,  &ctx->d_counter, &ctx->w_sph[0], &ctx->w_sph[1],
+                &ctx->w_sph[2],  &ctx->w_sph[3]};
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -385,7 +407,6 @@ int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int nt
                    int mode, int sphere, int stale) {
   if (!ctx) return RFS_E_ARG;
   CK(cudaSetDevice(ctx->device));
-  if (sphere) return fail(ctx, RFS_E_UNSUPPORTED, "spherical earth (sphere=True) is not built yet");
   if (nlayer < 2 || nmax_for(nlayer) < 0) return fail(ctx, RFS_E_ARG, "bad layer count");
   if (mode < 0 || mode > 16) return fail(ctx, RFS_E_ARG, "bad mode");
   const int nts[4] = {ntRc, ntRg, ntLc, ntLg};
@@ -399,6 +420,7 @@ int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int nt
   ctx->n_swd = nlayer;
   ctx->mode = mode;
   ctx->stale = stale ? 1 : 0;
+  ctx->sphere = sphere ? 1 : 0;
   ctx->has_swd = true;
   return RFS_OK;
 }
@@ -492,10 +514,13 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       if (sr != st) CK(cudaEventRecord(ctx->ev_join, sr));
     }
     if (use_swd) {
-      if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p,
-                        (const double *)ctx->w_swd.p, Bc, n, false, true, st)))
+      SwdBlocks blk;
+      if ((rc = make_blocks(ctx, (const double *)ctx->w_swd.p, Bc, n, ctx->sphere, blk, st))) return rc;
+      if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p, blk, Bc, n, false, true, st)))
         return rc;
       SwdView V;
+      V.blk = blk;
+      V.fwd = 0;
       V.croot = (const double *)ctx->w_croot.p;
       V.ugr = (const double *)ctx->w_ugr.p;
       V.kern = (const double *)ctx->w_kern.p;
@@ -554,7 +579,6 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
   if (!ctx) return RFS_E_ARG;
   if (wavetype < 0 || wavetype > 3)
     return fail(ctx, RFS_E_ARG, "wavetype should be one of [Rc,Rg,Lc,Lg]");
-  if (sphere) return fail(ctx, RFS_E_UNSUPPORTED, "spherical earth (sphere=True) is not built yet");
   if (B <= 0 || nT <= 0) return RFS_OK;
   if (n < 2 || nmax_for(n) < 0) return fail(ctx, RFS_E_ARG, "bad layer count");
   if (mode < 0 || mode > 16) return fail(ctx, RFS_E_ARG, "bad mode");
@@ -592,14 +616,18 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
       blk[F_IA * nB + (size_t)m * B + b] = 1.0 / a32;
       blk[F_IB * nB + (size_t)m * B + b] = 1.0 / b32;
       blk[F_IRHO * nB + (size_t)m * B + b] = 1.0 / r32;
+      blk[F_VTP * nB + (size_t)m * B + b] = 1.0;
+      blk[F_DTP * nB + (size_t)m * B + b] = 1.0;
+      blk[F_RTP * nB + (size_t)m * B + b] = 1.0;
     }
   if ((rc = ensure(ctx, ctx->w_swd, sizeof(double) * blk.size()))) return rc;
   if ((rc = ensure(ctx, ctx->io_a, sizeof(double) * periods.size()))) return rc;
   CK(cudaMemcpyAsync(ctx->w_swd.p, blk.data(), sizeof(double) * blk.size(), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->io_a.p, periods.data(), sizeof(double) * periods.size(),
                      cudaMemcpyHostToDevice, st));
-  if ((rc = run_swd(ctx, P, (const double *)ctx->io_a.p, (const double *)ctx->w_swd.p, B, n,
-                    all_modes, want_eigen, st)))
+  SwdBlocks dblk;
+  if ((rc = make_blocks(ctx, (const double *)ctx->w_swd.p, B, n, sphere ? 1 : 0, dblk, st))) return rc;
+  if ((rc = run_swd(ctx, P, (const double *)ctx->io_a.p, dblk, B, n, all_modes, want_eigen, st)))
     return rc;
   const int nmo = all_modes ? P.nmode : 1;
   const size_t nc = (size_t)B * nT, nk = (size_t)B * nT * n;
@@ -618,6 +646,8 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
     V.periods = (const double *)ctx->io_a.p;
     V.B = B;
     V.n = n;
+    V.blk = dblk;
+    V.fwd = want_kernels ? 0 : 1;
     LAUNCH(swd_export_row_kernel, gridFor(B * nT * n, 256), 256, 0, st, P, 0, V, stale,
            (double *)ctx->io_b.p, want_kernels ? (double *)ctx->io_c.p : nullptr,
            (double *)ctx->io_d.p, (double *)ctx->io_e.p, (double *)ctx->io_f.p);

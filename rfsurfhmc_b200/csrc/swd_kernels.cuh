@@ -61,6 +61,9 @@ __global__ void prep_models_kernel(const double *__restrict__ x, long long B, in
     swd[F_IA * nb + m * B + b] = 1.0 / a32;
     swd[F_IB * nb + m * B + b] = 1.0 / b32;
     swd[F_IRHO * nb + m * B + b] = 1.0 / r32;
+    swd[F_VTP * nb + m * B + b] = 1.0;
+    swd[F_DTP * nb + m * B + b] = 1.0;
+    swd[F_RTP * nb + m * B + b] = 1.0;
   }
   if (rfm) {
     rfm[0 * nb + m * B + b] = thk;
@@ -74,24 +77,90 @@ __global__ void prep_models_kernel(const double *__restrict__ x, long long B, in
   }
 }
 
-// explicit (thk,vp,vs,rho) -> SWD block, for the libsurf drop-in (float32 cast of main.cpp:9,62)
-__global__ void pack_swd_kernel(const double *__restrict__ thk, const double *__restrict__ vp,
-                                const double *__restrict__ vs, const double *__restrict__ rho,
-                                long long B, int n, double *__restrict__ swd) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= B * n) return;
-  const long long b = i % B;
-  const int m = (int)(i / B);
+// ---- earth flattening (sphere=True): build the four flattened model blocks from the flat one.
+// One thread per model (the transform accumulates depth layer by layer).
+//   root blocks: surfdisp96.f `sphere` (:495-564) — float32 arrays, radius 6370, density exponent
+//                -2.275 (Rayleigh) / -5 (Love) applied to the float32 btp;
+//   eig blocks : sregn96.f90 `bldsph` (:133-187, radius 6371, rho*tmp^-2.275) and
+//                slegn96.f90 `bldsph` (:107-167, rho*tmp^-5), float64 on the float32-cast inputs,
+//                plus the factors vtp, dtp, rtp used by sprayl/splove and sregnpu/slegnpu.
+__global__ void prep_sphere_kernel(const double *__restrict__ flat, long long B, int n,
+                                   double *__restrict__ rootR, double *__restrict__ rootL,
+                                   double *__restrict__ eigR, double *__restrict__ eigL) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b >= B) return;
   const long long nb = (long long)n * B;
-  const double d32 = (double)(float)thk[b * n + m], a32 = (double)(float)vp[b * n + m],
-               b32 = (double)(float)vs[b * n + m], r32 = (double)(float)rho[b * n + m];
-  swd[F_D * nb + m * B + b] = d32;
-  swd[F_A * nb + m * B + b] = a32;
-  swd[F_B * nb + m * B + b] = b32;
-  swd[F_RHO * nb + m * B + b] = r32;
-  swd[F_IA * nb + m * B + b] = 1.0 / a32;
-  swd[F_IB * nb + m * B + b] = 1.0 / b32;
-  swd[F_IRHO * nb + m * B + b] = 1.0 / r32;
+  auto at = [&](int f, int m) { return ((long long)f * n + m) * B + b; };
+  // ---- surfdisp96 sphere(): ar = 6370, d(mmax) = 1 while accumulating
+  {
+    const double ar = 6370.0;
+    double dr = 0.0, r0 = ar;
+    for (int i = 0; i < n; i++) {
+      const float d = (i == n - 1) ? 1.0f : (float)flat[at(F_D, i)];
+      const float a = (float)flat[at(F_A, i)], bb = (float)flat[at(F_B, i)], rho = (float)flat[at(F_RHO, i)];
+      dr = dr + (double)d;
+      const double r1 = ar - dr;
+      const double z0 = ar * log(ar / r0), z1 = ar * log(ar / r1);
+      const float dn = (i == n - 1) ? 0.0f : (float)(z1 - z0);
+      const double tmp = (ar + ar) / (r0 + r1);
+      const float an = (float)((double)a * tmp), bn = (float)((double)bb * tmp);
+      const float btp = (float)tmp;
+      const float b5 = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(btp, btp), btp), btp), btp);
+      const float rhoL = __fmul_rn(rho, __fdiv_rn(1.0f, b5));
+      const float rhoR = __fmul_rn(rho, powf(btp, -2.275f));
+      double *dst[2] = {rootR, rootL};
+      const float rr[2] = {rhoR, rhoL};
+      for (int f = 0; f < 2; f++) {
+        double *o = dst[f];
+        o[at(F_D, i)] = (double)dn;
+        o[at(F_A, i)] = (double)an;
+        o[at(F_B, i)] = (double)bn;
+        o[at(F_RHO, i)] = (double)rr[f];
+        o[at(F_IA, i)] = 1.0 / (double)an;
+        o[at(F_IB, i)] = 1.0 / (double)bn;
+        o[at(F_IRHO, i)] = 1.0 / (double)rr[f];
+        o[at(F_VTP, i)] = 1.0;
+        o[at(F_DTP, i)] = 1.0;
+        o[at(F_RTP, i)] = 1.0;
+      }
+      r0 = r1;
+    }
+  }
+  // ---- bldsph (both wave types): ar = 6371, last layer counts 1 km while accumulating
+  {
+    const double ar = 6371.0;
+    double dr = 0.0, r0 = ar;
+    for (int i = 0; i < n; i++) {
+      const double zd = (i == n - 1) ? 1.0 : flat[at(F_D, i)];
+      dr = dr + zd;
+      const double r1 = ar - dr;
+      const double z0 = ar * log(ar / r0), z1 = ar * log(ar / r1);
+      const double tmp = (2.0 * ar) / (r0 + r1);
+      const double dtp = ar / r0;
+      const double rtpR = pow(tmp, (double)(-2.275f));
+      const double t2 = tmp * tmp;
+      const double rtpL = 1.0 / (t2 * t2 * tmp);
+      const double dn = (i == n - 1) ? 0.0 : z1 - z0;
+      const double a = flat[at(F_A, i)] * tmp, bb = flat[at(F_B, i)] * tmp, rho = flat[at(F_RHO, i)];
+      double *dst[2] = {eigR, eigL};
+      const double rt[2] = {rtpR, rtpL};
+      for (int f = 0; f < 2; f++) {
+        double *o = dst[f];
+        o[at(F_D, i)] = dn;
+        o[at(F_A, i)] = a;
+        o[at(F_B, i)] = bb;
+        o[at(F_RHO, i)] = rho * rt[f];
+        o[at(F_IA, i)] = 1.0 / a;
+        o[at(F_IB, i)] = 1.0 / bb;
+        o[at(F_IRHO, i)] = 1.0 / (rho * rt[f]);
+        o[at(F_VTP, i)] = tmp;
+        o[at(F_DTP, i)] = dtp;
+        o[at(F_RTP, i)] = rt[f];
+      }
+      r0 = r1;
+    }
+  }
+  (void)nb;
 }
 
 // ---- K1: one thread per (model, sequence)
@@ -101,7 +170,7 @@ __global__ void pack_swd_kernel(const double *__restrict__ thk, const double *__
 #define RFS_ROOTS_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, RFS_ROOTS_MINBLOCKS)
-    swd_roots_kernel(SwdPlan plan, const double *__restrict__ swd, long long B, int n,
+    swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
                      int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
@@ -110,7 +179,7 @@ __global__ void __launch_bounds__(128, RFS_ROOTS_MINBLOCKS)
   const bool valid = i < B * plan.nseq;
   const long long b = valid ? i % B : 0;
   const int s = valid ? (int)(i / B) : 0;
-  SwdModel M{swd, B, n};
+  SwdModel M{blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n};
   unsigned int nev = 0;
   const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
                                    (long long)plan.nsolve * B, cwork, B, nev, valid,
@@ -130,7 +199,7 @@ __global__ void __launch_bounds__(128, RFS_ROOTS_MINBLOCKS)
 // ugr  : [nmode_out][nsolve][B]     kern : [nmode_out][nsolve][4][n][B]
 template <int NMAX>
 __global__ void __launch_bounds__(128)
-    swd_eigen_kernel(SwdPlan plan, const double *__restrict__ swd, long long B, int n,
+    swd_eigen_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int nmode_out,
                      const double *__restrict__ croot, double *__restrict__ ugr,
                      double *__restrict__ kern) {
@@ -149,7 +218,7 @@ __global__ void __launch_bounds__(128)
   const double T = __ldg(periods + sq.per_off + k) * sq.scale;
   const double c = croot[sv * B + b];
   double *kp = kern + sv * 4 * (long long)n * B + b;
-  SwdModel M{swd, B, n};
+  SwdModel M{blk.eig[sq.ifunc == 2 ? 0 : 1], B, n};
   double u;
   if (!(c > 0.0)) {
     // mode does not exist at this period (reference: c = 0 -> NaN kernels downstream)
@@ -172,33 +241,84 @@ struct SwdView {
   const double *periods;
   long long B;
   int n;
+  SwdBlocks blk;   // eig[f] carries vtp/dtp/rtp when blk.sphere
+  int fwd;         // 1: libsurf.forward semantics (phase velocity through _flat2sphere)
 };
+// sphericity factor tm of sprayl/splove/sregnpu/slegnpu (float32 pi, radius 6371)
+RFS_DEVINL double sph_tm(int love, double t, double c) {
+  const double om = (2.0 * RFS_PI32) / t;
+  const double x = love ? 3.0 * c / (2. * 6371.0 * om) : c / (2. * 6371.0 * om);
+  return sqrt(1. + x * x);
+}
 RFS_DEVINL double swd_row_value(const SwdPlan &plan, const SwdView &V, const SwdRow &rw, int k,
                                 long long b) {
   const int sv0 = plan.seq[rw.s0].out_off + k;
-  if (rw.type == 0 || rw.type == 2) return V.croot[(long long)sv0 * V.B + b];
-  return V.ugr[(long long)sv0 * V.B + b];
+  const double c = V.croot[(long long)sv0 * V.B + b];
+  const int love = rw.type >= 2;
+  if (rw.type == 0 || rw.type == 2) {
+    if (!V.blk.sphere) return c;
+    const double t = V.periods[rw.per_off + k];
+    if (V.fwd) {
+      // _flat2sphere (surfdisp.cpp:16-49): double pi
+      const double om = 2.0 * RFS_PI64 / t;
+      const double x = (love ? 1.5 : 0.5) * c / (6371.0 * om);
+      return c / sqrt(1. + x * x);
+    }
+    return c / sph_tm(love, t, c);  // csph of sprayl / splove
+  }
+  const double u = V.ugr[(long long)sv0 * V.B + b];
+  if (!V.blk.sphere) return u;
+  return u * sph_tm(love, V.periods[rw.per_off + k], c);
 }
 RFS_DEVINL void swd_row_kernels(const SwdPlan &plan, const SwdView &V, const SwdRow &rw, int k,
                                 int m, long long b, int stale, double K[4]) {
   const long long nB = (long long)V.n * V.B;
   const int sv0 = plan.seq[rw.s0].out_off + k;
   const double *k0 = V.kern + (long long)sv0 * 4 * nB + (long long)m * V.B + b;
+  const int love = rw.type >= 2;
+  double fvt = 1.0, frt = 1.0;
+  if (V.blk.sphere) {
+    const double *e = V.blk.eig[love];
+    fvt = e[((long long)F_VTP * V.n + m) * V.B + b];
+    frt = e[((long long)F_RTP * V.n + m) * V.B + b];
+  }
+  const double t = V.periods[rw.per_off + k];
+  const double cp = V.croot[(long long)sv0 * V.B + b];
   if (rw.type == 0 || rw.type == 2) {
     for (int p = 0; p < 4; p++) K[p] = k0[p * nB];
+    if (V.blk.sphere) {
+      // sprayl (sregn96.f90:1619-1626) / splove: kernels of the ORIGINAL spherical model
+      const double tm = sph_tm(love, t, cp);
+      const double i3 = 1.0 / (tm * tm * tm);
+      K[0] = K[0] * fvt * i3;
+      K[1] = K[1] * fvt * i3;
+      K[2] = K[2] * frt * i3;
+      K[3] = K[3] * i3;  // dtp is already inside the suffix sum
+    }
     return;
   }
   const int sv1 = plan.seq[rw.s1].out_off + k, sv2 = plan.seq[rw.s2].out_off + k;
   const double *k1 = V.kern + (long long)sv1 * 4 * nB + (long long)m * V.B + b;
   const double *k2 = V.kern + (long long)sv2 * 4 * nB + (long long)m * V.B + b;
-  const double t = V.periods[rw.per_off + k];
   const double t1 = t * (1.0 + 0.05), t2 = t * (1.0 - 0.05);
-  const double cp = V.croot[(long long)sv0 * V.B + b];
   const double cg = V.ugr[(long long)sv0 * V.B + b];
   const double uc1 = cg / cp;
+  double tm = 1.0, tm1 = 0.0;
+  if (V.blk.sphere) {
+    // sregnpu :1847-1868 / slegnpu :881-899
+    tm = sph_tm(love, t, cp);
+    const double om = (2.0 * RFS_PI32) / t;
+    const double y = (love ? 1.5 : 0.5) / (6371.0 * om);
+    tm1 = y * y / tm;
+  }
   for (int p = 0; p < 4; p++) {
     const double first = stale ? k2[p * nB] : k0[p * nB];
-    K[p] = uc1 * (2.0 - uc1) * first - uc1 * uc1 * t * (k2[p * nB] - k1[p * nB]) / (t2 - t1);
+    double du = uc1 * (2.0 - uc1) * first - uc1 * uc1 * t * (k2[p * nB] - k1[p * nB]) / (t2 - t1);
+    if (V.blk.sphere) {
+      const double f = (p == 2) ? frt : (p == 3 ? 1.0 : fvt);
+      du = (tm * du + cg * cp * k0[p * nB] * tm1) * f;
+    }
+    K[p] = du;
   }
   if (rw.type == 3) K[0] = 0.0;
 }

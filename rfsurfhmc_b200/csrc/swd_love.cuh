@@ -169,7 +169,7 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
     double dfac = fac * kern[(3LL * mmax + k) * ks];
     if (fabs(dfac) < 1.0e-38) dfac = 0.0;
     kern[(3LL * mmax + k) * ks] = suffix;
-    suffix += dfac;
+    suffix += dfac * M.ld(F_DTP, k, b);  // dtp = 1 on a flat earth (splove :660-664 otherwise)
   }
   *ugr_out = ugr;
 }

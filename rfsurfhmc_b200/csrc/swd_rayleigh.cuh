@@ -419,8 +419,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     kern[(2LL * mmax + m) * ks] = kern[(2LL * mmax + m) * ks] / nrm;
     double dfac = fac * kern[(3LL * mmax + m) * ks];
     if (fabs(dfac) < 1.0e-38) dfac = 0.0;
-    kern[(3LL * mmax + m) * ks] = suffix;  // dcdh(i) = sum_{j>i} raw(j); dcdh(mmax) = 0
-    suffix += dfac;
+    kern[(3LL * mmax + m) * ks] = suffix;  // dcdh(i) = sum_{j>i} raw(j) dtp(j); dcdh(mmax) = 0
+    suffix += dfac * M.ld(F_DTP, m, b);     // dtp = 1 on a flat earth (sprayl :1619-1626 otherwise)
   }
   *ugr_out = ugr;
 }

@@ -18,7 +18,18 @@
 namespace rfs {
 
 // field indices of the SWD model block (all values are float32-rounded, stored as double)
-enum { F_D = 0, F_A = 1, F_B = 2, F_RHO = 3, F_IA = 4, F_IB = 5, F_IRHO = 6, SWD_NF = 7 };
+// F_VTP/F_DTP/F_RTP: earth-flattening factors of bldsph (velocity, boundary, density); 1 when flat
+enum { F_D = 0, F_A = 1, F_B = 2, F_RHO = 3, F_IA = 4, F_IB = 5, F_IRHO = 6, F_VTP = 7, F_DTP = 8,
+       F_RTP = 9, SWD_NF = 10 };
+
+// Model blocks of one batch.  Flat earth: all four pointers alias one block.  Spherical earth:
+// root[f] is the model flattened by surfdisp96's `sphere` (float32, radius 6370), eig[f] the one
+// flattened by sregn96/slegn96's `bldsph` (float64, radius 6371); f = 0 Rayleigh, 1 Love.
+struct SwdBlocks {
+  const double *root[2];
+  const double *eig[2];
+  int sphere;
+};
 
 struct SwdModel {
   const double *p;   // [SWD_NF][n][stride]
@@ -81,6 +92,56 @@ RFS_DEVINL double dltar1_dev(double wvno, double omega, const SwdModel &M, long 
 struct VarHalf {
   double c, w, x, ex, e;  // cos-like, sin/r, (+-)r*sin, exponent, exp(-ex)
 };
+// P and S halves evaluated together: the two rsqrt / exp chains are independent straight-line
+// code (no branch between them), which doubles the ILP of the latency-bound inner loop; the
+// oscillatory (c > v) and grazing (c == v) cases are patched afterwards.
+RFS_DEVINL void var_pair(double wvno, double xka, double xkb, double dpth, VarHalf &P, VarHalf &S) {
+  const double x2a = (wvno + xka) * fabs(wvno - xka), x2b = (wvno + xkb) * fabs(wvno - xkb);
+  const double ria = (x2a > 0.0) ? rsqrt(x2a) : 0.0, rib = (x2b > 0.0) ? rsqrt(x2b) : 0.0;
+  const double ra = x2a * ria, rb = x2b * rib;
+  const double pa = ra * dpth, pb = rb * dpth;
+  const double ea = exp(-pa), eb = exp(-pb);
+  const double fa = (pa < 16.0) ? ea * ea : 0.0, fb = (pb < 16.0) ? eb * eb : 0.0;
+  const double sa = (1.0 - fa) * 0.5, sb = (1.0 - fb) * 0.5;
+  P.c = (1.0 + fa) * 0.5;
+  P.w = sa * ria;
+  P.x = ra * sa;
+  P.ex = pa;
+  P.e = ea;
+  S.c = (1.0 + fb) * 0.5;
+  S.w = sb * rib;
+  S.x = rb * sb;
+  S.ex = pb;
+  S.e = eb;
+  if (!(wvno > xka)) {
+    P.ex = 0.0;
+    P.e = 1.0;
+    if (wvno < xka) {
+      double s;
+      sincos(pa, &s, &P.c);
+      P.w = s * ria;
+      P.x = -ra * s;
+    } else {
+      P.c = 1.0;
+      P.w = dpth;
+      P.x = 0.0;
+    }
+  }
+  if (!(wvno > xkb)) {
+    S.ex = 0.0;
+    S.e = 1.0;
+    if (wvno < xkb) {
+      double s;
+      sincos(pb, &s, &S.c);
+      S.w = s * rib;
+      S.x = -rb * s;
+    } else {
+      S.c = 1.0;
+      S.w = dpth;
+      S.x = 0.0;
+    }
+  }
+}
 RFS_DEVINL VarHalf var_half(double wvno, double xk, double x2, double dpth) {
   VarHalf o;
   const double ri = (x2 > 0.0) ? rsqrt(x2) : 0.0;
@@ -145,8 +206,8 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const SwdMo
     const double t = bm * iom;
     const double gammk = 2.0 * t * t;
     const double gam = gammk * wvno2;
-    const VarHalf P = var_half(wvno, xka, (wvno + xka) * fabs(wvno - xka), dpth);
-    const VarHalf S = var_half(wvno, xkb, (wvno + xkb) * fabs(wvno - xkb), dpth);
+    VarHalf P, S;
+    var_pair(wvno, xka, xkb, dpth, P, S);
     const double exa = P.ex + S.ex;
     const double a0 = (exa < 60.0) ? P.e * S.e : 0.0;
     const double cpcq = P.c * S.c, cpy = P.c * S.w, cpz = P.c * S.x, cqw = S.c * P.w,

@@ -4,7 +4,7 @@
 
 Differences by design: invalid `rf_type` / `par_type` raise ValueError (reference: exit(-1),
 main.cpp:36-41,107-111); `kernel_all`'s accidental default rf_type ("P"+docstring, main.cpp:211-212)
-is "P"; method="time" (iterative deconvolution) raises RfsError(RFS_E_UNSUPPORTED) until K5 is built."""
+is "P"."""
 from ..._lib import default_context, rf_type_code, PARTYPES
 
 __doc__ = "Receiver function and partial derivative\n"

@@ -91,8 +91,8 @@ def test_error_conventions(ctx):
         librf.forward(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "freq", 0.001, "Q")
     with pytest.raises(ValueError):
         librf.kernel(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "freq", 0.001, "P", "zz")
-    with pytest.raises(RfsError):  # not built yet: fails loudly instead of falling back
-        libsurf.forward(thk, vp, vs, rho, [5.], "Rc", 0, True)
+    with pytest.raises(RfsError):  # water layers are not built yet: fail loudly, no fallback
+        libsurf.forward(thk, vp, np.array([0.0, 3.5]), rho, [5.], "Rc")
     with pytest.raises(RfsError):  # descending periods are rejected (mode cut-off logic needs ascending)
         libsurf.forward(thk, vp, vs, rho, [8., 5.], "Rc")
 
@@ -267,3 +267,43 @@ def test_time_domain_method_vs_oracle(ctx, oracle):
     assert np.max(np.abs(db - da)) <= TOL_RF * np.max(np.abs(da))
     eg = np.max(np.abs(gb - ga), axis=1) / np.max(np.abs(ga), axis=1)
     assert np.mean(eg <= TOL_G) >= 0.9 and eg.max() < 5e-2   # argmax spike picking can flip on near-ties
+
+
+def test_spherical_earth_vs_oracle(ctx, oracle):
+    """sphere=True: earth-flattening transformation (surfdisp96 `sphere`, bldsph, sprayl/splove,
+    _flat2sphere, spherical branches of sregnpu/slegnpu), drop-ins and fused objective."""
+    g = np.load(os.path.join(G, "f1_dropin.npz"))
+    thk, vs, vp, rho = g["thk"], g["vs"], g["vp"], g["rho"]
+    T = np.array([5., 8., 12., 20., 30., 40., 60.])
+    from rfsurfhmc_b200.model.lib import libsurf
+    for wt in ("Rc", "Rg", "Lc", "Lg"):
+        c0, ok0 = oracle.surf_forward(thk, vp, vs, rho, T, wt, 0, True)
+        c1, ok1 = libsurf.forward(thk, vp, vs, rho, T, wt, 0, True)
+        assert ok0 == ok1 and rel(c1, c0) <= TOL_C, wt
+        r0 = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, wt, 0, True)
+        r1 = libsurf.adjoint_kernel(thk, vp, vs, rho, T, wt, 0, True)
+        assert rel(r1[0], r0[0]) <= TOL_C, wt
+        for i in range(1, 5):
+            s = np.max(np.abs(r0[i]))
+            if s > 0:
+                assert np.max(np.abs(r1[i] - r0[i])) / s <= TOL_G, (wt, i)
+    # sphericity raises long-period phase velocities by a fraction of a percent
+    cf, _ = libsurf.forward(thk, vp, vs, rho, T, "Rc", 0, False)
+    cs, _ = libsurf.forward(thk, vp, vs, rho, T, "Rc", 0, True)
+    d = (cs - cf) / cf
+    assert np.all(np.abs(d) < 0.02) and abs(d[-1]) > abs(d[0])
+    # fused SWD objective on a spherical earth
+    cfg = dict(f1_config(), sphere=True)
+    x0 = f1_true_model()
+    X = perturbed_models(x0, 32, seed=21, rel=0.05)
+    dsw = np.hstack((oracle.surf_forward(thk, vp, vs, rho, cfg["tRc"], "Rc", 0, True)[0],
+                     oracle.surf_forward(thk, vp, vs, rho, cfg["tRg"], "Rg", 0, True)[0]))
+    ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"], sphere=True)
+    ctx.config_obs(dsw)
+    Ub, gb, db, fb = ctx.misfit_grad_host(X, which=2)
+    Ua, ga, da, fa = oracle.joint_batch(X, dsw, cfg, which=2, nthreads=8)
+    assert np.array_equal(fa, fb)
+    assert rel(db[fa], da[fa]) <= TOL_C
+    eg = np.max(np.abs(gb[fa] - ga[fa]), axis=1) / np.max(np.abs(ga[fa]), axis=1)
+    assert eg.max() <= TOL_G
+    ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"], sphere=False)

@@ -153,3 +153,19 @@ def test_group_kernel_identity_and_stale_switch(oracle):
 def test_invalid_wavetype_raises(oracle):
     with pytest.raises(ValueError):
         oracle.surf_forward(THK, VP, VS, RHO, [5.], "Xx")
+
+
+def test_spherical_earth_oracle_sanity(oracle):
+    """sphere=True: flattening is a small, period-growing correction; the phase kernels of the
+    spherical model still satisfy c = sum(vp dc/dvp + vs dc/dvs + h dc/dh) approximately."""
+    T = np.array([5., 10., 20., 40., 80.])
+    for wt in ("Rc", "Lc"):
+        cf, _ = oracle.surf_forward(THK, VP, VS, RHO, T, wt, 0, False)
+        cs, ok = oracle.surf_forward(THK, VP, VS, RHO, T, wt, 0, True)
+        d = (cs - cf) / cf
+        assert ok and np.all(np.abs(d) < 0.03) and abs(d[-1]) > abs(d[0])
+        c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, T, wt, 0, True)
+        assert ok and np.all(np.isfinite(db)) and db.min() > -0.02 and db.max() > 0.1
+    ug, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Rg", 0, True)
+    uf, _ = oracle.surf_forward(THK, VP, VS, RHO, T, "Rg", 0, False)
+    assert ok and np.all(np.abs(ug - uf) / uf < 0.05)
