@@ -141,6 +141,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   const double wvno = omega / c;
   const double wvno2 = wvno * wvno, om2 = omega * omega;
   double cdl[NMAX * 6];  // [m][0..4] = cd, [m][5] = exe   (thread-local, L1-backed)
+  double vsl[NMAX * 10]; // varsv results of the up-sweep, reused by the down-sweep:
+                         // [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S; r < 0 <=> imaginary
 
   // ---------------- up-sweep (:404-492): half-space vector from evalg (:736-768)
   {
@@ -174,6 +176,16 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     const double xka = omega / za, xkb = omega / zb;
     const VSV P = varsv_half(wvno2 - xka * xka, zd);
     const VSV S = varsv_half(wvno2 - xkb * xkb, zd);
+    vsl[m * 10 + 0] = P.c;
+    vsl[m * 10 + 1] = P.rs;
+    vsl[m * 10 + 2] = P.sr;
+    vsl[m * 10 + 3] = P.ex;
+    vsl[m * 10 + 4] = P.imag ? -P.r : P.r;
+    vsl[m * 10 + 5] = S.c;
+    vsl[m * 10 + 6] = S.rs;
+    vsl[m * 10 + 7] = S.sr;
+    vsl[m * 10 + 8] = S.ex;
+    vsl[m * 10 + 9] = S.imag ? -S.r : S.r;
     const Dnk A = dnka_r(P, S, zr, zb, P.ex + S.ex, wvno, wvno2, om2);
     const double d0 = cdl[(m + 1) * 6 + 0], d1 = cdl[(m + 1) * 6 + 1], d2 = cdl[(m + 1) * 6 + 2],
                  d3 = cdl[(m + 1) * 6 + 3], d4 = cdl[(m + 1) * 6 + 4];
@@ -242,8 +254,16 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     }
     kern[(3LL * mmax + m) * ks] = gsum;  // scaled by `fac` in the epilogue
 
-    // ---- E, E^-1 of this layer (evalg :736-768)
-    const cd ra = mk(sa < 0.0, sqrt(fabs(sa))), rb = mk(sb < 0.0, sqrt(fabs(sb)));
+    // ---- E, E^-1 of this layer (evalg :736-768); nu_a, nu_b come from the up-sweep when available
+    cd ra, rb;
+    if (!half) {
+      const double sra = vsl[m * 10 + 4], srb = vsl[m * 10 + 9];
+      ra = mk(sra < 0.0 || (sra == 0.0 && sa < 0.0), fabs(sra));
+      rb = mk(srb < 0.0 || (srb == 0.0 && sb < 0.0), fabs(srb));
+    } else {
+      ra = mk(sa < 0.0, sqrt(fabs(sa)));
+      rb = mk(sb < 0.0, sqrt(fabs(sb)));
+    }
     double gam = zb * wvno / omega;
     gam = 2.0 * (gam * gam);
     const double gamm1 = gam - 1.0;
@@ -259,8 +279,14 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     VSV P, S;
     if (!half) {
       // ---- Haskell step (hska :917-991, down :993-1063)
-      P = varsv_half(sa, zd);
-      S = varsv_half(sb, zd);
+      P.c = vsl[m * 10 + 0];
+      P.rs = vsl[m * 10 + 1];
+      P.sr = vsl[m * 10 + 2];
+      P.ex = vsl[m * 10 + 3];
+      S.c = vsl[m * 10 + 5];
+      S.rs = vsl[m * 10 + 6];
+      S.sr = vsl[m * 10 + 7];
+      S.ex = vsl[m * 10 + 8];
       const double dfac = ((P.ex - S.ex) > 70.0) ? 0.0 : exp(S.ex - P.ex);
       const double cosp = P.c, rsinp = P.rs, sinpr = P.sr;
       const double cossv = dfac * S.c, rsinsv = dfac * S.rs, sinsvr = dfac * S.sr;

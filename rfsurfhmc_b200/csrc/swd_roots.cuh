@@ -173,6 +173,68 @@ RFS_DEVINL VarHalf var_half(double wvno, double xk, double x2, double dpth) {
 // ---- Rayleigh secular function: Dunkin 5-vector compound matrix (surfdisp96.f:791-891).
 // iom = 1/omega (hoisted per period); per-layer reciprocals 1/a, 1/b, 1/rho come from the model
 // block.  Same formulas as dltar4/var/dnka/normc; divisions replaced by reciprocal multiplies.
+struct Dunkin {
+  double c11, c12, c13, c14, c15, c21, c22, c23, c24, c31, c32, c33, c34, c35, c41, c42, c43, c51,
+      c53;
+};
+RFS_DEVINL Dunkin dunkin_layer(const SwdModel &M, long long b, int m, double wvno, double wvno2,
+                               double omega, double iom) {
+  const double bm = M.ld(F_B, m, b);
+  const double dpth = M.ld(F_D, m, b), rho = M.ld(F_RHO, m, b), irho = M.ld(F_IRHO, m, b);
+  const double xka = omega * M.ld(F_IA, m, b), xkb = omega * M.ld(F_IB, m, b);
+  const double t = bm * iom;
+  const double gammk = 2.0 * t * t;
+  const double gam = gammk * wvno2;
+  VarHalf P, S;
+  var_pair(wvno, xka, xkb, dpth, P, S);
+  const double exa = P.ex + S.ex;
+  const double a0 = (exa < 60.0) ? P.e * S.e : 0.0;
+  const double cpcq = P.c * S.c, cpy = P.c * S.w, cpz = P.c * S.x, cqw = S.c * P.w,
+               cqx = S.c * P.x, xy = P.x * S.w, xz = P.x * S.x, wy = P.w * S.w, wz = P.w * S.x;
+  // Dunkin matrix (dnka :1044-1088), unique entries only
+  const double gamm1 = gam - 1.0, twgm1 = gam + gamm1, gmgmk = gam * gammk, gmgm1 = gam * gamm1,
+               gm1sq = gamm1 * gamm1, rho2 = rho * rho, irho2 = irho * irho, a0pq = a0 - cpcq;
+  Dunkin C;
+  C.c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
+  C.c12 = (wvno2 * cpy - cqx) * irho;
+  C.c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * irho;
+  C.c14 = (cpz - wvno2 * cqw) * irho;
+  C.c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * irho2;
+  C.c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
+  C.c22 = cpcq;
+  C.c23 = gammk * cpz - gamm1 * cqw;
+  C.c24 = -wz;
+  C.c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
+  C.c42 = -xy;
+  C.c43 = gamm1 * cpy - gammk * cqx;
+  C.c51 = -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
+  C.c53 = -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
+  const double tt = -2.0 * wvno2;
+  C.c31 = tt * C.c53;
+  C.c32 = tt * C.c43;
+  C.c33 = a0 + 2.0 * (cpcq - C.c11);
+  C.c34 = tt * C.c23;
+  C.c35 = tt * C.c13;
+  return C;
+}
+// e <- normc(e * ca): ee(i) = sum_j e(j) ca(j,i), with ca(2,5)=c14 ca(4,4)=c22 ca(4,5)=c12
+// ca(5,2)=c41 ca(5,4)=c21 ca(5,5)=c11; two partial sums per component shorten the chain
+RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2, double &e3,
+                             double &e4) {
+  const double n0 = (e0 * C.c11 + e1 * C.c21) + (e2 * C.c31 + e3 * C.c41) + e4 * C.c51;
+  const double n1 = (e0 * C.c12 + e1 * C.c22) + (e2 * C.c32 + e3 * C.c42) + e4 * C.c41;
+  const double n2 = (e0 * C.c13 + e1 * C.c23) + (e2 * C.c33 + e3 * C.c43) + e4 * C.c53;
+  const double n3 = (e0 * C.c14 + e1 * C.c24) + (e2 * C.c34 + e3 * C.c22) + e4 * C.c21;
+  const double n4 = (e0 * C.c15 + e1 * C.c14) + (e2 * C.c35 + e3 * C.c12) + e4 * C.c11;
+  double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
+  if (t1 < 1.e-40) t1 = 1.0;
+  const double it1 = 1.0 / t1;
+  e0 = n0 * it1;
+  e1 = n1 * it1;
+  e2 = n2 * it1;
+  e3 = n3 * it1;
+  e4 = n4 * it1;
+}
 RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const SwdModel &M,
                              long long b, int llw) {
   const int mmax = M.n;
@@ -199,56 +261,10 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const SwdMo
     e3 = rho1 * rb;
     e4 = wvno2 - ra * rb;
   }
+  // (forming two layer matrices per trip for more ILP was measured SLOWER: 166 registers or spills)
   for (int m = mmax - 2; m >= llw - 1; m--) {
-    const double bm = M.ld(F_B, m, b);
-    const double dpth = M.ld(F_D, m, b), rho = M.ld(F_RHO, m, b), irho = M.ld(F_IRHO, m, b);
-    const double xka = omega * M.ld(F_IA, m, b), xkb = omega * M.ld(F_IB, m, b);
-    const double t = bm * iom;
-    const double gammk = 2.0 * t * t;
-    const double gam = gammk * wvno2;
-    VarHalf P, S;
-    var_pair(wvno, xka, xkb, dpth, P, S);
-    const double exa = P.ex + S.ex;
-    const double a0 = (exa < 60.0) ? P.e * S.e : 0.0;
-    const double cpcq = P.c * S.c, cpy = P.c * S.w, cpz = P.c * S.x, cqw = S.c * P.w,
-                 cqx = S.c * P.x, xy = P.x * S.w, xz = P.x * S.x, wy = P.w * S.w, wz = P.w * S.x;
-    // Dunkin matrix (dnka :1044-1088), unique entries only
-    const double gamm1 = gam - 1.0, twgm1 = gam + gamm1, gmgmk = gam * gammk, gmgm1 = gam * gamm1,
-                 gm1sq = gamm1 * gamm1, rho2 = rho * rho, irho2 = irho * irho, a0pq = a0 - cpcq;
-    const double c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
-    const double c12 = (wvno2 * cpy - cqx) * irho;
-    const double c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * irho;
-    const double c14 = (cpz - wvno2 * cqw) * irho;
-    const double c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * irho2;
-    const double c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
-    const double c22 = cpcq;
-    const double c23 = gammk * cpz - gamm1 * cqw;
-    const double c24 = -wz;
-    const double c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
-    const double c42 = -xy;
-    const double c43 = gamm1 * cpy - gammk * cqx;
-    const double c51 =
-        -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
-    const double c53 =
-        -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
-    const double tt = -2.0 * wvno2;
-    const double c31 = tt * c53, c32 = tt * c43, c33 = a0 + 2.0 * (cpcq - c11), c34 = tt * c23,
-                 c35 = tt * c13;
-    // ee(i) = sum_j e(j) ca(j,i), with ca(2,5)=c14 ca(4,4)=c22 ca(4,5)=c12 ca(5,2)=c41
-    // ca(5,4)=c21 ca(5,5)=c11; two partial sums per component shorten the dependent chain
-    const double n0 = (e0 * c11 + e1 * c21) + (e2 * c31 + e3 * c41) + e4 * c51;
-    const double n1 = (e0 * c12 + e1 * c22) + (e2 * c32 + e3 * c42) + e4 * c41;
-    const double n2 = (e0 * c13 + e1 * c23) + (e2 * c33 + e3 * c43) + e4 * c53;
-    const double n3 = (e0 * c14 + e1 * c24) + (e2 * c34 + e3 * c22) + e4 * c21;
-    const double n4 = (e0 * c15 + e1 * c14) + (e2 * c35 + e3 * c12) + e4 * c11;
-    double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
-    if (t1 < 1.e-40) t1 = 1.0;
-    const double it1 = 1.0 / t1;
-    e0 = n0 * it1;
-    e1 = n1 * it1;
-    e2 = n2 * it1;
-    e3 = n3 * it1;
-    e4 = n4 * it1;
+    const Dunkin C = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
+    dunkin_apply(C, e0, e1, e2, e3, e4);
   }
   if (llw != 1) {
     // water layer on top (surfdisp96.f:870-886)
