@@ -448,12 +448,12 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
           clow = cc;
           ifirst = 1;
         } else if (k == 0 && iq > 1) {
-          c1 = cwork[(long long)(kb + 0) * stride + b] + one * dc;
+          c1 = cwork[(long long)(sq.out_off + kb + 0) * stride + b] + one * dc;
           clow = c1;
           ifirst = 1;
         } else if (k > 0 && iq > 1) {
           ifirst = 0;
-          clow = cwork[(long long)(kb + k) * stride + b] + one * dc;
+          clow = cwork[(long long)(sq.out_off + kb + k) * stride + b] + one * dc;
           c1 = cprev;
           if (c1 < clow) c1 = clow;
         } else {
@@ -651,7 +651,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     if (iret == 1) {
       double *cq = cout + (all_modes ? (long long)(iq - 1) * cout_mode_stride : 0);
       cprev = c1;
-      if (nmode > 1) cwork[(long long)(kb + k) * stride + b] = c1;
+      if (nmode > 1) cwork[(long long)(sq.out_off + kb + k) * stride + b] = c1;
       cq[(long long)(sq.out_off + kb + k) * stride + b] = (double)(float)c1;  // cg(k)=sngl(c(k))
       k++;
       phase = PH_SETUP;

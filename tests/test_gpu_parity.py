@@ -307,3 +307,44 @@ def test_spherical_earth_vs_oracle(ctx, oracle):
     eg = np.max(np.abs(gb[fa] - ga[fa]), axis=1) / np.max(np.abs(ga[fa]), axis=1)
     assert eg.max() <= TOL_G
     ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"], sphere=False)
+
+
+def test_forty_layer_models_vs_oracle(ctx, oracle):
+    """BASELINE config-2/3 layer count (n=40 -> the NMAX=48 kernel instantiations): fused SWD objective
+    with all four wave types and first higher mode, and fused RF objective, against the oracle."""
+    rng = np.random.default_rng(7)
+    n, B = 40, 12
+    i = np.arange(n - 1)
+    thk = np.hstack((0.5 + 0.1 * i, [0.0]))[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (B, n)))
+    thk[:, -1] = 0.0
+    vs0 = 2.0 + 2.7 * (np.arange(n) / 39.0)**0.7
+    vs = np.clip(vs0[None, :] * (1 + 0.04 * rng.standard_normal((B, n))), 1.5, 5.0)
+    X = np.hstack((vs, thk))
+    T = np.geomspace(2, 100, 24)
+    base = dict(f1_config(), tRc=T, tRg=T, tLc=T, tLg=T, nt=256, dt=0.1, gauss=2.5, ray_p=0.06)
+    for mode in (0, 1):
+        cfg = dict(base, mode=mode)
+        dobs = np.full(96, 3.2)
+        ctx.config_swd(n, T, T, T, T, mode=mode)
+        ctx.config_obs(dobs)
+        Ub, gb, db, fb = ctx.misfit_grad_host(X, which=2)
+        Ua, ga, da, fa = oracle.joint_batch(X, dobs, cfg, which=2, nthreads=8)
+        assert np.array_equal(fa, fb)
+        ok = np.isfinite(da) & (da != 0)
+        assert np.array_equal(np.isfinite(db) & (db != 0), ok)       # same missing-mode pattern
+        assert rel(db[ok], da[ok]) <= TOL_C
+        fin = np.isfinite(ga).all(axis=1)
+        assert np.array_equal(fin, np.isfinite(gb).all(axis=1))      # NaN gradients where a mode is missing
+        if fin.any():
+            eg = np.max(np.abs(gb[fin] - ga[fin]), axis=1) / np.max(np.abs(ga[fin]), axis=1)
+            assert eg.max() <= TOL_G
+    for rft in ("P", "S"):
+        cfg = dict(base, rf_type=rft)
+        ctx.config_rf(n, 0.06, 256, 0.1, 2.5, 5.0, 0.001, rft, "freq")
+        dobs = np.zeros(256)
+        ctx.config_obs(dobs)
+        Ub, gb, db, fb = ctx.misfit_grad_host(X, which=1)
+        Ua, ga, da, fa = oracle.joint_batch(X, dobs, cfg, which=1, nthreads=8)
+        assert np.max(np.abs(db - da)) <= TOL_RF * np.max(np.abs(da))
+        eg = np.max(np.abs(gb - ga), axis=1) / np.max(np.abs(ga), axis=1)
+        assert eg.max() <= TOL_G, rft
