@@ -34,7 +34,7 @@ extern "C" {
 #define RFS_OK 0
 #define RFS_E_CUDA -1      /* CUDA runtime error (message has the detail) */
 #define RFS_E_ARG -2       /* invalid argument (bad wave type / rf type / sizes) */
-#define RFS_E_UNSUPPORTED -3 /* reference feature not built yet (water layers) */
+#define RFS_E_UNSUPPORTED -3 /* reference feature not built (currently unused) */
 #define RFS_E_CONFIG -4    /* context not configured for this call */
 
 typedef struct rfs_ctx rfs_ctx;

@@ -583,9 +583,11 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
   if (n < 2 || nmax_for(n) < 0) return fail(ctx, RFS_E_ARG, "bad layer count");
   if (mode < 0 || mode > 16) return fail(ctx, RFS_E_ARG, "bad mode");
   CK(cudaSetDevice(ctx->device));
-  for (long long i = 0; i < B * n; i++)
-    if (!((float)vs[i] > 0.0f))
-      return fail(ctx, RFS_E_UNSUPPORTED, "water layers (vs<=0) are not built yet");
+  // a fluid layer is accepted at the top of the stack only (surfdisp96.f:138-139 handles b(1)<=0)
+  for (long long b = 0; b < B; b++)
+    for (int m = 1; m < n; m++)
+      if (!((float)vs[b * n + m] > 0.0f))
+        return fail(ctx, RFS_E_ARG, "vs <= 0 is only supported for the top (water) layer");
   SwdPlan P;
   std::vector<double> periods;
   int nts[4] = {0, 0, 0, 0};

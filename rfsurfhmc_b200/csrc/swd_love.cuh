@@ -6,7 +6,7 @@
 //
 // Re-design: the up-sweep keeps (uu,tt,exl) per layer in thread-local memory; the top-down
 // rescale of shfunc, the energy integrals and the dc/dh boundary terms are fused in one pass.
-// Solid layers only.  kern layout: [4][n] with stride ks, order dcda(=0), dcdb, dcdr, dcdh.
+// kern layout: [4][n] with stride ks, order dcda(=0), dcdb, dcdr, dcdh.
 #pragma once
 #include "common.cuh"
 #include "swd_roots.cuh"
@@ -65,7 +65,16 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
     }
     ul[m * 3 + 2] = 0.0;
   }
-  for (int k = mmax - 2; k >= 0; k--) {
+  // fluid layers carry no SH motion: they are skipped everywhere (iwat tests of up/shfunc/energy);
+  // only a contiguous block of water layers at the top is supported (k0 = first solid layer)
+  int k0 = 0;
+  while (k0 < mmax - 1 && !(M.ld(F_B, k0, b) > 0.0)) {
+    ul[k0 * 3 + 0] = 0.0;
+    ul[k0 * 3 + 1] = 0.0;
+    ul[k0 * 3 + 2] = 0.0;
+    k0++;
+  }
+  for (int k = mmax - 2; k >= k0; k--) {
     const double zb = M.ld(F_B, k, b), zr = M.ld(F_RHO, k, b), dpth = M.ld(F_D, k, b);
     const VarL v = varl_dev(zb, omega, wvno, dpth);
     const double mu = zr * zb * zb;
@@ -83,7 +92,7 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
   {
     double ext = 0.0;
     ul[1] = 0.0;
-    for (int k = 1; k < mmax; k++) {
+    for (int k = max(1, k0); k < mmax; k++) {
       ext = ext + ul[(k - 1) * 3 + 2];
       double fact = 0.0;
       if (ext < 80.0) fact = 1. / exp(ext);
@@ -96,7 +105,7 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
         if (fabs(ul[k * 3 + 0]) > fabs(umax)) umax = ul[k * 3 + 0];
     }
     if (fabs(umax) > 0.0) {
-      for (int k = 0; k < mmax; k++) {
+      for (int k = k0; k < mmax; k++) {
         ul[k * 3 + 0] /= umax;
         ul[k * 3 + 1] /= umax;
       }
@@ -106,7 +115,9 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
   const double cph = omega / wvno;
   double sumi0 = 0.0, sumi1 = 0.0, sumi2 = 0.0;
   double zr_prev = 0.0, xmu_prev = 0.0;
-  for (int k = 0; k < mmax; k++) {
+  for (int k = 0; k < k0; k++)
+    for (int p = 0; p < 4; p++) kern[((long long)p * mmax + k) * ks] = 0.0;
+  for (int k = k0; k < mmax; k++) {
     const double zb = M.ld(F_B, k, b), zr = M.ld(F_RHO, k, b), dpth = M.ld(F_D, k, b);
     const double xmu = zr * zb * zb;
     const VarL v = varl_dev(zb, omega, wvno, dpth);
@@ -146,7 +157,7 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
         0.5 * cph * (-cph * cph * upup + zb * zb * upup + zb * zb * dupdup / wvno2);
     // boundary term of dc/dh (:588-607)
     double drho, dmu, dvdz;
-    if (k == 0) {
+    if (k == k0) {
       drho = zr;
       dmu = xmu;
       dvdz = 0.0;

@@ -14,7 +14,7 @@
 //  * the six intijr integrals of a layer are ONE symmetric bilinear form a_i^T W a_j in the
 //    potentials; evalg (E, E^-1) is evaluated once per layer (reference: 6x).
 //  * vertical wavenumbers are real or purely imaginary, so varsv is done in real arithmetic.
-// Solid layers only (water layers: INTEGRATION.md "not yet").
+// Fluid (water) layers follow the iwat branches of dnka / hska / intijr / energy / getdcdh.
 #pragma once
 #include "common.cuh"
 #include "swd_roots.cuh"
@@ -173,9 +173,20 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   for (int m = mmax - 2; m >= 0; m--) {
     const double za = M.ld(F_A, m, b), zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b),
                  zd = M.ld(F_D, m, b);
-    const double xka = omega / za, xkb = omega / zb;
+    const bool wat = !(zb > 0.0);
+    const double xka = omega / za, xkb = wat ? 0.0 : omega / zb;
     const VSV P = varsv_half(wvno2 - xka * xka, zd);
-    const VSV S = varsv_half(wvno2 - xkb * xkb, zd);
+    VSV S;
+    if (wat) {  // fluid layer: no SV wave (varsv :860-880)
+      S.c = 1.0;
+      S.rs = 0.0;
+      S.sr = 0.0;
+      S.ex = 0.0;
+      S.r = 0.0;
+      S.imag = false;
+    } else {
+      S = varsv_half(wvno2 - xkb * xkb, zd);
+    }
     vsl[m * 10 + 0] = P.c;
     vsl[m * 10 + 1] = P.rs;
     vsl[m * 10 + 2] = P.sr;
@@ -186,17 +197,29 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     vsl[m * 10 + 7] = S.sr;
     vsl[m * 10 + 8] = S.ex;
     vsl[m * 10 + 9] = S.imag ? -S.r : S.r;
-    const Dnk A = dnka_r(P, S, zr, zb, P.ex + S.ex, wvno, wvno2, om2);
     const double d0 = cdl[(m + 1) * 6 + 0], d1 = cdl[(m + 1) * 6 + 1], d2 = cdl[(m + 1) * 6 + 2],
                  d3 = cdl[(m + 1) * 6 + 3], d4 = cdl[(m + 1) * 6 + 4];
-    // ee(i) = sum_j cd(m+1,j) ca(j,i); symmetric fill-ins of :620-645
-    //   ca(2,5)=c14 ca(3,4)=-2 c23 ca(3,5)=-2 c13 ca(4,3)=-c32/2 ca(4,4)=c22 ca(4,5)=c12
-    //   ca(5,2)=c41 ca(5,3)=-c31/2 ca(5,4)=c21 ca(5,5)=c11
-    double n0 = d0 * A.c11 + d1 * A.c21 + d2 * A.c31 + d3 * A.c41 + d4 * A.c51;
-    double n1 = d0 * A.c12 + d1 * A.c22 + d2 * A.c32 + d3 * A.c42 + d4 * A.c41;
-    double n2 = d0 * A.c13 + d1 * A.c23 + d2 * A.c33 + d3 * (-A.c32 / 2.0) + d4 * (-A.c31 / 2.0);
-    double n3 = d0 * A.c14 + d1 * A.c24 + d2 * (-2.0 * A.c23) + d3 * A.c22 + d4 * A.c21;
-    double n4 = d0 * A.c15 + d1 * A.c14 + d2 * (-2.0 * A.c13) + d3 * A.c12 + d4 * A.c11;
+    double n0, n1, n2, n3, n4;
+    if (wat) {
+      // fluid compound matrix (dnka :555-572): only 9 non-zero entries
+      const double dfac = (P.ex > 35.0) ? 0.0 : exp(-P.ex);
+      const double ca12 = -P.rs / (zr * om2), ca21 = -zr * P.sr * om2;
+      n0 = d0 * P.c + d1 * ca21;
+      n1 = d0 * ca12 + d1 * P.c;
+      n2 = d2 * dfac;
+      n3 = d3 * P.c + d4 * ca21;
+      n4 = d3 * ca12 + d4 * P.c;
+    } else {
+      const Dnk A = dnka_r(P, S, zr, zb, P.ex + S.ex, wvno, wvno2, om2);
+      // ee(i) = sum_j cd(m+1,j) ca(j,i); symmetric fill-ins of :620-645
+      //   ca(2,5)=c14 ca(3,4)=-2 c23 ca(3,5)=-2 c13 ca(4,3)=-c32/2 ca(4,4)=c22 ca(4,5)=c12
+      //   ca(5,2)=c41 ca(5,3)=-c31/2 ca(5,4)=c21 ca(5,5)=c11
+      n0 = d0 * A.c11 + d1 * A.c21 + d2 * A.c31 + d3 * A.c41 + d4 * A.c51;
+      n1 = d0 * A.c12 + d1 * A.c22 + d2 * A.c32 + d3 * A.c42 + d4 * A.c41;
+      n2 = d0 * A.c13 + d1 * A.c23 + d2 * A.c33 + d3 * (-A.c32 / 2.0) + d4 * (-A.c31 / 2.0);
+      n3 = d0 * A.c14 + d1 * A.c24 + d2 * (-2.0 * A.c23) + d3 * A.c22 + d4 * A.c21;
+      n4 = d0 * A.c15 + d1 * A.c14 + d2 * (-2.0 * A.c13) + d3 * A.c12 + d4 * A.c11;
+    }
     double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
     if (t1 < 1.e-40) t1 = 1.0;
     exsum = exsum + P.ex + S.ex + log(t1);
@@ -216,27 +239,37 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   et.uz = 1.0;
   et.tz = 0.0;
   et.tr = 0.0;
+  // leading water layers (svfunc :318-334): Ur = Tr = 0 at their tops
+  bool lead_water = !(M.ld(F_B, 0, b) > 0.0);
+  if (lead_water) {
+    et.ur = 0.0;
+    et.tr = 0.0;
+  }
   double v0 = 1.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // vv(m,1:4)
   double exa_sum = 0.0;
   double sumi0 = 0.0, sumi1 = 0.0, sumi2 = 0.0, sumi3 = 0.0;
   const double cph = omega / wvno;
   double zr_prev = 0.0, xmu_prev = 0.0, xlam_prev = 0.0;
+  bool wat_prev = false;
   for (int m = 0; m < mmax; m++) {
     const bool half = (m == mmax - 1);
     const double za = M.ld(F_A, m, b), zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b),
                  zd = M.ld(F_D, m, b);
+    const bool wat = !(zb > 0.0);
     const double xmu = zr * zb * zb;
     const double xlam = zr * za * za - 2 * xmu;
-    const double xka = omega / za, xkb = omega / zb;
+    const double xka = omega / za, xkb = wat ? 0.0 : omega / zb;
     const double sa = wvno2 - xka * xka, sb = wvno2 - xkb * xkb;
+    const double rom2 = zr * om2;
 
-    // ---- boundary term of dc/dh at the top of layer m (getdcdh :1436-1535, solid branches)
+    // ---- boundary term of dc/dh at the top of layer m (getdcdh :1436-1535)
     double gsum;
     {
-      const double tur = et.ur, tuz = et.uz, ttz = et.tz, ttr = et.tr;
+      const double tuz = et.uz, ttz = et.tz, ttr = et.tr;
+      const double tur = wat ? -wvno * ttz / rom2 : et.ur;
       const double xl2mp = xlam + xmu + xmu;
       const double duzdzp = (ttz + wvno * xlam * tur) / xl2mp;
-      const double durdzp = (ttr / xmu) - wvno * tuz;
+      const double durdzp = (xmu == 0.0) ? wvno * tuz : (ttr / xmu) - wvno * tuz;
       if (m == 0) {
         const double drho = zr, dmu = xmu, dl2mu = xlam + dmu + dmu;
         gsum = om2 * drho * tuz * tuz + om2 * (tur * tur * drho) - wvno2 * dmu * tuz * tuz -
@@ -245,16 +278,27 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
         const double drho = zr - zr_prev, dmu = xmu - xmu_prev, dlm = xlam - xlam_prev;
         const double dl2mu = dlm + dmu + dmu;
         const double xl2mm = xlam_prev + xmu_prev + xmu_prev;
-        const double durdzm = (ttr / xmu_prev) - wvno * tuz;
-        const double duzdzm = (ttz + wvno * xlam_prev * tur) / xl2mm;
-        gsum = om2 * drho * tuz * tuz + om2 * (tur * tur * drho) - wvno2 * dmu * tuz * tuz -
-               wvno2 * (tur * tur * dl2mu) + (xl2mp * duzdzp * duzdzp - xl2mm * duzdzm * duzdzm) +
+        const double durdzm = (xmu_prev == 0.0) ? wvno * tuz : (ttr / xmu_prev) - wvno * tuz;
+        double drur2, dlur2, duzdzm;
+        if (wat_prev) {
+          // Ur is discontinuous across a fluid boundary (:1497-1510)
+          const double URB = -wvno * ttz / (zr_prev * om2);
+          drur2 = tur * tur * zr - URB * URB * zr_prev;
+          dlur2 = tur * tur * xl2mp - URB * URB * xl2mm;
+          duzdzm = (ttz + wvno * xlam_prev * URB) / (wat ? xl2mm : xlam_prev);
+        } else {
+          drur2 = tur * tur * drho;
+          dlur2 = tur * tur * dl2mu;
+          duzdzm = (ttz + wvno * xlam_prev * tur) / xl2mm;
+        }
+        gsum = om2 * drho * tuz * tuz + om2 * drur2 - wvno2 * dmu * tuz * tuz - wvno2 * dlur2 +
+               (xl2mp * duzdzp * duzdzp - xl2mm * duzdzm * duzdzm) +
                (xmu * durdzp * durdzp - xmu_prev * durdzm * durdzm);
       }
     }
     kern[(3LL * mmax + m) * ks] = gsum;  // scaled by `fac` in the epilogue
 
-    // ---- E, E^-1 of this layer (evalg :736-768); nu_a, nu_b come from the up-sweep when available
+    // ---- nu_a, nu_b of this layer; they come from the up-sweep when available
     cd ra, rb;
     if (!half) {
       const double sra = vsl[m * 10 + 4], srb = vsl[m * 10 + 9];
@@ -264,21 +308,11 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       ra = mk(sa < 0.0, sqrt(fabs(sa)));
       rb = mk(sb < 0.0, sqrt(fabs(sb)));
     }
-    double gam = zb * wvno / omega;
-    gam = 2.0 * (gam * gam);
-    const double gamm1 = gam - 1.0;
-    const double rom2 = zr * om2;
-    const cd ira = cinv(ra), irb = cinv(rb);
-    // EINV rows (acting on [ur, uz, tz, tr])
-    const double ei11 = 0.5 * gam / wvno, ei13 = -0.5 / rom2;
-    const cd ei12 = (-0.5 * gamm1) * ira, ei14 = (0.5 * wvno / rom2) * ira;
-    const cd ei21 = (-0.5 * gamm1) * irb, ei23 = (0.5 * wvno / rom2) * irb;
-    // rows 3,4: EINV(3,:) = [ei11, -ei12, ei13, -ei14]; EINV(4,:) = [-ei21, ei11, -ei23, ei13]
+    const cd ira = cinv(ra);
 
     Eig4 eb = et;  // eigenfunction at the bottom of the layer (top of m+1)
     VSV P, S;
     if (!half) {
-      // ---- Haskell step (hska :917-991, down :993-1063)
       P.c = vsl[m * 10 + 0];
       P.rs = vsl[m * 10 + 1];
       P.sr = vsl[m * 10 + 2];
@@ -287,29 +321,41 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       S.rs = vsl[m * 10 + 6];
       S.sr = vsl[m * 10 + 7];
       S.ex = vsl[m * 10 + 8];
-      const double dfac = ((P.ex - S.ex) > 70.0) ? 0.0 : exp(S.ex - P.ex);
-      const double cosp = P.c, rsinp = P.rs, sinpr = P.sr;
-      const double cossv = dfac * S.c, rsinsv = dfac * S.rs, sinsvr = dfac * S.sr;
-      const float bf = (float)zb;
-      const double gmh = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 / om2;
-      const double gmh1 = gmh - 1.0;
-      const double a11 = cossv + gmh * (cosp - cossv);
-      const double a12 = -wvno * gmh1 * sinpr + gmh * rsinsv / wvno;
-      const double a13 = -wvno * (cosp - cossv) / rom2;
-      const double a14 = (wvno2 * sinpr - rsinsv) / rom2;
-      const double a21 = gmh * rsinp / wvno - wvno * gmh1 * sinsvr;
-      const double a22 = cosp - gmh * (cosp - cossv);
-      const double a23 = (-rsinp + wvno2 * sinsvr) / rom2;
-      const double a24 = -a13;
-      const double a31 = rom2 * gmh * gmh1 * (cosp - cossv) / wvno;
-      const double a32 = rom2 * (-gmh1 * gmh1 * sinpr + gmh * gmh * rsinsv / wvno2);
-      const double a33 = a22, a34 = -a12;
-      const double a41 = rom2 * (gmh * gmh * rsinp / wvno2 - gmh1 * gmh1 * sinsvr);
-      const double a42 = -a31, a43 = -a21, a44 = a11;
-      double w0 = a11 * v0 + a12 * v1 + a13 * v2 + a14 * v3;
-      double w1 = a21 * v0 + a22 * v1 + a23 * v2 + a24 * v3;
-      double w2 = a31 * v0 + a32 * v1 + a33 * v2 + a34 * v3;
-      double w3 = a41 * v0 + a42 * v1 + a43 * v2 + a44 * v3;
+      double w0, w1, w2, w3;
+      if (wat) {
+        // fluid Haskell step (hska :930-944)
+        const double dfac = (P.ex > 35.0) ? 0.0 : exp(-P.ex);
+        const double a23 = -P.rs / rom2, a32 = -rom2 * P.sr;
+        w0 = dfac * v0;
+        w1 = P.c * v1 + a23 * v2;
+        w2 = a32 * v1 + P.c * v2;
+        w3 = dfac * v3;
+      } else {
+        // ---- elastic Haskell step (hska :945-989, down :993-1063)
+        const double dfac = ((P.ex - S.ex) > 70.0) ? 0.0 : exp(S.ex - P.ex);
+        const double cosp = P.c, rsinp = P.rs, sinpr = P.sr;
+        const double cossv = dfac * S.c, rsinsv = dfac * S.rs, sinsvr = dfac * S.sr;
+        const float bf = (float)zb;
+        const double gmh = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 / om2;
+        const double gmh1 = gmh - 1.0;
+        const double a11 = cossv + gmh * (cosp - cossv);
+        const double a12 = -wvno * gmh1 * sinpr + gmh * rsinsv / wvno;
+        const double a13 = -wvno * (cosp - cossv) / rom2;
+        const double a14 = (wvno2 * sinpr - rsinsv) / rom2;
+        const double a21 = gmh * rsinp / wvno - wvno * gmh1 * sinsvr;
+        const double a22 = cosp - gmh * (cosp - cossv);
+        const double a23 = (-rsinp + wvno2 * sinsvr) / rom2;
+        const double a24 = -a13;
+        const double a31 = rom2 * gmh * gmh1 * (cosp - cossv) / wvno;
+        const double a32 = rom2 * (-gmh1 * gmh1 * sinpr + gmh * gmh * rsinsv / wvno2);
+        const double a33 = a22, a34 = -a12;
+        const double a41 = rom2 * (gmh * gmh * rsinp / wvno2 - gmh1 * gmh1 * sinsvr);
+        const double a42 = -a31, a43 = -a21, a44 = a11;
+        w0 = a11 * v0 + a12 * v1 + a13 * v2 + a14 * v3;
+        w1 = a21 * v0 + a22 * v1 + a23 * v2 + a24 * v3;
+        w2 = a31 * v0 + a32 * v1 + a33 * v2 + a34 * v3;
+        w3 = a41 * v0 + a42 * v1 + a43 * v2 + a44 * v3;
+      }
       double t1 = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
       if (t1 < 1.e-40) t1 = 1.0;
       v0 = w0 / t1;
@@ -336,78 +382,115 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       } else {
         eb.ur = eb.uz = eb.tz = eb.tr = 0.0;
       }
+      lead_water = lead_water && wat && !(M.ld(F_B, i, b) > 0.0);
+      if (lead_water) {
+        eb.ur = 0.0;
+        eb.tr = 0.0;
+      }
     }
 
-    // ---- potentials (intijr :1203-1323)
-    // downward coefficients at the top of the layer (rows 3,4 of E^-1), upward at the bottom
-    const cd km1pd = ei11 * et.ur - ei12 * et.uz + ei13 * et.tz - ei14 * et.tr;
-    const cd km1sd = -1.0 * (ei21 * et.ur) + ei11 * et.uz - ei23 * et.tz + ei13 * et.tr;
-    // E columns: E(:,1)=[k, ra, r g1, r g ra/k]  E(:,2)=[rb, k, r g rb/k, r g1]
-    //            E(:,3)=[k,-ra, r g1,-r g ra/k]  E(:,4)=[-rb, k,-r g rb/k, r g1]     (r = rho om^2)
-    const double rg1 = rom2 * gamm1;
-    const cd e41 = (rom2 * gam / wvno) * ra, e32 = (rom2 * gam / wvno) * rb;
-    cd a3[4], a4[4];  // a_i3 = E(i,3) km1pd, a_i4 = E(i,4) km1sd
-    a3[0] = wvno * km1pd;
-    a3[1] = -1.0 * (ra * km1pd);
-    a3[2] = rg1 * km1pd;
-    a3[3] = -1.0 * (e41 * km1pd);
-    a4[0] = -1.0 * (rb * km1sd);
-    a4[1] = wvno * km1sd;
-    a4[2] = -1.0 * (e32 * km1sd);
-    a4[3] = rg1 * km1sd;
-    double I11, I13, I22, I24, I33, I44;
-    if (half) {
-      const cd qa = 0.5 * ira, qb = 0.5 * irb, qab = cinv(ra + rb);
+    if (wat) {
+      // ---- fluid layer: 2x2 potentials (intijr :1246-1266) and energy (energy :1123-1143)
+      const cd kmpu = (0.5 * ira) * eb.uz - (0.5 / rom2) * eb.tz;
+      const cd km1pd = -1.0 * ((0.5 * ira) * et.uz) - (0.5 / rom2) * et.tz;
+      const cd FA = ffunc_d(ra, zd), GA = gfunc_d(ra, zd);
+      const cd pp = kmpu * kmpu * FA + km1pd * km1pd * FA, pm = 2.0 * (kmpu * km1pd * GA);
+      const double I11 = ((ra * ra) * (pp - pm)).x;
+      const double I22 = (rom2 * rom2) * (pp + pm).x;
+      const double a12f = -(wvno2 - om2 / (za * za)) / rom2;
+      const double wq = wvno / rom2;
+      const double URUR = I22 * wq * wq, UZUZ = I11, URDUZ = -wq * a12f * I22,
+                   DUZDUZ = a12f * a12f * I22;
+      const double TA = zr * za * za;
+      sumi0 += zr * (URUR + UZUZ);
+      sumi1 += TA * URUR;
+      sumi2 -= TA * URDUZ;
+      sumi3 += TA * DUZDUZ;
+      const double facah = zr * za * (URUR - 2. * URDUZ / wvno);
+      const double facav = zr * za * DUZDUZ / wvno2;
+      const double facr = -0.5 * cph * cph * (URUR + UZUZ);
+      kern[(0LL * mmax + m) * ks] = facah + facav;
+      kern[(1LL * mmax + m) * ks] = 0.0;  // reference leaves dcdb of a fluid layer unset
+      kern[(2LL * mmax + m) * ks] = 0.5 * (za * facav + za * facah) / zr + facr;
+    } else {
+      // ---- E, E^-1 of this layer (evalg :736-768)
+      double gam = zb * wvno / omega;
+      gam = 2.0 * (gam * gam);
+      const double gamm1 = gam - 1.0;
+      const cd irb = cinv(rb);
+      // EINV rows (acting on [ur, uz, tz, tr])
+      const double ei11 = 0.5 * gam / wvno, ei13 = -0.5 / rom2;
+      const cd ei12 = (-0.5 * gamm1) * ira, ei14 = (0.5 * wvno / rom2) * ira;
+      const cd ei21 = (-0.5 * gamm1) * irb, ei23 = (0.5 * wvno / rom2) * irb;
+      // rows 3,4: EINV(3,:) = [ei11, -ei12, ei13, -ei14]; EINV(4,:) = [-ei21, ei11, -ei23, ei13]
+      // ---- potentials (intijr :1203-1323)
+      // downward coefficients at the top of the layer (rows 3,4 of E^-1), upward at the bottom
+      const cd km1pd = ei11 * et.ur - ei12 * et.uz + ei13 * et.tz - ei14 * et.tr;
+      const cd km1sd = -1.0 * (ei21 * et.ur) + ei11 * et.uz - ei23 * et.tz + ei13 * et.tr;
+      // E columns: E(:,1)=[k, ra, r g1, r g ra/k]  E(:,2)=[rb, k, r g rb/k, r g1]
+      //            E(:,3)=[k,-ra, r g1,-r g ra/k]  E(:,4)=[-rb, k,-r g rb/k, r g1]     (r = rho om^2)
+      const double rg1 = rom2 * gamm1;
+      const cd e41 = (rom2 * gam / wvno) * ra, e32 = (rom2 * gam / wvno) * rb;
+      cd a3[4], a4[4];  // a_i3 = E(i,3) km1pd, a_i4 = E(i,4) km1sd
+      a3[0] = wvno * km1pd;
+      a3[1] = -1.0 * (ra * km1pd);
+      a3[2] = rg1 * km1pd;
+      a3[3] = -1.0 * (e41 * km1pd);
+      a4[0] = -1.0 * (rb * km1sd);
+      a4[1] = wvno * km1sd;
+      a4[2] = -1.0 * (e32 * km1sd);
+      a4[3] = rg1 * km1sd;
+      double I11, I13, I22, I24, I33, I44;
+      if (half) {
+        const cd qa = 0.5 * ira, qb = 0.5 * irb, qab = cinv(ra + rb);
 #define RFS_HS(i, j) \
   ((a3[i] * a3[j]) * qa + (a3[i] * a4[j] + a4[i] * a3[j]) * qab + (a4[i] * a4[j]) * qb).x
-      I11 = RFS_HS(0, 0);
-      I13 = RFS_HS(0, 2);
-      I22 = RFS_HS(1, 1);
-      I24 = RFS_HS(1, 3);
-      I33 = RFS_HS(2, 2);
-      I44 = RFS_HS(3, 3);
+        I11 = RFS_HS(0, 0);
+        I13 = RFS_HS(0, 2);
+        I22 = RFS_HS(1, 1);
+        I24 = RFS_HS(1, 3);
+        I33 = RFS_HS(2, 2);
+        I44 = RFS_HS(3, 3);
 #undef RFS_HS
-    } else {
-      const cd kmpu = ei11 * eb.ur + ei12 * eb.uz + ei13 * eb.tz + ei14 * eb.tr;
-      const cd kmsu = ei21 * eb.ur + ei11 * eb.uz + ei23 * eb.tz + ei13 * eb.tr;
-      cd a1[4], a2[4];
-      a1[0] = wvno * kmpu;
-      a1[1] = ra * kmpu;
-      a1[2] = rg1 * kmpu;
-      a1[3] = e41 * kmpu;
-      a2[0] = rb * kmsu;
-      a2[1] = wvno * kmsu;
-      a2[2] = e32 * kmsu;
-      a2[3] = rg1 * kmsu;
-      const cd FA = ffunc_d(ra, zd), GA = gfunc_d(ra, zd), FB = ffunc_d(rb, zd),
-               GB = gfunc_d(rb, zd), H1 = h1func_d(ra, rb, zd), H2 = h2func_d(ra, rb, zd);
-      // INT_ij = a_i^T W a_j,  W = [[FA,H1,GA,H2],[H1,FB,H2,GB],[GA,H2,FA,H1],[H2,GB,H1,FB]]
+      } else {
+        const cd kmpu = ei11 * eb.ur + ei12 * eb.uz + ei13 * eb.tz + ei14 * eb.tr;
+        const cd kmsu = ei21 * eb.ur + ei11 * eb.uz + ei23 * eb.tz + ei13 * eb.tr;
+        cd a1[4], a2[4];
+        a1[0] = wvno * kmpu;
+        a1[1] = ra * kmpu;
+        a1[2] = rg1 * kmpu;
+        a1[3] = e41 * kmpu;
+        a2[0] = rb * kmsu;
+        a2[1] = wvno * kmsu;
+        a2[2] = e32 * kmsu;
+        a2[3] = rg1 * kmsu;
+        const cd FA = ffunc_d(ra, zd), GA = gfunc_d(ra, zd), FB = ffunc_d(rb, zd),
+                 GB = gfunc_d(rb, zd), H1 = h1func_d(ra, rb, zd), H2 = h2func_d(ra, rb, zd);
+        // INT_ij = a_i^T W a_j,  W = [[FA,H1,GA,H2],[H1,FB,H2,GB],[GA,H2,FA,H1],[H2,GB,H1,FB]]
 #define RFS_WJ(j, b1, b2, b3, b4)                                     \
   const cd b1 = FA * a1[j] + H1 * a2[j] + GA * a3[j] + H2 * a4[j];   \
   const cd b2 = H1 * a1[j] + FB * a2[j] + H2 * a3[j] + GB * a4[j];   \
   const cd b3 = GA * a1[j] + H2 * a2[j] + FA * a3[j] + H1 * a4[j];   \
   const cd b4 = H2 * a1[j] + GB * a2[j] + H1 * a3[j] + FB * a4[j];
 #define RFS_DOT(i, b1, b2, b3, b4) (a1[i] * b1 + a2[i] * b2 + a3[i] * b3 + a4[i] * b4).x
-      {
-        RFS_WJ(0, p1, p2, p3, p4) I11 = RFS_DOT(0, p1, p2, p3, p4);
-      }
-      {
-        RFS_WJ(1, p1, p2, p3, p4) I22 = RFS_DOT(1, p1, p2, p3, p4);
-      }
-      {
-        RFS_WJ(2, p1, p2, p3, p4) I13 = RFS_DOT(0, p1, p2, p3, p4);
-        I33 = RFS_DOT(2, p1, p2, p3, p4);
-      }
-      {
-        RFS_WJ(3, p1, p2, p3, p4) I24 = RFS_DOT(1, p1, p2, p3, p4);
-        I44 = RFS_DOT(3, p1, p2, p3, p4);
-      }
+        {
+          RFS_WJ(0, p1, p2, p3, p4) I11 = RFS_DOT(0, p1, p2, p3, p4);
+        }
+        {
+          RFS_WJ(1, p1, p2, p3, p4) I22 = RFS_DOT(1, p1, p2, p3, p4);
+        }
+        {
+          RFS_WJ(2, p1, p2, p3, p4) I13 = RFS_DOT(0, p1, p2, p3, p4);
+          I33 = RFS_DOT(2, p1, p2, p3, p4);
+        }
+        {
+          RFS_WJ(3, p1, p2, p3, p4) I24 = RFS_DOT(1, p1, p2, p3, p4);
+          I44 = RFS_DOT(3, p1, p2, p3, p4);
+        }
 #undef RFS_WJ
 #undef RFS_DOT
-    }
-
-    // ---- energy integrals and un-normalised partials (energy :1065-1201, getmat :1537-1589)
-    {
+      }
+      // ---- energy integrals and un-normalised partials (energy :1144-1183, getmat :1537-1589)
       const double TL = zr * zb * zb, TC = zr * za * za, TA = TC, TF = TA - 2. * TL;
       const double a12 = -wvno, a14 = 1.0 / TL, a21 = wvno * TF / TC, a23 = 1.0 / TC;
       const double URUR = I11, UZUZ = I22;
@@ -431,6 +514,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     zr_prev = zr;
     xmu_prev = xmu;
     xlam_prev = xlam;
+    wat_prev = wat;
   }
   (void)sumi3;
   // ---------------- epilogue: U, normalisation, boundary -> thickness suffix sums

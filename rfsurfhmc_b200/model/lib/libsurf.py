@@ -3,7 +3,7 @@ module (/root/reference/src/SWD/main.cpp:84-94), computed by the sm_100a kernels
 C ABI (include/rfsurfhmc.h: rfs_surf_forward / rfs_surf_adjoint_kernel).
 
 Differences by design: an invalid `wavetype` raises ValueError (the reference prints and calls
-exit(0), main.cpp:19-25); water layers (vs<=0) raise RfsError(RFS_E_UNSUPPORTED) until built;
+exit(0), main.cpp:19-25); a fluid layer is accepted only at the top of the stack;
 Love `dcda` is returned as zeros (the reference returns uninitialised memory, main.cpp:68)."""
 import numpy as np
 from ..._lib import default_context, wavetype_code

@@ -91,8 +91,9 @@ def test_error_conventions(ctx):
         librf.forward(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "freq", 0.001, "Q")
     with pytest.raises(ValueError):
         librf.kernel(thk, rho, vp, vs, q, q, 0.05, 64, 0.2, 2.0, 3.0, "freq", 0.001, "P", "zz")
-    with pytest.raises(RfsError):  # water layers are not built yet: fail loudly, no fallback
-        libsurf.forward(thk, vp, np.array([0.0, 3.5]), rho, [5.], "Rc")
+    with pytest.raises(RfsError):  # a fluid layer below the top is rejected loudly
+        libsurf.forward(np.array([5., 5., 0.]), np.array([5., 1.5, 6.]), np.array([3., 0.0, 3.5]),
+                        np.array([2.5, 1.0, 2.8]), [5.], "Rc")
     with pytest.raises(RfsError):  # descending periods are rejected (mode cut-off logic needs ascending)
         libsurf.forward(thk, vp, vs, rho, [8., 5.], "Rc")
 
@@ -348,3 +349,31 @@ def test_forty_layer_models_vs_oracle(ctx, oracle):
         assert np.max(np.abs(db - da)) <= TOL_RF * np.max(np.abs(da))
         eg = np.max(np.abs(gb - ga), axis=1) / np.max(np.abs(ga), axis=1)
         assert eg.max() <= TOL_G, rft
+
+
+def test_water_layer_on_top_vs_oracle(ctx, oracle):
+    """Ocean model: fluid top layer (vs = 0): root search with the water-layer term of dltar4, fluid
+    branches of the Rayleigh eigen kernels, Love ignoring the fluid; plus the scaling identities."""
+    thk = np.array([3.0, 2.0, 5.0, 12.0, 0.0])
+    vs = np.array([0.0, 2.2, 3.3, 3.9, 4.6])
+    vp = np.array([1.5, 4.2, 5.9, 6.8, 8.1])
+    rho = np.array([1.03, 2.3, 2.7, 2.9, 3.3])
+    T = np.array([6., 10., 15., 25., 40.])
+    from rfsurfhmc_b200.model.lib import libsurf
+    for wt in ("Rc", "Rg", "Lc", "Lg"):
+        c0, ok0 = oracle.surf_forward(thk, vp, vs, rho, T, wt)
+        c1, ok1 = libsurf.forward(thk, vp, vs, rho, T, wt)
+        assert ok0 == ok1 and rel(c1, c0) <= TOL_C, wt
+        r0 = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, wt)
+        r1 = libsurf.adjoint_kernel(thk, vp, vs, rho, T, wt)
+        assert rel(r1[0], r0[0]) <= TOL_C, wt
+        for i in range(1, 5):
+            s = np.max(np.abs(r0[i]))
+            if s > 0:
+                assert np.max(np.abs(r1[i] - r0[i])) / s <= TOL_G, (wt, i)
+    c, da, db, dr, dh, ok = libsurf.adjoint_kernel(thk, vp, vs, rho, T, "Rc")
+    v32 = lambda a: a.astype(np.float32).astype(np.float64)
+    euler = (da * v32(vp)).sum(1) + (db * v32(vs)).sum(1) + (dh * v32(thk)).sum(1)
+    assert np.max(np.abs(euler - c) / c) < 1e-4       # homogeneity incl. the water layer's vp and h
+    assert np.max(np.abs((dr * v32(rho)).sum(1))) < 3e-4
+    assert np.all(db[:, 0] == 0.0)

@@ -169,3 +169,22 @@ def test_spherical_earth_oracle_sanity(oracle):
     ug, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Rg", 0, True)
     uf, _ = oracle.surf_forward(THK, VP, VS, RHO, T, "Rg", 0, False)
     assert ok and np.all(np.abs(ug - uf) / uf < 0.05)
+
+
+def test_water_layer_oracle_identities(oracle):
+    """The fluid branches of the restated sregn96 satisfy the scaling identities; Love ignores water."""
+    thk = np.array([3.0, 2.0, 5.0, 12.0, 0.0])
+    vs = np.array([0.0, 2.2, 3.3, 3.9, 4.6])
+    vp = np.array([1.5, 4.2, 5.9, 6.8, 8.1])
+    rho = np.array([1.03, 2.3, 2.7, 2.9, 3.3])
+    T = np.array([6., 10., 15., 25., 40.])
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, "Rc")
+    assert ok and np.all(c > 1.0)
+    v32 = lambda a: a.astype(np.float32).astype(np.float64)
+    euler = (da * v32(vp)).sum(1) + (db * v32(vs)).sum(1) + (dh * v32(thk)).sum(1)
+    assert np.max(np.abs(euler - c) / c) < 1e-4
+    assert np.max(np.abs((dr * v32(rho)).sum(1))) < 3e-4
+    # Love waves do not see the water: same as the model without the top layer
+    cl, okl = oracle.surf_forward(thk, vp, vs, rho, T, "Lc")
+    cs, oks = oracle.surf_forward(thk[1:], vp[1:], vs[1:], rho[1:], T, "Lc")
+    assert okl and oks and np.allclose(cl, cs, rtol=2e-6)
