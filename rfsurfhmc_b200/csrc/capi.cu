@@ -211,7 +211,8 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
   if ((rc = ensure(ctx, ctx->w_croot, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_cwork, sizeof(double) * (size_t)P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
-  LAUNCH(swd_roots_kernel, gridFor(B * P.nseq, 128), 128, 0, st, P, d_swd, B, n, d_periods,
+  LAUNCH(swd_roots_kernel, gridFor(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd, B, n,
+         d_periods,
          all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
          (int *)ctx->w_ierr.p,
          ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr);

@@ -169,12 +169,15 @@ __global__ void prep_sphere_kernel(const double *__restrict__ flat, long long B,
 #ifndef RFS_ROOTS_MINBLOCKS
 #define RFS_ROOTS_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, RFS_ROOTS_MINBLOCKS)
+#ifndef RFS_ROOTS_BLOCK
+#define RFS_ROOTS_BLOCK 128
+#endif
+__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
     swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
                      int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
-  __shared__ double wsm_all[4][33];
+  __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool valid = i < B * plan.nseq;
   const long long b = valid ? i % B : 0;
