@@ -105,7 +105,8 @@ int rfs_rf_kernel_all(rfs_ctx *ctx, long long B, int n, const double *thk, const
 
 /* ---- device-resident HMC (replaces the Python loops of pyhmc/hmc.py:140-276 and
  *      pyhmc/hmcda.py:170-369; chain i uses NumPy-legacy MT19937 seeded with seed+chain_id[i]) ---
- * sampler: 0 HamitonianMC (fixed dt, L ~ randint[Lmin,Lmax]), 1 HMCDualAveraging (L0, target).
+ * sampler: 0 HamitonianMC (fixed dt, L ~ randint[Lmin,Lmax]), 1 HMCDualAveraging (L0, target;
+ *          Lmax > 0 caps L = max(1,int(lambda/dt)) — an extension, 0 = unlimited as the reference).
  * bounds [2n][2] (low, high), shared by all chains (host pointer).
  * Outputs (host pointers, may be NULL): samples [C][nsamples][2n], misfit [C][nsamples],
  * syn [C][nsamples][ndata], initmodel [C][2n], n_iter [C] (trajectories run), n_acc [C],

@@ -54,6 +54,7 @@ struct rfs_ctx {
   Buf d_dobs;
   // ---- workspace (grown on demand, never shrunk)
   Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
+  Buf w_rstat;
   Buf w_swd, w_rfm, w_chain, w_qa, w_qb, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
       w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
@@ -216,6 +217,14 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
          all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
          (int *)ctx->w_ierr.p,
          ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr);
+  // per-period retries of failed fundamental-mode searches (rare; idle warps exit at once)
+  if ((rc = ensure(ctx, ctx->w_rstat, sizeof(int) * (size_t)P.nsolve * B))) return rc;
+  LAUNCH(swd_retry_kernel, gridFor(B * P.nsolve, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd,
+         B, n, d_periods, all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
+         (const int *)ctx->w_ierr.p, (int *)ctx->w_rstat.p,
+         ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr);
+  LAUNCH(swd_retry_finish_kernel, gridFor(B * P.nseq, 128), 128, 0, st, P, B, all_modes ? 1 : 0,
+         (double *)ctx->w_croot.p, (int *)ctx->w_ierr.p, (const int *)ctx->w_rstat.p);
   if (!want_eigen) return RFS_OK;
   if ((rc = ensure(ctx, ctx->w_ugr, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_kern, sizeof(double) * (size_t)nmo * P.nsolve * 4 * n * B)))
@@ -390,7 +399,7 @@ void rfs_destroy(rfs_ctx *ctx) {
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
                 &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state, &ctx->h_rng,
                 &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out,  &ctx->d_counter, &ctx->w_sph[0], &ctx->w_sph[1],
-                &ctx->w_sph[2],  &ctx->w_sph[3]};
+                &ctx->w_sph[2],  &ctx->w_sph[3], &ctx->w_rstat};
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -455,6 +455,10 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
         const double q = cfg.lambda / dt;
         L = (q >= 2147483647.0) ? 2147483647 : (int)q;
         if (L < 1) L = 1;
+        // extension (off when Lmax = 0): cap the trajectory length.  The reference lets L explode
+        // (L = int(lambda/dt) ~ 4e5 after one rejected warm-up trajectory because gamma = 0.05);
+        // with thousands of chains some chain always hits that and the run never ends.
+        if (cfg.Lmax > 0 && L > cfg.Lmax) L = cfg.Lmax;
       }
       D.L[c] = L;
       double K = 0.0;

@@ -194,8 +194,11 @@ RFS_DEVINL cd nan0(cd z) { return (isnan(z.x) || isnan(z.y)) ? cd(0.0, 0.0) : z;
 //  dspec: [B][NQ*n][n2] complex  D = R22_m R21 - R21_m R22
 //         NQ==4: rows rho,vp,vs,h (kernel_all order);  NQ==2: rows vs-chain, thk
 //  sigma: imaginary part of omega is -sigma (freq method) or 0 (time method)
+#ifndef RFS_RF_MINBLOCKS
+#define RFS_RF_MINBLOCKS 2
+#endif
 template <int NMAX, int NQ>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
     rf_propagate_kernel(const double *__restrict__ rfm, const double *__restrict__ chain,
                         const double *__restrict__ qa, const double *__restrict__ qb, long long B,
                         int n, int n2, int nft, double dt, double ray_p, double sigma,

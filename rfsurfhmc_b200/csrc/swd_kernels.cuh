@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
   unsigned int nev = 0;
   const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
                                    (long long)plan.nsolve * B, cwork, B, nev, valid,
-                                   wsm_all[threadIdx.x >> 5]);
+                                   wsm_all[threadIdx.x >> 5], -1);
   if (valid) ierr[(long long)s * B + b] = e;
   if (neval_total) {
     // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
@@ -198,10 +198,88 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
   }
 }
 
+// ---- per-period retries of _surfdisp (surfdisp.cpp:93-100): when the fundamental mode failed in
+// the main pass, every period whose reported value is zero / NaN is searched again as a fresh
+// single-period problem (start value cc, scan upward in dc steps: hundreds of evaluations).
+// The reference does these one after the other and stops at the first one that fails again; the
+// jobs are independent, so they run here as one thread per (model, sequence, period) — in a warp
+// that is otherwise idle, whose 31 spare lanes take over the look-ahead scan — and
+// swd_retry_finish_kernel re-imposes the sequential stop rule.
+//   rstat [nsolve][B] int: -1 not retried, 0 retried ok, 1 retried and failed again
+__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
+    swd_retry_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
+                     const double *__restrict__ periods, int all_modes,
+                     double *__restrict__ croot, double *__restrict__ cwork,
+                     const int *__restrict__ ierr, int *__restrict__ rstat,
+                     unsigned long long *__restrict__ neval_total) {
+  __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool inrange = i < B * plan.nsolve;
+  const long long b = inrange ? i % B : 0;
+  const int solve = inrange ? (int)(i / B) : 0;
+  int s = 0;
+  for (int q = 0; q < plan.nseq; q++)
+    if (solve >= plan.seq[q].out_off && solve < plan.seq[q].out_off + plan.seq[q].nper) s = q;
+  const int k = solve - plan.seq[s].out_off;
+  bool valid = false;
+  if (inrange && ierr[(long long)s * B + b] != 0) {
+    const double *clast = croot + (all_modes ? (long long)(plan.nmode - 1) * plan.nsolve * B : 0);
+    const double v = clast[(long long)solve * B + b];
+    valid = (v == 0.0 || isnan(v));
+  }
+  // whole warps without work leave (the warp-cooperative loop needs all 32 lanes of a live warp)
+  if (__ballot_sync(0xffffffffu, valid) == 0u) {
+    if (inrange) rstat[(long long)solve * B + b] = -1;
+    return;
+  }
+  SwdModel M{blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n};
+  unsigned int nev = 0;
+  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
+                                   wsm_all[threadIdx.x >> 5], k);
+  if (inrange) rstat[(long long)solve * B + b] = valid ? e : -1;
+  if (neval_total) {
+    unsigned int w = nev;
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
+  }
+}
+
+// sequential stop rule of the retry loop: `if(ierr !=0) return ierr;` leaves the later periods
+// un-retried (zero) and reports failure; otherwise ierr is that of the last retry (0).
+__global__ void swd_retry_finish_kernel(SwdPlan plan, long long B, int all_modes,
+                                        double *__restrict__ croot, int *__restrict__ ierr,
+                                        const int *__restrict__ rstat) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * plan.nseq) return;
+  const long long b = i % B;
+  const int s = (int)(i / B);
+  if (ierr[(long long)s * B + b] == 0) return;
+  const SwdSeq sq = plan.seq[s];
+  double *clast = croot + (all_modes ? (long long)(plan.nmode - 1) * plan.nsolve * B : 0);
+  int e = 1;  // ierr stays 1 if nothing was retried (cannot happen: a failed period is zero)
+  bool stopped = false;
+  for (int k = 0; k < sq.nper; k++) {
+    const long long o = (long long)(sq.out_off + k) * B + b;
+    const int r = rstat[o];
+    if (r < 0) continue;
+    if (stopped) {
+      clast[o] = 0.0;  // the reference never retried this period
+      continue;
+    }
+    e = r;
+    if (r != 0) stopped = true;
+  }
+  ierr[(long long)s * B + b] = e;
+}
+
 // ---- K2: one thread per (model, solve=(sequence,period)[, mode])
 // ugr  : [nmode_out][nsolve][B]     kern : [nmode_out][nsolve][4][n][B]
+#ifndef RFS_EIGEN_MINBLOCKS
+#define RFS_EIGEN_MINBLOCKS 3
+#endif
 template <int NMAX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RFS_EIGEN_MINBLOCKS)
     swd_eigen_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int nmode_out,
                      const double *__restrict__ croot, double *__restrict__ ugr,

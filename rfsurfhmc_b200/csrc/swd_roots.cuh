@@ -316,11 +316,11 @@ enum { PH_SETUP = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE, PH_DONE };
 // Solve all modes 1..nmode of sequence `sq` for model b.
 //  cout  : [nmode_out][nper][stride] float32-rounded roots (0 where a mode does not exist)
 //  cwork : [nper][stride] unrounded roots of the running mode (chain state), used when nmode > 1
-// returns ierr (1 = fundamental mode not found, even after the per-period retry).
+// returns ierr of this job (1 = fundamental mode not found).
 //
-// The job loop (main pass + per-period retries of surfdisp.cpp:93-100), the mode loop, the period
-// loop, getsol and nevill are ONE loop whose body performs exactly one secular evaluation:
-// lanes never wait for each other at period or mode boundaries.
+// The mode loop, the period loop, getsol and nevill are ONE loop whose body performs exactly one
+// secular evaluation: lanes never wait for each other at period or mode boundaries.  The per-period
+// retries of _surfdisp (surfdisp.cpp:93-100) are separate single-period jobs (swd_retry_kernel).
 //
 // Warp-cooperative tail: rare models need 5-10x more evaluations than the rest (upward scans from
 // the floor velocity in the per-period retries).  All 32 lanes of a warp stay in the loop until
@@ -331,7 +331,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
                                   const double *__restrict__ periods, int nmode, int all_modes,
                                   double *__restrict__ cout, long long cout_mode_stride,
                                   double *__restrict__ cwork, long long stride,
-                                  unsigned int &n_evals, bool valid, double *wsm) {
+                                  unsigned int &n_evals, bool valid, double *wsm, int only_k) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int mmax = M.n;
@@ -369,9 +369,9 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
   const double twopi = 2.0 * RFS_PI64;
 
   // ---- loop-nest state (job / mode / period)
-  int ierr = 0;
-  int kb = 0, jk = kmax;  // current job covers periods [kb, kb+jk)
-  int retry_k = -1;       // <0: main pass; else next period index to examine for a retry
+  // only_k < 0: the main pass over all periods; only_k >= 0: the single-period job with which
+  // _surfdisp retries a period whose result was zero (surfdisp.cpp:93-100, run by swd_retry_kernel)
+  int kb = (only_k < 0) ? 0 : only_k, jk = (only_k < 0) ? kmax : 1;  // job = periods [kb, kb+jk)
   int iq = 1, k = 0, ift = 999, job_ierr = 0;
   double cprev = 0.0, del1st = 0.0;
   // ---- root-search state (getsol / nevill)
@@ -401,43 +401,9 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
           k = 0;
           continue;
         }
-        if (iq > nmode) {
-          // ---- job finished: emulate _surfdisp's retry of zero periods when ierr != 0
-          bool stop = false;
-          if (retry_k < 0) {
-            if (job_ierr == 0) {
-              stop = true;
-            } else {
-              ierr = 1;
-              retry_k = 0;
-            }
-          } else {
-            ierr = job_ierr;
-            if (job_ierr != 0) stop = true;  // `if(ierr !=0) return ierr;`
-          }
-          int kn = -1;
-          if (!stop) {
-            const double *clast = cout + (all_modes ? (long long)(nmode - 1) * cout_mode_stride : 0);
-            for (int i = retry_k; i < kmax; i++) {
-              const double v = clast[(long long)(sq.out_off + i) * stride + b];
-              if (v == 0.0 || isnan(v)) {
-                kn = i;
-                break;
-              }
-            }
-          }
-          if (stop || kn < 0) {
-            phase = PH_DONE;
-            break;
-          }
-          kb = kn;
-          jk = 1;
-          retry_k = kn + 1;
-          iq = 1;
-          k = 0;
-          ift = 999;
-          job_ierr = 0;
-          continue;
+        if (iq > nmode) {  // job finished
+          phase = PH_DONE;
+          break;
         }
         // ---- start values of (iq, k) (surfdisp96.f:257-276)
         const double t1 = __ldg(periods + sq.per_off + kb + k) * sq.scale;
@@ -666,7 +632,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     }
     if (nhelp) __syncwarp();  // wsm may be rewritten in the next trip
   }
-  return ierr;
+  return job_ierr;
 }
 
 }  // namespace rfs

@@ -27,6 +27,7 @@ class HMCDualAveraging:
         self.outdir = outdir
         self.delta = target_ratio
         self.max_iters = 0
+        self.max_L = 0   # extension: cap on L = max(1, int(lambda/dt)); 0 = unlimited (reference)
         self.last = None
 
     @classmethod
@@ -38,7 +39,8 @@ class HMCDualAveraging:
     def sample_chains(self, chain_ids, want_syn=True, log_accepts=0, save=False):
         n = self.boundaries.shape[0] // 2
         ctx = self.model.device_context(n)
-        out = ctx.hmc_run(1, chain_ids, self.boundaries, self.dt, L0=self.L, target_ratio=self.delta,
+        out = ctx.hmc_run(1, chain_ids, self.boundaries, self.dt, Lrange=(1, self.max_L), L0=self.L,
+                          target_ratio=self.delta,
                           seed=self._base_seed, nsamples=self.nsamples, ndraws=self.ndraws,
                           max_iters=self.max_iters, want_samples=True, want_syn=want_syn,
                           log_accepts=log_accepts)
