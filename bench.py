@@ -37,13 +37,23 @@ def workload(nchains, seed):
 
 
 def make_dobs(cfg, x0):
-    """Observations = synthetics of the true model (main_base.py:49-56), computed by the oracle
-    on the CPU (test infrastructure used as data generator, not on the timed path)."""
+    """CPU arm only: observations = synthetics of the true model (main_base.py:49-56) from the
+    oracle, which is the implementation that arm measures."""
     from oracle.oracle import Oracle
     O = Oracle()
     nd = cfg["nt"] + len(cfg["tRc"]) + len(cfg["tRg"])
     _, _, d, _ = O.joint_batch(x0[None, :], np.zeros(nd), cfg)
     return d[0]
+
+
+def make_dobs_gpu(ctx, cfg, x0):
+    """Our arm: observations = synthetics of the true model computed by the CUDA path itself, as
+    the reference driver does with its own forward model (main_base.py:49-56)."""
+    nd = cfg["nt"] + len(cfg["tRc"]) + len(cfg["tRg"])
+    ctx.config_obs(np.zeros(nd))
+    _, _, d, f = ctx.misfit_grad_host(x0[None, :])
+    assert f[0]
+    return d[0].copy()
 
 
 class ClockSampler(threading.Thread):
@@ -162,12 +172,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.chains
     cfg, x0, _ = workload(1, 0)
-    dobs = make_dobs(cfg, x0)
-    nd = dobs.size
     ctx = Context(local_rank)
     ctx.config_swd(N_LAYERS, tRc=cfg["tRc"], tRg=cfg["tRg"])
     ctx.config_rf(N_LAYERS, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"],
                   cfg["water"], cfg["rf_type"], cfg["method"])
+    dobs = make_dobs_gpu(ctx, cfg, x0)
+    nd = dobs.size
     ctx.config_obs(dobs)
     nrot = 4
     Xs = [workload(B, 1000 + 97 * rank + i)[2] for i in range(nrot)]

@@ -1,4 +1,4 @@
-"""Print GPU-vs-oracle error statistics (run on a GPU box: `python tools/gpu_parity_report.py`)."""
+"""Print GPU-vs-oracle error statistics (run on a GPU box: `python tests/gpu_parity_report.py`)."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

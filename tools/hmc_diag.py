@@ -4,11 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from rfsurfhmc_b200._lib import Context
 from rfsurfhmc_b200.fixtures import *
-from bench import make_dobs, workload
+from bench import make_dobs_gpu, workload
 cfg, x0, X0 = workload(16384, 5)
-dobs = make_dobs(cfg, x0)
 ctx = Context(0)
-ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"]); ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], cfg["rf_type"], cfg["method"]); ctx.config_obs(dobs)
+ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"]); ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], cfg["rf_type"], cfg["method"]); dobs = make_dobs_gpu(ctx, cfg, x0); ctx.config_obs(dobs)
 def timeit(X, label):
     ctx.misfit_grad_host(X)
     ctx.count_evals(True)

@@ -4,13 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from rfsurfhmc_b200._lib import Context
 from rfsurfhmc_b200.fixtures import *
-from bench import make_dobs, workload
+from bench import make_dobs_gpu, workload
 nch = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 max_iters = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
 cfg, x0, _ = workload(1, 0)
-dobs = make_dobs(cfg, x0)
 ctx = Context(0)
-ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"]); ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], cfg["rf_type"], cfg["method"]); ctx.config_obs(dobs)
+ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"]); ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], cfg["rf_type"], cfg["method"]); dobs = make_dobs_gpu(ctx, cfg, x0); ctx.config_obs(dobs)
 b = driver_bounds(x0)
 for sampler, kw in ((0, dict(dt=0.1, Lrange=(5, 20))), (1, dict(dt=0.1, L0=10, target_ratio=0.65))):
     t0 = time.time()
