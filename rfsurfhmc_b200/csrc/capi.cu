@@ -386,6 +386,11 @@ int rfs_create(rfs_ctx **out, int device) {
     return RFS_E_CUDA;
   }
   if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
+  // workspace budget per chunk of the fused path (MiB); batches larger than what fits are chunked
+  if (const char *e = getenv("RFS_WS_BUDGET_MB")) {
+    const long long mb = atoll(e);
+    if (mb > 0) ctx->ws_budget = (size_t)mb << 20;
+  }
   *out = ctx;
   return RFS_OK;
 }
@@ -474,7 +479,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t pm = per_model_bytes(ctx, which);
-  long long Bmax = (long long)std::max<size_t>(1024, ctx->ws_budget / pm);
+  long long Bmax = (long long)std::max<size_t>(32, ctx->ws_budget / pm);
   const double *d_dobs = (const double *)ctx->d_dobs.p;
   double tshift = ctx->tshift;
   if (ctx->rf_type == 2) tshift = -tshift;  // src/RF/main.cpp:35
