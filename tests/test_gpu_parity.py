@@ -439,3 +439,32 @@ def test_two_hundred_layer_models_vs_oracle(ctx, oracle):
     assert fin.sum() >= 2 and np.isfinite(gb).all()
     eg = np.max(np.abs(gb[fin] - ga[fin]), axis=1) / np.max(np.abs(ga[fin]), axis=1)
     assert eg.max() <= TOL_G
+
+
+def test_host_pipeline_matches_blocking_api(ctx):
+    """rfsurfhmc_b200.batched.HostPipeline (the e2e path of bench.py) returns, batch by batch, exactly
+    what the blocking host API returns."""
+    import torch
+    from rfsurfhmc_b200.batched import HostPipeline
+    cfg = f1_config()
+    x0 = f1_true_model()
+    dobs = np.load(os.path.join(G, "f1_joint.npz"))["dobs"]
+    _joint_ctx(ctx, dobs, cfg)
+    B = 96
+    batches = [sorted_uniform_models(driver_bounds(x0), B, seed=300 + i) for i in range(5)]
+    ref = [ctx.misfit_grad_host(X) for X in batches]
+    pipe = HostPipeline(cfg, dobs, 7, B, device=0)
+    got = []
+    for X in batches:
+        done = pipe.submit(torch.from_numpy(X).pin_memory())
+        if done is not None:
+            got.append([t.numpy().copy() for t in done])
+    # two slots: the last two batches are still in flight
+    pipe.slots[pipe.i % 2]["event"].synchronize()
+    s = pipe.slots[pipe.i % 2]
+    got.append([s[k].numpy().copy() for k in ("Uh", "Gh", "Dh", "Fh")])
+    got.append([t.numpy().copy() for t in pipe.drain()])
+    assert len(got) == 5
+    for (U, g, d, f), (U2, g2, d2, f2) in zip(ref, got):
+        assert np.array_equal(U, U2) and np.array_equal(g, g2) and np.array_equal(d, d2)
+        assert np.array_equal(f, f2.astype(bool))

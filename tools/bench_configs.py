@@ -106,7 +106,40 @@ def cpu_leg():
                       "models_per_s": len(Xr) / t3, "sample": "%d models" % len(Xr)}))
 
 
+def c5_leg(B):
+    """C5: fine parameterisation joint evaluation (n=200, 128 Rc + 128 Rg periods, nt=4096)."""
+    n = 200
+    rng = np.random.default_rng(5)
+    thk = 0.4 * (1 + 0.1 * rng.uniform(-1, 1, (B, n)))
+    thk[:, -1] = 0.0
+    vs0 = 2.0 + 2.7 * (np.arange(n) / (n - 1.0))**0.7
+    vs = np.clip(vs0[None, :] * (1 + 0.04 * rng.standard_normal((B, n))), 1.5, 5.0)
+    X = np.hstack((vs, thk))
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(X).to(dev)
+    T = np.geomspace(1, 150, 128)
+    nt = 4096
+    ctx = Context(0)
+    ctx.config_swd(n, T, T)
+    ctx.config_rf(n, 0.06, nt, 0.025, 2.5, 5.0, 1e-3, "P", "freq")
+    nd = nt + 256
+    ctx.config_obs(np.hstack((np.zeros(nt), np.full(256, 3.3))))
+    U = torch.empty(B, dtype=torch.float64, device=dev)
+    G = torch.empty(B, 2 * n, dtype=torch.float64, device=dev)
+    D = torch.empty(B, nd, dtype=torch.float64, device=dev)
+    Fl = torch.empty(B, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    t = timed(lambda: ctx.misfit_grad_dev(B, xd.data_ptr(), 0, U.data_ptr(), G.data_ptr(), D.data_ptr(),
+                                          Fl.data_ptr(), st), reps=1)
+    print(json.dumps({"config": "C5 joint evaluation: n=200, 128 Rc + 128 Rg periods, nt=4096", "batch": B,
+                      "evals_per_s": B / t, "seconds": t, "failed": int((Fl == 0).sum().item()),
+                      "finite_grad_fraction": float(torch.isfinite(G).all(dim=1).float().mean().item())}))
+
+
 if __name__ == "__main__":
+    if "--c5" in sys.argv:
+        c5_leg(int(sys.argv[sys.argv.index("--c5") + 1]))
+        sys.exit(0)
     if "--cpu" in sys.argv:
         cpu_leg()
     main()
