@@ -55,12 +55,12 @@ struct rfs_ctx {
   // ---- workspace (grown on demand, never shrunk)
   Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
   Buf w_rstat;
-  Buf w_swd, w_rfm, w_chain, w_qa, w_qb, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
+  Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
       w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
   // ---- HMC
   long long hmc_evals = 0;
-  Buf h_state, h_rng, h_misc, h_x, h_p, h_out;
+  Buf h_state, h_misc, h_out;
   size_t ws_budget = (size_t)24 << 30;  // workspace budget per chunk (bytes)
   Buf d_counter;                 // [0] secular-function evaluations (algorithmic-work counter)
   bool count_evals = false;
@@ -398,12 +398,12 @@ int rfs_create(rfs_ctx **out, int device) {
 void rfs_destroy(rfs_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain, &ctx->w_qa,
-                &ctx->w_qb,      &ctx->w_croot, &ctx->w_cwork, &ctx->w_ugr, &ctx->w_kern, &ctx->w_ierr,
+  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain,
+                &ctx->w_croot, &ctx->w_cwork, &ctx->w_ugr, &ctx->w_kern, &ctx->w_ierr,
                 &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
-                &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state, &ctx->h_rng,
-                &ctx->h_misc,    &ctx->h_x,     &ctx->h_p,    &ctx->h_out,  &ctx->d_counter, &ctx->w_sph[0], &ctx->w_sph[1],
+                &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state,
+                &ctx->h_misc,    &ctx->h_out,  &ctx->d_counter, &ctx->w_sph[0], &ctx->w_sph[1],
                 &ctx->w_sph[2],  &ctx->w_sph[3], &ctx->w_rstat};
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);

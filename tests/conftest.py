@@ -11,6 +11,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def native_artifacts():
+    """Compile the CUDA library (nvcc cross-compiles without a GPU) and the oracle if they are not
+    there yet, so that the suite also runs on a fresh checkout."""
+    import __graft_entry__ as entry
+    if not os.path.exists(entry.LIB):
+        entry.build()
+    from oracle import oracle as orc
+    orc.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle.oracle import Oracle
