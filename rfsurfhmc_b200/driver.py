@@ -21,7 +21,7 @@ from .fixtures import driver_bounds
 from . import distributed as D
 
 
-def run(param, sampler="base", nchains=4, save_chains=True):
+def run(param, sampler="base", nchains=4, save_chains=True, max_iters=0, max_L=0):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -53,6 +53,9 @@ def run(param, sampler="base", nchains=4, save_chains=True):
     boundaries = driver_bounds(x)
     cls = HamitonianMC if sampler == "base" else HMCDualAveraging
     chain = cls.init(model, boundaries, 0, **param['hmc'])
+    chain.max_iters = int(max_iters)  # 0 = unbounded, as the reference's `while True` loops
+    if sampler == "da":
+        chain.max_L = int(max_L)      # 0 = the reference's uncapped L = int(lambda/dt)
     ids = D.shard_chains(nchains)
     out = chain.sample_chains(ids, want_syn=save_chains, save=save_chains)
     misfit = D.gather_chains(out["misfit"], nchains)
@@ -68,11 +71,21 @@ def main():
     ap.add_argument("--sampler", default="base", choices=["base", "da"])
     ap.add_argument("--chains", type=int, default=4)
     ap.add_argument("--no-chain-files", action="store_true")
+    ap.add_argument("--outdir", default=None, help="override hmc.OUTPUT_DIR of the parameter file")
+    ap.add_argument("--nsamples", type=int, default=None, help="override hmc.nsamples")
+    ap.add_argument("--ndraws", type=int, default=None, help="override hmc.ndraws")
+    ap.add_argument("--max-iters", type=int, default=0,
+                    help="stop a chain after this many trajectories (0 = unbounded, as the reference)")
+    ap.add_argument("--max-L", type=int, default=0,
+                    help="dual averaging only: cap on leapfrog steps per trajectory (0 = uncapped)")
     a = ap.parse_args()
     with open(a.param, "r") as f:
         param = yaml.safe_load(f)
+    for key, val in (("OUTPUT_DIR", a.outdir), ("nsamples", a.nsamples), ("ndraws", a.ndraws)):
+        if val is not None:
+            param['hmc'][key] = val
     tic = time.time()
-    misfit, n_iter, _ = run(param, a.sampler, a.chains, not a.no_chain_files)
+    misfit, n_iter, _ = run(param, a.sampler, a.chains, not a.no_chain_files, a.max_iters, a.max_L)
     if int(os.environ.get("RANK", "0")) == 0:
         print("chains %d, accepted samples %d, mean accept ratio %.3f" %
               (misfit.shape[0], misfit.size, (misfit.shape[1] + param['hmc']['ndraws']) / n_iter.mean()))
