@@ -55,6 +55,7 @@ struct rfs_ctx {
   // ---- workspace (grown on demand, never shrunk)
   Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
   Buf w_rstat;
+  Buf w_rfl;  // RfLayer table [B][n]
   Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
       w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
@@ -209,6 +210,9 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
             long long B, int n, bool all_modes, bool want_eigen, cudaStream_t st) {
   const int nmo = all_modes ? P.nmode : 1;
   int rc;
+  // the kernels index the model block with 32-bit element offsets (SwdModel::ld)
+  if ((long long)SWD_NF * n * B > 2147483647LL)
+    return fail(ctx, RFS_E_ARG, "SWD batch too large: 10*layers*models must stay below 2^31 per call");
   if ((rc = ensure(ctx, ctx->w_croot, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_cwork, sizeof(double) * (size_t)P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
@@ -255,11 +259,15 @@ int run_rf_spectra(rfs_ctx *ctx, const double *d_rfm, const double *d_chain, con
   if (nq > 0)
     if ((rc = ensure(ctx, ctx->w_dspec, sizeof(double2) * (size_t)B * nq * n * n2))) return rc;
   double2 *dsp = nq > 0 ? (double2 *)ctx->w_dspec.p : nullptr;
+  // frequency-independent layer constants, once per (model, layer)
+  if ((rc = ensure(ctx, ctx->w_rfl, sizeof(RfLayer) * (size_t)B * n))) return rc;
+  LAUNCH(rf_layer_kernel, gridFor(B * n, 128), 128, 0, st, d_rfm, d_qa, d_qb, B, n, ctx->ray_p,
+         (RfLayer *)ctx->w_rfl.p);
   const long long tot = B * n2;
-#define PROP(NM, NQ)                                                                           \
-  LAUNCH((rf_propagate_kernel<NM, NQ>), gridFor(tot, 128), 128, 0, st, d_rfm, d_chain, d_qa,   \
-         d_qb, B, n, n2, ctx->nft, ctx->dt, ctx->ray_p, sigma, pi_used, ctx->rf_type,          \
-         (double2 *)ctx->w_spec.p, dsp)
+#define PROP(NM, NQ)                                                                             \
+  LAUNCH((rf_propagate_kernel<NM, NQ>), gridFor(tot, 128), 128, 0, st,                           \
+         (const RfLayer *)ctx->w_rfl.p, d_chain, B, n, n2, ctx->nft, ctx->dt, ctx->ray_p, sigma, \
+         pi_used, ctx->rf_type, (double2 *)ctx->w_spec.p, dsp)
 #define PROPQ(NM)    \
   if (nq == 2) {     \
     PROP(NM, 2);     \
@@ -353,7 +361,7 @@ size_t per_model_bytes(const rfs_ctx *ctx, int which) {
                            (size_t)P.nsolve * 4 * ctx->n_swd) + sizeof(int) * P.nseq;
   }
   if (which != 2 && ctx->has_rf) {
-    s += sizeof(double) * (6 * (size_t)ctx->n_rf) +
+    s += sizeof(double) * (6 * (size_t)ctx->n_rf) + sizeof(RfLayer) * (size_t)ctx->n_rf +
          sizeof(double2) * ((size_t)2 * ctx->n2 + (size_t)2 * ctx->n_rf * ctx->n2) +
          sizeof(double) * (1 + 2 * (size_t)ctx->n_rf);
     if (ctx->method == 0)
@@ -398,7 +406,7 @@ int rfs_create(rfs_ctx **out, int device) {
 void rfs_destroy(rfs_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain,
+  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain, &ctx->w_rfl,
                 &ctx->w_croot, &ctx->w_cwork, &ctx->w_ugr, &ctx->w_kern, &ctx->w_ierr,
                 &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
@@ -480,6 +488,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   cudaStream_t st = (cudaStream_t)stream;
   const size_t pm = per_model_bytes(ctx, which);
   long long Bmax = (long long)std::max<size_t>(32, ctx->ws_budget / pm);
+  Bmax = std::min(Bmax, 2147483647LL / ((long long)SWD_NF * n));  // 32-bit offsets in SwdModel::ld
   const double *d_dobs = (const double *)ctx->d_dobs.p;
   double tshift = ctx->tshift;
   if (ctx->rf_type == 2) tshift = -tshift;  // src/RF/main.cpp:35

@@ -49,11 +49,16 @@ RFS_DEVINL void scale10(M10 &M, cd s) {
   M.m41 = M.m41 * s;
 }
 
-// frequency-independent layer constants
+// frequency-independent layer constants; computed once per (model, layer) by rf_layer_kernel and
+// read (warp-broadcast, L1-resident) by every frequency bin instead of being re-derived per bin
 struct RfLayer {
   cd alpha, beta, miu, gamma, gamma1, va_k, vb_k;
+  // reciprocals used by the layer matrices and their derivatives
+  cd ialpha, ibeta, ivak, ivbk, imu2, g3, g2, ivak2;  // 1/alpha 1/beta 1/va_k 1/vb_k 1/(2mu) 1/(g-2) g/(alpha p)^2 1/va_k^2
+  cd bvs, avp;                                        // beta/vs, alpha/vp (complex -> real velocity factors)
   double thick, rho, vp, vs;
 };
+static_assert(sizeof(RfLayer) == 38 * sizeof(double), "RfLayer is read as 19 double2");
 RFS_DEVINL RfLayer rf_layer(double thick, double rho, double vp, double vs, double qa, double qb,
                             double p) {
   RfLayer L;
@@ -69,40 +74,91 @@ RFS_DEVINL RfLayer rf_layer(double thick, double rho, double vp, double vs, doub
   L.gamma1 = 1.0 - cinv(L.gamma);
   L.va_k = csqrt(p * p - cinv(L.alpha * L.alpha)) / p;
   L.vb_k = csqrt(p * p - cinv(b2)) / p;
+  L.ialpha = cinv(L.alpha);
+  L.ibeta = cinv(L.beta);
+  L.ivak = cinv(L.va_k);
+  L.ivbk = cinv(L.vb_k);
+  L.imu2 = cinv(2.0 * L.miu);
+  L.g3 = cinv(L.gamma - 2.0);
+  const cd ap = L.alpha * p;
+  L.g2 = L.gamma * cinv(ap * ap);
+  L.ivak2 = cinv(L.va_k * L.va_k);
+  L.bvs = L.beta / vs;
+  L.avp = L.alpha / vp;
+  return L;
+}
+// one thread per (model, layer): rfm [4][n][B] thk, rho, vp, vs -> tab [B][n] RfLayer
+__global__ void rf_layer_kernel(const double *__restrict__ rfm, const double *__restrict__ qa,
+                                const double *__restrict__ qb, long long B, int n, double ray_p,
+                                RfLayer *__restrict__ tab) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * n) return;
+  const long long b = i % B;
+  const int m = (int)(i / B);
+  const long long nB = (long long)n * B;
+  const double qam = qa ? qa[m * B + b] : 9999.0, qbm = qb ? qb[m * B + b] : 9999.0;
+  tab[b * n + m] = rf_layer(rfm[0 * nB + m * B + b], rfm[1 * nB + m * B + b],
+                            rfm[2 * nB + m * B + b], rfm[3 * nB + m * B + b], qam, qbm, ray_p);
+}
+RFS_DEVINL RfLayer rf_layer_ld(const RfLayer *__restrict__ tab, long long idx) {
+  RfLayer L;
+  const double2 *src = reinterpret_cast<const double2 *>(tab + idx);
+  double2 *dst = reinterpret_cast<double2 *>(&L);
+#pragma unroll
+  for (int j = 0; j < 19; j++) dst[j] = __ldg(src + j);
   return L;
 }
 
 struct RfTrig {
   cd c_a, x_a, y_a, c_b, x_b, y_b;
+  cd v_a, v_b;  // vertical wavenumbers (reused by the derivative pass)
 };
 RFS_DEVINL void ccoshsinh(cd z, cd &ch, cd &sh) {
   // cosh(x+iy) = cosh x cos y + i sinh x sin y ; sinh(x+iy) = sinh x cos y + i cosh x sin y
   double s, c;
   sincos(z.y, &s, &c);
-  const double chx = cosh(z.x), shx = sinh(z.x);
+  // one exponential for cosh and sinh; sinh by its series below 0.5 (no cancellation)
+  const double ax = fabs(z.x);
+  const double e = exp_cb(fmin(ax, 700.0)), ei = 1.0 / e;
+  const double chx = 0.5 * (e + ei);
+  double shx;
+  if (ax < 0.5) {
+    const double x2 = ax * ax;
+    double q = fma(x2, 1.6059043836821613e-10, 2.5052108385441720e-08);  // 1/13!, 1/11!
+    q = fma(x2, q, 2.7557319223985893e-06);                              // 1/9!
+    q = fma(x2, q, 1.9841269841269841e-04);                              // 1/7!
+    q = fma(x2, q, 8.3333333333333332e-03);                              // 1/5!
+    q = fma(x2, q, 1.6666666666666666e-01);                              // 1/3!
+    shx = fma(ax * x2, q, ax);
+  } else {
+    shx = 0.5 * (e - ei);
+  }
+  shx = copysign(shx, z.x);
   ch = cd(chx * c, shx * s);
   sh = cd(shx * c, chx * s);
 }
 RFS_DEVINL void rf_trig(const RfLayer &L, cd omega, double p, cd &k, cd &v_alpha, cd &v_beta,
                         RfTrig &t) {
   k = omega * p;
-  const cd k_alpha = omega / L.alpha, k_beta = omega / L.beta;
+  const cd k_alpha = omega * L.ialpha, k_beta = omega * L.ibeta;
   v_alpha = csqrt(k * k - k_alpha * k_alpha);
   v_beta = csqrt(k * k - k_beta * k_beta);
   cd ch, sh;
   ccoshsinh(v_alpha * L.thick, ch, sh);
   t.c_a = ch;
   t.x_a = L.va_k * sh;
-  t.y_a = sh / L.va_k;
+  t.y_a = sh * L.ivak;
   ccoshsinh(v_beta * L.thick, ch, sh);
   t.c_b = ch;
   t.x_b = L.vb_k * sh;
-  t.y_b = sh / L.vb_k;
+  t.y_b = sh * L.ivbk;
+  t.v_a = v_alpha;
+  t.v_b = v_beta;
 }
 
 // cal_matrix_a (:709-764)
 RFS_DEVINL void rf_mat_a(const RfLayer &L, const RfTrig &t, M10 &A) {
-  const cd g1 = L.gamma1, mu2 = 2.0 * L.miu, imu2 = cinv(mu2);
+  const cd g1 = L.gamma1, mu2 = 2.0 * L.miu, imu2 = L.imu2;
   A.m11 = t.c_a - g1 * t.c_b;
   A.m12 = g1 * t.y_a - t.x_b;
   A.m13 = (t.c_b - t.c_a) * imu2;
@@ -122,10 +178,10 @@ RFS_DEVINL void rf_mat_a_par(const RfLayer &L, const RfTrig &t, cd k, cd v_alpha
   const cd g = L.gamma, g1 = L.gamma1, miu = L.miu;
   const cd kt = k * L.thick;
   if (ipar == 3) {
-    const cd g3 = cinv(g - 2.0);
-    const cd ib = cinv(L.beta);
+    const cd g3 = L.g3;
+    const cd ib = L.ibeta;
     const cd ktcb_p = kt * t.c_b + t.y_b, ktcb_m = kt * t.c_b - t.y_b, ktyb = kt * t.y_b;
-    const cd imb = cinv(miu) * ib;
+    const cd imb = (2.0 * L.imu2) * ib;
     D.m11 = (2.0 * ib) * (g * (t.c_a - t.c_b) - g1 * ktyb);
     D.m12 = (2.0 * ib) * (g * (t.y_a - t.x_b) - ktcb_p);
     D.m13 = ktyb * imb;
@@ -136,14 +192,13 @@ RFS_DEVINL void rf_mat_a_par(const RfLayer &L, const RfTrig &t, cd k, cd v_alpha
     D.m31 = (4.0 * miu * ib) * ((2.0 * g - 1.0) * (t.c_a - t.c_b) - g1 * ktyb);
     D.m32 = (4.0 * miu * ib) * ((2.0 * g) * (g1 * t.y_a - t.x_b) - ktcb_p);
     D.m41 = (4.0 * miu * g * ib) * (2.0 * g1 * t.y_b - 2.0 * t.x_a + g1 * g1 * g3 * ktcb_m);
-    scale10(D, L.beta / L.vs);
+    scale10(D, L.bvs);
   } else if (ipar == 2) {
-    const cd ap = L.alpha * p;
-    const cd g2 = g * cinv(ap * ap);
-    const cd ia = cinv(L.alpha);
-    const cd ivak2 = cinv(L.va_k * L.va_k);
+    const cd g2 = L.g2;
+    const cd ia = L.ialpha;
+    const cd ivak2 = L.ivak2;
     const cd ktya = kt * t.y_a, ktca_m = kt * t.c_a - t.y_a, ktca_p = kt * t.c_a + t.y_a;
-    const cd i2m = cinv(2.0 * miu);
+    const cd i2m = L.imu2;
     D.m11 = ktya * g2 * ia;
     D.m12 = ivak2 * ia * g1 * g2 * ktca_m;
     D.m13 = -1.0 * (ktya * g2 * i2m * ia);
@@ -154,9 +209,9 @@ RFS_DEVINL void rf_mat_a_par(const RfLayer &L, const RfTrig &t, cd k, cd v_alpha
     D.m31 = ktya * g1 * g2 * (2.0 * miu) * ia;
     D.m32 = (2.0 * miu * ia) * (g1 * g1) * g2 * ktca_m * ivak2;
     D.m41 = -1.0 * ((2.0 * miu * ia) * ktca_p * g2);
-    scale10(D, L.alpha / L.vp);
+    scale10(D, L.avp);
   } else if (ipar == 1) {
-    const cd f = -1.0 * (g * cinv((2.0 * L.rho) * miu));
+    const cd f = -1.0 * (g * L.imu2) / L.rho;
     const cd h = (2.0 / L.rho) * (miu * g);
     D.m11 = cd(0.0);
     D.m12 = cd(0.0);
@@ -169,7 +224,7 @@ RFS_DEVINL void rf_mat_a_par(const RfLayer &L, const RfTrig &t, cd k, cd v_alpha
     D.m32 = h * (g1 * g1 * t.y_a - t.x_b);
     D.m41 = h * (g1 * g1 * t.y_b - t.x_a);
   } else {
-    const cd i2m = cinv(2.0 * miu), mu2 = 2.0 * miu;
+    const cd i2m = L.imu2, mu2 = 2.0 * miu;
     const cd vbb = v_beta * L.vb_k, vaa = v_alpha * L.va_k;
     D.m11 = (t.x_a - g1 * t.x_b) * k;
     D.m12 = g1 * k * t.c_a - vbb * t.c_b;
@@ -199,9 +254,8 @@ RFS_DEVINL cd nan0(cd z) { return (isnan(z.x) || isnan(z.y)) ? cd(0.0, 0.0) : z;
 #endif
 template <int NMAX, int NQ>
 __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
-    rf_propagate_kernel(const double *__restrict__ rfm, const double *__restrict__ chain,
-                        const double *__restrict__ qa, const double *__restrict__ qb, long long B,
-                        int n, int n2, int nft, double dt, double ray_p, double sigma,
+    rf_propagate_kernel(const RfLayer *__restrict__ tab, const double *__restrict__ chain,
+                        long long B, int n, int n2, int nft, double dt, double ray_p, double sigma,
                         double pi_used, int rf_type, double2 *__restrict__ spec,
                         double2 *__restrict__ dspec) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -222,18 +276,16 @@ __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
   cd l[4];
   {
     const int m = n - 1;
-    const double qam = qa ? qa[m * B + b] : 9999.0, qbm = qb ? qb[m * B + b] : 9999.0;
-    const RfLayer L = rf_layer(rfm[0 * nB + m * B + b], rfm[1 * nB + m * B + b],
-                               rfm[2 * nB + m * B + b], rfm[3 * nB + m * B + b], qam, qbm, p);
-    const cd hg = 0.5 * L.gamma, i2m = cinv(2.0 * L.miu);
+    const RfLayer L = rf_layer_ld(tab, b * n + m);
+    const cd hg = 0.5 * L.gamma, i2m = L.imu2;
     if (row == 0) {
-      const cd iv = cinv(L.va_k);
+      const cd iv = L.ivak;
       l[0] = -1.0 * hg;
       l[1] = -1.0 * (hg * L.gamma1 * iv);
       l[2] = hg * i2m;
       l[3] = hg * i2m * iv;
     } else {
-      const cd iv = cinv(L.vb_k);
+      const cd iv = L.ivbk;
       l[0] = hg * L.gamma1 * iv;
       l[1] = hg;
       l[2] = -1.0 * (hg * i2m * iv);
@@ -242,9 +294,7 @@ __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
   }
   // ---- bottom-up: store l_j, then l <- l A_j
   for (int m = n - 2; m >= 0; m--) {
-    const double qam = qa ? qa[m * B + b] : 9999.0, qbm = qb ? qb[m * B + b] : 9999.0;
-    const RfLayer L = rf_layer(rfm[0 * nB + m * B + b], rfm[1 * nB + m * B + b],
-                               rfm[2 * nB + m * B + b], rfm[3 * nB + m * B + b], qam, qbm, p);
+    const RfLayer L = rf_layer_ld(tab, b * n + m);
     cd k, va, vb;
     RfTrig t;
     rf_trig(L, omega, p, k, va, vb, t);
@@ -281,15 +331,12 @@ __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
   cd r1[4] = {cd(0.0), cd(1.0), cd(0.0), cd(0.0)};
   double2 *dout = dspec + (b * (long long)(NQ * n)) * n2 + kf;
   for (int m = 0; m < n; m++) {
-    const double qam = qa ? qa[m * B + b] : 9999.0, qbm = qb ? qb[m * B + b] : 9999.0;
-    const RfLayer L = rf_layer(rfm[0 * nB + m * B + b], rfm[1 * nB + m * B + b],
-                               rfm[2 * nB + m * B + b], rfm[3 * nB + m * B + b], qam, qbm, p);
+    const RfLayer L = rf_layer_ld(tab, b * n + m);
     const cd k = omega * p;
-    const cd k_alpha = omega / L.alpha, k_beta = omega / L.beta;
-    const cd va = csqrt(k * k - k_alpha * k_alpha), vb = csqrt(k * k - k_beta * k_beta);
     cd dR[4][2];  // per parameter (rho, vp, vs, h): derivative of (a(row,1), a(row,2))
     if (m < n - 1) {
       const RfTrig t = Ts[m];
+      const cd va = t.v_a, vb = t.v_b;
       cd lj[4] = {Ls[m * 4 + 0], Ls[m * 4 + 1], Ls[m * 4 + 2], Ls[m * 4 + 3]};
 #pragma unroll
       for (int q = 1; q <= 4; q++) {
@@ -315,6 +362,8 @@ __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
       r1[3] = o[3];
     } else {
       // half-space: rows of dE^-1/dq (cal_E_inv_par :924-987; intended va_k formula :978-979)
+      const cd k_alpha = omega * L.ialpha, k_beta = omega * L.ibeta;
+      const cd va = csqrt(k * k - k_alpha * k_alpha), vb = csqrt(k * k - k_beta * k_beta);
       const cd gam = 2.0 * (k * k) * (L.beta * L.beta) / (omega * omega);
       const cd gam1 = 1.0 - cinv(gam);
       const cd gam3 = cinv(gam - 2.0);

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
   const bool valid = i < B * plan.nseq;
   const long long b = valid ? i % B : 0;
   const int s = valid ? (int)(i / B) : 0;
-  SwdModel M{blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n};
+  SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
   unsigned int nev = 0;
   const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
                                    (long long)plan.nsolve * B, cwork, B, nev, valid,
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
     if (inrange) rstat[(long long)solve * B + b] = -1;
     return;
   }
-  SwdModel M{blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n};
+  SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
   unsigned int nev = 0;
   const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
                                    (long long)plan.nsolve * B, cwork, B, nev, valid,
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(128, RFS_EIGEN_MINBLOCKS)
   const double T = __ldg(periods + sq.per_off + k) * sq.scale;
   const double c = croot[sv * B + b];
   double *kp = kern + sv * 4 * (long long)n * B + b;
-  SwdModel M{blk.eig[sq.ifunc == 2 ? 0 : 1], B, n};
+  SwdModel M(blk.eig[sq.ifunc == 2 ? 0 : 1], B, n);
   double u;
   if (!(c > 0.0)) {
     // mode does not exist at this period (reference: c = 0 -> NaN kernels downstream)

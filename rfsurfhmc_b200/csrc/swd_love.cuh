@@ -24,7 +24,7 @@ RFS_DEVINL VarL varl_dev(double zb, double omega, double wvno, double dpth) {
   o.eexl = 0.0;
   if (wvno < o.xkb) {
     double sinq;
-    sincos(q, &sinq, &o.cosq);
+    sincos_cb(q, &sinq, &o.cosq);
     o.yl = sinq / o.rb;
     o.zl = -o.rb * sinq;
   } else if (wvno == o.xkb) {
@@ -34,7 +34,7 @@ RFS_DEVINL VarL varl_dev(double zb, double omega, double wvno, double dpth) {
   } else {
     o.eexl = q;
     double fac = 0.0;
-    if (q < 18.0) fac = exp(-2.0 * q);
+    if (q < 18.0) fac = exp_neg(2.0 * q);
     o.cosq = (1.0 + fac) * 0.5;
     const double sinq = (1.0 - fac) * 0.5;
     o.yl = sinq / o.rb;
@@ -138,9 +138,9 @@ RFS_DEVINL void love_solve(const SwdModel &M, long long b, double T, double c, d
       const cd km1dn = hw * uk - (0.5 * iwx) * tk;
       const cd kmup = hw * u1 + (0.5 * iwx) * t1;
       const cd f3 = nub * dpth;
-      cd exqq = (f3.x < 40.0) ? cexp(-2.0 * f3) : cd(0.0);
+      cd exqq = (f3.x < 40.0) ? cexp_b(-2.0 * f3) : cd(0.0);
       const cd f = (1.0 - exqq) / (2.0 * nub);
-      exqq = (f3.x < 75.0) ? cexp(-1.0 * f3) : cd(0.0);
+      exqq = (f3.x < 75.0) ? cexp_b(-1.0 * f3) : cd(0.0);
       const cd g = dpth * exqq;
       const double w2 = wvno * wvno;
       const cd f1 = f * (w2 * (kmup * kmup) + w2 * (km1dn * km1dn));

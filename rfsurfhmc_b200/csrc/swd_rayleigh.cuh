@@ -26,32 +26,50 @@ struct VSV {
   double c, rs, sr, ex;  // cos-like, r*sinh-like, sinh-like/r, exponent
   bool imag;             // vertical wavenumber purely imaginary (oscillatory)
   double r;              // |nu|
+  double e;              // exp(-ex): exp(-2 ex) = e*e and exp(-(ex_p+ex_s)) = e_p*e_s (one exp per half)
 };
 RFS_DEVINL VSV varsv_half(double s, double zd) {
   VSV o;
   const double small = (double)1.0e-5f;
+  const double as = fabs(s);
+  const double ri = (as > 0.0) ? rsqrt(as) : 0.0;  // r = |s| rsqrt(|s|), 1/r = rsqrt(|s|)
+  o.r = as * ri;
   if (s >= 0.0) {
     o.imag = false;
-    o.r = sqrt(s);
     const double pr = o.r * zd;
-    const double pfac = (pr < 30.0) ? exp(-2.0 * pr) : 0.0;
+    o.e = exp_neg(pr);
+    const double pfac = (pr < 30.0) ? o.e * o.e : 0.0;
     o.c = 0.5 + pfac * 0.5;
     const double sinp = 0.5 - pfac * 0.5;
     o.rs = o.r * sinp;
-    o.sr = (fabs(pr) < small && o.r < small) ? zd : sinp / o.r;
+    o.sr = (fabs(pr) < small && o.r < small) ? zd : sinp * ri;
     o.ex = pr;
   } else {
     o.imag = true;
-    o.r = sqrt(-s);
     const double pi_ = o.r * zd;
     double sn, cs;
-    sincos(pi_, &sn, &cs);
+    sincos_cb(pi_, &sn, &cs);
     o.c = cs;
     o.rs = -o.r * sn;
-    o.sr = (o.r < small) ? zd : sn / o.r;
+    o.sr = (o.r < small) ? zd : sn * ri;
     o.ex = 0.0;
+    o.e = 1.0;
   }
   return o;
+}
+
+// max |v_i| on the integer pipe (bit patterns of non-negative doubles order like integers), the
+// power of two 2^-k with 2^k <= max < 2^(k+1), and k ln2.  The reference divides the propagated
+// vectors by the max itself and adds log(max) to the exponent bookkeeping (normc :1405-1434); a
+// power-of-two scale keeps the same bookkeeping exact, costs no divisions and no logarithm.
+#define RFS_ABSBITS(v) \
+  (((unsigned long long)((unsigned)__double2hiint(v) & 0x7fffffffu) << 32) | (unsigned)__double2loint(v))
+RFS_DEVINL double pow2_scale(unsigned long long umax, double &logscale) {
+  double t1 = __longlong_as_double((long long)umax);
+  if (t1 < 1.e-40) t1 = 1.0;
+  const int k = (__double2hiint(t1) >> 20) - 1023;
+  logscale = (double)k * 0.6931471805599453;
+  return __hiloint2double((1023 - k) << 20, 0);
 }
 
 // sregn96.f90 dnka (:494-650), elastic branch: reduced 5x5 compound matrix, unique entries
@@ -59,42 +77,41 @@ struct Dnk {
   double c11, c12, c13, c14, c15, c21, c22, c23, c24, c31, c32, c33, c41, c42, c51;
 };
 RFS_DEVINL Dnk dnka_r(const VSV &P, const VSV &S, double rho, double b, double exa, double wvno,
-                      double wvno2, double om2) {
+                      double wvno2, double om2, double iwv, double iwv2, double iom2, double irom2) {
   Dnk o;
-  const double a0 = (exa < 60.0) ? exp(-exa) : 0.0;
+  const double a0 = (exa < 60.0) ? P.e * S.e : 0.0;
   const double cpcq = P.c * S.c, cpy = P.c * S.sr, cpz = P.c * S.rs, cqw = S.c * P.sr,
                cqx = S.c * P.rs, xy = P.rs * S.sr, xz = P.rs * S.rs, wy = P.sr * S.sr,
                wz = P.sr * S.rs;
   const float bf = (float)b, rf = (float)rho;
   const double rho2 = (double)__fmul_rn(rf, rf);                        // REAL*4 rho*rho
-  const double gam = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 / om2;  // 2.0*b*b in REAL*4
+  const double gam = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 * iom2;  // 2.0*b*b in REAL*4
   const double gam2 = gam * gam, gamm1 = gam - 1.0, gamm2 = gamm1 * gamm1;
-  const double cqww2 = cqw * wvno2, cqxw2 = cqx / wvno2, gg1 = gam * gamm1;
+  const double cqww2 = cqw * wvno2, cqxw2 = cqx * iwv2, gg1 = gam * gamm1;
   const double a0c = 2.0 * (a0 - cpcq);
-  const double xz2 = xz / wvno2, gxz2 = gam * xz2, g2xz2 = gam2 * xz2;
+  const double xz2 = xz * iwv2, gxz2 = gam * xz2, g2xz2 = gam2 * xz2;
   const double a0cgg1 = a0c * (gam + gamm1);
   const double wy2 = wy * wvno2, g2wy2 = gamm2 * wy2, g1wy2 = gamm1 * wy2;
-  const double rom2 = rho * om2;
   double temp = a0c * gg1 + g2xz2 + g2wy2;
   o.c33 = a0 + temp + temp;
   o.c11 = cpcq - temp;
-  o.c12 = (-cqx + wvno2 * cpy) / rom2;
+  o.c12 = (-cqx + wvno2 * cpy) * irom2;
   temp = 0.5 * a0cgg1 + gxz2 + g1wy2;
-  o.c13 = wvno * temp / rom2;
-  o.c14 = (-cqww2 + cpz) / rom2;
+  o.c13 = wvno * temp * irom2;
+  o.c14 = (-cqww2 + cpz) * irom2;
   temp = wvno2 * (a0c + wy2) + xz;
-  o.c15 = -temp / (rho2 * om2 * om2);
-  o.c21 = (-gamm2 * cqw + gam2 * cpz / wvno2) * rho * om2;
+  o.c15 = -temp * (iom2 * iom2) / rho2;
+  o.c21 = (-gamm2 * cqw + gam2 * cpz * iwv2) * rho * om2;
   o.c22 = cpcq;
-  o.c23 = (gamm1 * cqww2 - gam * cpz) / wvno;
+  o.c23 = (gamm1 * cqww2 - gam * cpz) * iwv;
   o.c24 = -wz;
   temp = 0.5 * a0cgg1 * gg1 + gam2 * gxz2 + gamm2 * g1wy2;
-  o.c31 = -2.0 * temp * rho * om2 / wvno;
+  o.c31 = -2.0 * temp * rho * om2 * iwv;
   o.c32 = -wvno * (gam * cqxw2 - gamm1 * cpy) * 2.0;
   o.c41 = (-gam2 * cqxw2 + gamm2 * cpy) * rho * om2;
   o.c42 = -xy;
   temp = gamm2 * (a0c * gam2 + g2wy2) + gam2 * g2xz2;
-  o.c51 = -rho2 * om2 * om2 * temp / wvno2;
+  o.c51 = -rho2 * om2 * om2 * temp * iwv2;
   return o;
 }
 
@@ -102,28 +119,28 @@ RFS_DEVINL cd mk(bool imag, double r) { return imag ? cd(0.0, r) : cd(r, 0.0); }
 
 // ffunc/gfunc/h1func/h2func (:1325-1403)
 RFS_DEVINL cd ffunc_d(cd nub, double dm) {
-  if (cabs(nub) < 1.0e-08) return cd(dm);
+  if (norm2(nub) < 1.0e-16) return cd(dm);
   const cd arg = nub * dm;
-  cd exqq = (arg.x < 40.0) ? cexp(-2.0 * arg) : cd(0.0);
+  cd exqq = (arg.x < 40.0) ? cexp_b(-2.0 * arg) : cd(0.0);
   return (1.0 - exqq) / (2.0 * nub);
 }
 RFS_DEVINL cd gfunc_d(cd nub, double dm) {
   const cd arg = nub * dm;
-  if (arg.x < 75.0) return cexp(-arg) * dm;
+  if (arg.x < 75.0) return cexp_b(-arg) * dm;
   return cd(0.0);
 }
 RFS_DEVINL cd h1func_d(cd nua, cd nub, double dm) {
   if (cabs(nub + nua) < 1.0e-08) return cd(dm);
   const cd arg = (nua + nub) * dm;
-  cd exqq = (arg.x < 40.0) ? cexp(-arg) : cd(0.0);
+  cd exqq = (arg.x < 40.0) ? cexp_b(-arg) : cd(0.0);
   return (1.0 - exqq) / (nub + nua);
 }
 RFS_DEVINL cd h2func_d(cd nua, cd nub, double dm) {
   if (cabs(nub - nua) < 1.0e-08) return cd(dm);
   cd arg = nua * dm;
-  cd exqp = (arg.x < 40.0) ? cexp(-arg) : cd(0.0);
+  cd exqp = (arg.x < 40.0) ? cexp_b(-arg) : cd(0.0);
   arg = nub * dm;
-  cd exqq = (arg.x < 40.0) ? cexp(-arg) : cd(0.0);
+  cd exqq = (arg.x < 40.0) ? cexp_b(-arg) : cd(0.0);
   return (exqq - exqp) / (nua - nub);
 }
 
@@ -140,6 +157,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   const double omega = (2.0 * RFS_PI32) / T;
   const double wvno = omega / c;
   const double wvno2 = wvno * wvno, om2 = omega * omega;
+  const double iwv = 1.0 / wvno, iwv2 = iwv * iwv, iomega = 1.0 / omega, iom2 = iomega * iomega;
+  const double slow = wvno * iomega;  // 1/c
   double cdl[NMAX * 6];  // [m][0..4] = cd, [m][5] = exe   (thread-local, L1-backed)
   double vsl[NMAX * 10]; // varsv results of the up-sweep, reused by the down-sweep:
                          // [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S; r < 0 <=> imaginary
@@ -171,10 +190,10 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   }
   double exsum = 0.0;
   for (int m = mmax - 2; m >= 0; m--) {
-    const double za = M.ld(F_A, m, b), zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b),
-                 zd = M.ld(F_D, m, b);
+    const double zb = M.ld(F_B, m, b), zr = M.ld(F_RHO, m, b), zd = M.ld(F_D, m, b);
     const bool wat = !(zb > 0.0);
-    const double xka = omega / za, xkb = wat ? 0.0 : omega / zb;
+    const double xka = omega * M.ld(F_IA, m, b), xkb = wat ? 0.0 : omega * M.ld(F_IB, m, b);
+    const double irom2 = M.ld(F_IRHO, m, b) * iom2;
     const VSV P = varsv_half(wvno2 - xka * xka, zd);
     VSV S;
     if (wat) {  // fluid layer: no SV wave (varsv :860-880)
@@ -183,6 +202,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       S.sr = 0.0;
       S.ex = 0.0;
       S.r = 0.0;
+      S.e = 1.0;
       S.imag = false;
     } else {
       S = varsv_half(wvno2 - xkb * xkb, zd);
@@ -202,15 +222,15 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     double n0, n1, n2, n3, n4;
     if (wat) {
       // fluid compound matrix (dnka :555-572): only 9 non-zero entries
-      const double dfac = (P.ex > 35.0) ? 0.0 : exp(-P.ex);
-      const double ca12 = -P.rs / (zr * om2), ca21 = -zr * P.sr * om2;
+      const double dfac = (P.ex > 35.0) ? 0.0 : P.e;
+      const double ca12 = -P.rs * irom2, ca21 = -zr * P.sr * om2;
       n0 = d0 * P.c + d1 * ca21;
       n1 = d0 * ca12 + d1 * P.c;
       n2 = d2 * dfac;
       n3 = d3 * P.c + d4 * ca21;
       n4 = d3 * ca12 + d4 * P.c;
     } else {
-      const Dnk A = dnka_r(P, S, zr, zb, P.ex + S.ex, wvno, wvno2, om2);
+      const Dnk A = dnka_r(P, S, zr, zb, P.ex + S.ex, wvno, wvno2, om2, iwv, iwv2, iom2, irom2);
       // ee(i) = sum_j cd(m+1,j) ca(j,i); symmetric fill-ins of :620-645
       //   ca(2,5)=c14 ca(3,4)=-2 c23 ca(3,5)=-2 c13 ca(4,3)=-c32/2 ca(4,4)=c22 ca(4,5)=c12
       //   ca(5,2)=c41 ca(5,3)=-c31/2 ca(5,4)=c21 ca(5,5)=c11
@@ -220,19 +240,21 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       n3 = d0 * A.c14 + d1 * A.c24 + d2 * (-2.0 * A.c23) + d3 * A.c22 + d4 * A.c21;
       n4 = d0 * A.c15 + d1 * A.c14 + d2 * (-2.0 * A.c13) + d3 * A.c12 + d4 * A.c11;
     }
-    double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
-    if (t1 < 1.e-40) t1 = 1.0;
-    exsum = exsum + P.ex + S.ex + log(t1);
-    cdl[m * 6 + 0] = n0 / t1;
-    cdl[m * 6 + 1] = n1 / t1;
-    cdl[m * 6 + 2] = n2 / t1;
-    cdl[m * 6 + 3] = n3 / t1;
-    cdl[m * 6 + 4] = n4 / t1;
+    double lsc;
+    const double sc = pow2_scale(max(max(max(RFS_ABSBITS(n0), RFS_ABSBITS(n1)),
+                                         max(RFS_ABSBITS(n2), RFS_ABSBITS(n3))), RFS_ABSBITS(n4)), lsc);
+    exsum = exsum + P.ex + S.ex + lsc;
+    cdl[m * 6 + 0] = n0 * sc;
+    cdl[m * 6 + 1] = n1 * sc;
+    cdl[m * 6 + 2] = n2 * sc;
+    cdl[m * 6 + 3] = n3 * sc;
+    cdl[m * 6 + 4] = n4 * sc;
     cdl[m * 6 + 5] = exsum;
   }
 
   // ---------------- fused down-sweep / eigenfunctions / energy integrals
   const double f1213 = -cdl[1];
+  const double if1213 = 1.0 / f1213;
   const double exe1 = cdl[5];
   Eig4 et;  // eigenfunction at the top of the current layer
   et.ur = cdl[2] / cdl[1];
@@ -249,7 +271,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   double exa_sum = 0.0;
   double sumi0 = 0.0, sumi1 = 0.0, sumi2 = 0.0, sumi3 = 0.0;
   const double cph = omega / wvno;
-  double zr_prev = 0.0, xmu_prev = 0.0, xlam_prev = 0.0;
+  double zr_prev = 0.0, xmu_prev = 0.0, xlam_prev = 0.0, ixmu_prev = 0.0, ixl2m_prev = 0.0,
+         irom2_prev = 0.0;
   bool wat_prev = false;
   for (int m = 0; m < mmax; m++) {
     const bool half = (m == mmax - 1);
@@ -258,18 +281,20 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     const bool wat = !(zb > 0.0);
     const double xmu = zr * zb * zb;
     const double xlam = zr * za * za - 2 * xmu;
-    const double xka = omega / za, xkb = wat ? 0.0 : omega / zb;
+    const double xka = omega * M.ld(F_IA, m, b), xkb = wat ? 0.0 : omega * M.ld(F_IB, m, b);
     const double sa = wvno2 - xka * xka, sb = wvno2 - xkb * xkb;
-    const double rom2 = zr * om2;
+    const double rom2 = zr * om2, irho = M.ld(F_IRHO, m, b), irom2 = irho * iom2;
+    const double ixmu = wat ? 0.0 : 1.0 / xmu;        // 1/(rho b^2)
+    const double ixl2m = 1.0 / (xlam + xmu + xmu);    // 1/(rho a^2)
 
     // ---- boundary term of dc/dh at the top of layer m (getdcdh :1436-1535)
     double gsum;
     {
       const double tuz = et.uz, ttz = et.tz, ttr = et.tr;
-      const double tur = wat ? -wvno * ttz / rom2 : et.ur;
+      const double tur = wat ? -wvno * ttz * irom2 : et.ur;
       const double xl2mp = xlam + xmu + xmu;
-      const double duzdzp = (ttz + wvno * xlam * tur) / xl2mp;
-      const double durdzp = (xmu == 0.0) ? wvno * tuz : (ttr / xmu) - wvno * tuz;
+      const double duzdzp = (ttz + wvno * xlam * tur) * ixl2m;
+      const double durdzp = (xmu == 0.0) ? wvno * tuz : (ttr * ixmu) - wvno * tuz;
       if (m == 0) {
         const double drho = zr, dmu = xmu, dl2mu = xlam + dmu + dmu;
         gsum = om2 * drho * tuz * tuz + om2 * (tur * tur * drho) - wvno2 * dmu * tuz * tuz -
@@ -278,18 +303,18 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
         const double drho = zr - zr_prev, dmu = xmu - xmu_prev, dlm = xlam - xlam_prev;
         const double dl2mu = dlm + dmu + dmu;
         const double xl2mm = xlam_prev + xmu_prev + xmu_prev;
-        const double durdzm = (xmu_prev == 0.0) ? wvno * tuz : (ttr / xmu_prev) - wvno * tuz;
+        const double durdzm = (xmu_prev == 0.0) ? wvno * tuz : (ttr * ixmu_prev) - wvno * tuz;
         double drur2, dlur2, duzdzm;
         if (wat_prev) {
           // Ur is discontinuous across a fluid boundary (:1497-1510)
-          const double URB = -wvno * ttz / (zr_prev * om2);
+          const double URB = -wvno * ttz * irom2_prev;
           drur2 = tur * tur * zr - URB * URB * zr_prev;
           dlur2 = tur * tur * xl2mp - URB * URB * xl2mm;
           duzdzm = (ttz + wvno * xlam_prev * URB) / (wat ? xl2mm : xlam_prev);
         } else {
           drur2 = tur * tur * drho;
           dlur2 = tur * tur * dl2mu;
-          duzdzm = (ttz + wvno * xlam_prev * tur) / xl2mm;
+          duzdzm = (ttz + wvno * xlam_prev * tur) * ixl2m_prev;
         }
         gsum = om2 * drho * tuz * tuz + om2 * drur2 - wvno2 * dmu * tuz * tuz - wvno2 * dlur2 +
                (xl2mp * duzdzp * duzdzp - xl2mm * duzdzm * duzdzm) +
@@ -324,45 +349,46 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       double w0, w1, w2, w3;
       if (wat) {
         // fluid Haskell step (hska :930-944)
-        const double dfac = (P.ex > 35.0) ? 0.0 : exp(-P.ex);
-        const double a23 = -P.rs / rom2, a32 = -rom2 * P.sr;
+        const double dfac = (P.ex > 35.0) ? 0.0 : exp_neg(P.ex);
+        const double a23 = -P.rs * irom2, a32 = -rom2 * P.sr;
         w0 = dfac * v0;
         w1 = P.c * v1 + a23 * v2;
         w2 = a32 * v1 + P.c * v2;
         w3 = dfac * v3;
       } else {
         // ---- elastic Haskell step (hska :945-989, down :993-1063)
-        const double dfac = ((P.ex - S.ex) > 70.0) ? 0.0 : exp(S.ex - P.ex);
+        const double dfac = ((P.ex - S.ex) > 70.0) ? 0.0 : exp_cb(S.ex - P.ex);
         const double cosp = P.c, rsinp = P.rs, sinpr = P.sr;
         const double cossv = dfac * S.c, rsinsv = dfac * S.rs, sinsvr = dfac * S.sr;
         const float bf = (float)zb;
-        const double gmh = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 / om2;
+        const double gmh = (double)__fmul_rn(__fmul_rn(2.0f, bf), bf) * wvno2 * iom2;
         const double gmh1 = gmh - 1.0;
         const double a11 = cossv + gmh * (cosp - cossv);
-        const double a12 = -wvno * gmh1 * sinpr + gmh * rsinsv / wvno;
-        const double a13 = -wvno * (cosp - cossv) / rom2;
-        const double a14 = (wvno2 * sinpr - rsinsv) / rom2;
-        const double a21 = gmh * rsinp / wvno - wvno * gmh1 * sinsvr;
+        const double a12 = -wvno * gmh1 * sinpr + gmh * rsinsv * iwv;
+        const double a13 = -wvno * (cosp - cossv) * irom2;
+        const double a14 = (wvno2 * sinpr - rsinsv) * irom2;
+        const double a21 = gmh * rsinp * iwv - wvno * gmh1 * sinsvr;
         const double a22 = cosp - gmh * (cosp - cossv);
-        const double a23 = (-rsinp + wvno2 * sinsvr) / rom2;
+        const double a23 = (-rsinp + wvno2 * sinsvr) * irom2;
         const double a24 = -a13;
-        const double a31 = rom2 * gmh * gmh1 * (cosp - cossv) / wvno;
-        const double a32 = rom2 * (-gmh1 * gmh1 * sinpr + gmh * gmh * rsinsv / wvno2);
+        const double a31 = rom2 * gmh * gmh1 * (cosp - cossv) * iwv;
+        const double a32 = rom2 * (-gmh1 * gmh1 * sinpr + gmh * gmh * rsinsv * iwv2);
         const double a33 = a22, a34 = -a12;
-        const double a41 = rom2 * (gmh * gmh * rsinp / wvno2 - gmh1 * gmh1 * sinsvr);
+        const double a41 = rom2 * (gmh * gmh * rsinp * iwv2 - gmh1 * gmh1 * sinsvr);
         const double a42 = -a31, a43 = -a21, a44 = a11;
         w0 = a11 * v0 + a12 * v1 + a13 * v2 + a14 * v3;
         w1 = a21 * v0 + a22 * v1 + a23 * v2 + a24 * v3;
         w2 = a31 * v0 + a32 * v1 + a33 * v2 + a34 * v3;
         w3 = a41 * v0 + a42 * v1 + a43 * v2 + a44 * v3;
       }
-      double t1 = fmax(fmax(fabs(w0), fabs(w1)), fmax(fabs(w2), fabs(w3)));
-      if (t1 < 1.e-40) t1 = 1.0;
-      v0 = w0 / t1;
-      v1 = w1 / t1;
-      v2 = w2 / t1;
-      v3 = w3 / t1;
-      exa_sum = exa_sum + P.ex + log(t1);
+      double lsc;
+      const double sc = pow2_scale(max(max(RFS_ABSBITS(w0), RFS_ABSBITS(w1)),
+                                       max(RFS_ABSBITS(w2), RFS_ABSBITS(w3))), lsc);
+      v0 = w0 * sc;
+      v1 = w1 * sc;
+      v2 = w2 * sc;
+      v3 = w3 * sc;
+      exa_sum = exa_sum + P.ex + lsc;
       // ---- eigenfunction at the top of layer m+1 (svfunc :268-315)
       const int i = m + 1;
       const double cd1 = cdl[i * 6 + 0], cd2 = cdl[i * 6 + 1], cd3 = cdl[i * 6 + 2], cd4 = -cd3,
@@ -374,11 +400,11 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       const double uu4 = -tz1 * cd4 + tz2 * cd2 - tz3 * cd1;
       const double ext = exa_sum + cdl[i * 6 + 5] - exe1;
       if (ext > -80.0 && ext < 80.0) {
-        const double fact = exp(ext);
-        eb.ur = uu1 * fact / f1213;
-        eb.uz = uu2 * fact / f1213;
-        eb.tz = uu3 * fact / f1213;
-        eb.tr = uu4 * fact / f1213;
+        const double fact = exp_cb(ext) * if1213;
+        eb.ur = uu1 * fact;
+        eb.uz = uu2 * fact;
+        eb.tz = uu3 * fact;
+        eb.tr = uu4 * fact;
       } else {
         eb.ur = eb.uz = eb.tz = eb.tr = 0.0;
       }
@@ -391,8 +417,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
 
     if (wat) {
       // ---- fluid layer: 2x2 potentials (intijr :1246-1266) and energy (energy :1123-1143)
-      const cd kmpu = (0.5 * ira) * eb.uz - (0.5 / rom2) * eb.tz;
-      const cd km1pd = -1.0 * ((0.5 * ira) * et.uz) - (0.5 / rom2) * et.tz;
+      const cd kmpu = (0.5 * ira) * eb.uz - (0.5 * irom2) * eb.tz;
+      const cd km1pd = -1.0 * ((0.5 * ira) * et.uz) - (0.5 * irom2) * et.tz;
       const cd FA = ffunc_d(ra, zd), GA = gfunc_d(ra, zd);
       const cd pp = kmpu * kmpu * FA + km1pd * km1pd * FA, pm = 2.0 * (kmpu * km1pd * GA);
       const double I11 = ((ra * ra) * (pp - pm)).x;
@@ -414,14 +440,14 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       kern[(2LL * mmax + m) * ks] = 0.5 * (za * facav + za * facah) / zr + facr;
     } else {
       // ---- E, E^-1 of this layer (evalg :736-768)
-      double gam = zb * wvno / omega;
+      double gam = zb * slow;
       gam = 2.0 * (gam * gam);
       const double gamm1 = gam - 1.0;
       const cd irb = cinv(rb);
       // EINV rows (acting on [ur, uz, tz, tr])
-      const double ei11 = 0.5 * gam / wvno, ei13 = -0.5 / rom2;
-      const cd ei12 = (-0.5 * gamm1) * ira, ei14 = (0.5 * wvno / rom2) * ira;
-      const cd ei21 = (-0.5 * gamm1) * irb, ei23 = (0.5 * wvno / rom2) * irb;
+      const double ei11 = 0.5 * gam * iwv, ei13 = -0.5 * irom2;
+      const cd ei12 = (-0.5 * gamm1) * ira, ei14 = (0.5 * wvno * irom2) * ira;
+      const cd ei21 = (-0.5 * gamm1) * irb, ei23 = (0.5 * wvno * irom2) * irb;
       // rows 3,4: EINV(3,:) = [ei11, -ei12, ei13, -ei14]; EINV(4,:) = [-ei21, ei11, -ei23, ei13]
       // ---- potentials (intijr :1203-1323)
       // downward coefficients at the top of the layer (rows 3,4 of E^-1), upward at the bottom
@@ -430,7 +456,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       // E columns: E(:,1)=[k, ra, r g1, r g ra/k]  E(:,2)=[rb, k, r g rb/k, r g1]
       //            E(:,3)=[k,-ra, r g1,-r g ra/k]  E(:,4)=[-rb, k,-r g rb/k, r g1]     (r = rho om^2)
       const double rg1 = rom2 * gamm1;
-      const cd e41 = (rom2 * gam / wvno) * ra, e32 = (rom2 * gam / wvno) * rb;
+      const cd e41 = (rom2 * gam * iwv) * ra, e32 = (rom2 * gam * iwv) * rb;
       cd a3[4], a4[4];  // a_i3 = E(i,3) km1pd, a_i4 = E(i,4) km1sd
       a3[0] = wvno * km1pd;
       a3[1] = -1.0 * (ra * km1pd);
@@ -464,8 +490,24 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
         a2[1] = wvno * kmsu;
         a2[2] = e32 * kmsu;
         a2[3] = rg1 * kmsu;
-        const cd FA = ffunc_d(ra, zd), GA = gfunc_d(ra, zd), FB = ffunc_d(rb, zd),
-                 GB = gfunc_d(rb, zd), H1 = h1func_d(ra, rb, zd), H2 = h2func_d(ra, rb, zd);
+        // ffunc/gfunc/h1func/h2func (:1325-1403) from TWO complex exponentials: with
+        // ea = exp(-nu_a d), eb = exp(-nu_b d): exp(-2 nu d) = e^2, exp(-(nu_a+nu_b) d) = ea eb
+        // (the reference evaluates seven); cut-offs as in the reference
+        const cd arga = ra * zd, argb = rb * zd;
+        const cd ea = (arga.x < 75.0) ? cexp_b(-1.0 * arga) : cd(0.0);
+        const cd ebx = (argb.x < 75.0) ? cexp_b(-1.0 * argb) : cd(0.0);
+        const cd sab = ra + rb, dab = ra - rb;
+        const cd FA = (norm2(ra) < 1.0e-16) ? cd(zd)
+                                            : (1.0 - ((arga.x < 40.0) ? ea * ea : cd(0.0))) * (0.5 * ira);
+        const cd FB = (norm2(rb) < 1.0e-16) ? cd(zd)
+                                            : (1.0 - ((argb.x < 40.0) ? ebx * ebx : cd(0.0))) * (0.5 * irb);
+        const cd GA = ea * zd, GB = ebx * zd;
+        const cd H1 = (norm2(sab) < 1.0e-16)
+                          ? cd(zd)
+                          : (1.0 - ((arga.x + argb.x < 40.0) ? ea * ebx : cd(0.0))) * cinv(sab);
+        const cd H2 = (norm2(dab) < 1.0e-16)
+                          ? cd(zd)
+                          : (((argb.x < 40.0) ? ebx : cd(0.0)) - ((arga.x < 40.0) ? ea : cd(0.0))) * cinv(dab);
         // INT_ij = a_i^T W a_j,  W = [[FA,H1,GA,H2],[H1,FB,H2,GB],[GA,H2,FA,H1],[H2,GB,H1,FB]]
 #define RFS_WJ(j, b1, b2, b3, b4)                                     \
   const cd b1 = FA * a1[j] + H1 * a2[j] + GA * a3[j] + H2 * a4[j];   \
@@ -492,7 +534,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       }
       // ---- energy integrals and un-normalised partials (energy :1144-1183, getmat :1537-1589)
       const double TL = zr * zb * zb, TC = zr * za * za, TA = TC, TF = TA - 2. * TL;
-      const double a12 = -wvno, a14 = 1.0 / TL, a21 = wvno * TF / TC, a23 = 1.0 / TC;
+      const double a12 = -wvno, a14 = ixmu, a23 = ixl2m, a21 = wvno * TF * a23;
       const double URUR = I11, UZUZ = I22;
       const double DURDUR = a12 * a12 * I22 + 2. * a12 * a14 * I24 + a14 * a14 * I44;
       const double DUZDUZ = a21 * a21 * I11 + 2. * a21 * a23 * I13 + a23 * a23 * I33;
@@ -502,18 +544,21 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       sumi1 += TL * UZUZ + TA * URUR;
       sumi2 += TL * UZDUR - TF * URDUZ;
       sumi3 += TL * DURDUR + TC * DUZDUZ;
-      const double facah = zr * za * (URUR - 2. * URDUZ / wvno);
-      const double facav = zr * za * DUZDUZ / wvno2;
-      const double facbv = zr * zb * (UZUZ + 2. * UZDUR / wvno + DURDUR / wvno2 + 4. * URDUZ / wvno);
+      const double facah = zr * za * (URUR - 2. * URDUZ * iwv);
+      const double facav = zr * za * DUZDUZ * iwv2;
+      const double facbv = zr * zb * (UZUZ + 2. * UZDUR * iwv + DURDUR * iwv2 + 4. * URDUZ * iwv);
       const double facr = -0.5 * cph * cph * (URUR + UZUZ);
       kern[(0LL * mmax + m) * ks] = facah + facav;
       kern[(1LL * mmax + m) * ks] = facbv;
-      kern[(2LL * mmax + m) * ks] = 0.5 * (za * facav + za * facah + zb * facbv) / zr + facr;
+      kern[(2LL * mmax + m) * ks] = 0.5 * (za * facav + za * facah + zb * facbv) * irho + facr;
     }
     et = eb;
     zr_prev = zr;
     xmu_prev = xmu;
     xlam_prev = xlam;
+    ixmu_prev = ixmu;
+    ixl2m_prev = ixl2m;
+    irom2_prev = irom2;
     wat_prev = wat;
   }
   (void)sumi3;
@@ -521,12 +566,12 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   const double ugr = (wvno * sumi1 + sumi2) / (omega * sumi0);
   const double are = wvno / (2.0 * omega * ugr * sumi0);
   const double fac = are * cph / wvno2;
-  const double nrm = ugr * sumi0;
+  const double inrm = 1.0 / (ugr * sumi0);
   double suffix = 0.0;
   for (int m = mmax - 1; m >= 0; m--) {
-    kern[(0LL * mmax + m) * ks] = kern[(0LL * mmax + m) * ks] / nrm;
-    kern[(1LL * mmax + m) * ks] = kern[(1LL * mmax + m) * ks] / nrm;
-    kern[(2LL * mmax + m) * ks] = kern[(2LL * mmax + m) * ks] / nrm;
+    kern[(0LL * mmax + m) * ks] = kern[(0LL * mmax + m) * ks] * inrm;
+    kern[(1LL * mmax + m) * ks] = kern[(1LL * mmax + m) * ks] * inrm;
+    kern[(2LL * mmax + m) * ks] = kern[(2LL * mmax + m) * ks] * inrm;
     double dfac = fac * kern[(3LL * mmax + m) * ks];
     if (fabs(dfac) < 1.0e-38) dfac = 0.0;
     kern[(3LL * mmax + m) * ks] = suffix;  // dcdh(i) = sum_{j>i} raw(j) dtp(j); dcdh(mmax) = 0

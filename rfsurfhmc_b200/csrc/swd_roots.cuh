@@ -32,11 +32,16 @@ struct SwdBlocks {
 };
 
 struct SwdModel {
-  const double *p;   // [SWD_NF][n][stride]
-  long long stride;  // models in the batch (B)
-  int n;             // layers (last = half-space)
+  const double *p;  // [SWD_NF][n][stride]
+  int stride;       // models in the batch (B)
+  int n;            // layers (last = half-space)
+  int fs;           // field stride n*B
+  // 32-bit element indices (the host keeps SWD_NF*n*B below 2^31, see run_swd): one IMAD per field
+  // on top of the shared m*B+b term instead of a 64-bit multiply chain per load
+  RFS_DEVINL SwdModel(const double *blk, long long B, int nl)
+      : p(blk), stride((int)B), n(nl), fs(nl * (int)B) {}
   RFS_DEVINL double ld(int f, int m, long long b) const {
-    return __ldg(p + ((long long)f * n + m) * stride + b);
+    return __ldg(p + (f * fs + (m * stride + (int)b)));
   }
 };
 
@@ -60,7 +65,7 @@ RFS_DEVINL double dltar1_dev(double wvno, double omega, const SwdModel &M, long 
     double y, z, cosq;
     if (wvno < xkb) {
       double sinq;
-      sincos(q, &sinq, &cosq);
+      sincos_cb(q, &sinq, &cosq);
       y = sinq / rb;
       z = -rb * sinq;
     } else if (wvno == xkb) {
@@ -69,7 +74,7 @@ RFS_DEVINL double dltar1_dev(double wvno, double omega, const SwdModel &M, long 
       z = 0.0;
     } else {
       double fac = 0.0;
-      if (q < 16.0) fac = exp(-2.0 * q);
+      if (q < 16.0) fac = exp_neg(2.0 * q);
       cosq = (1.0 + fac) * 0.5;
       const double sinq = (1.0 - fac) * 0.5;
       y = sinq / rb;
@@ -100,7 +105,7 @@ RFS_DEVINL void var_pair(double wvno, double xka, double xkb, double dpth, VarHa
   const double ria = (x2a > 0.0) ? rsqrt(x2a) : 0.0, rib = (x2b > 0.0) ? rsqrt(x2b) : 0.0;
   const double ra = x2a * ria, rb = x2b * rib;
   const double pa = ra * dpth, pb = rb * dpth;
-  const double ea = exp(-pa), eb = exp(-pb);
+  const double ea = exp_neg(pa), eb = exp_neg(pb);
   const double fa = (pa < 16.0) ? ea * ea : 0.0, fb = (pb < 16.0) ? eb * eb : 0.0;
   const double sa = (1.0 - fa) * 0.5, sb = (1.0 - fb) * 0.5;
   P.c = (1.0 + fa) * 0.5;
@@ -118,7 +123,7 @@ RFS_DEVINL void var_pair(double wvno, double xka, double xkb, double dpth, VarHa
     P.e = 1.0;
     if (wvno < xka) {
       double s;
-      sincos(pa, &s, &P.c);
+      sincos_cb(pa, &s, &P.c);
       P.w = s * ria;
       P.x = -ra * s;
     } else {
@@ -132,7 +137,7 @@ RFS_DEVINL void var_pair(double wvno, double xka, double xkb, double dpth, VarHa
     S.e = 1.0;
     if (wvno < xkb) {
       double s;
-      sincos(pb, &s, &S.c);
+      sincos_cb(pb, &s, &S.c);
       S.w = s * rib;
       S.x = -rb * s;
     } else {
@@ -151,7 +156,7 @@ RFS_DEVINL VarHalf var_half(double wvno, double xk, double x2, double dpth) {
   o.e = 1.0;
   if (wvno < xk) {
     double s;
-    sincos(pq, &s, &o.c);
+    sincos_cb(pq, &s, &o.c);
     o.w = s * ri;
     o.x = -r * s;
   } else if (wvno == xk) {
@@ -160,7 +165,7 @@ RFS_DEVINL VarHalf var_half(double wvno, double xk, double x2, double dpth) {
     o.x = 0.0;
   } else {
     o.ex = pq;
-    o.e = exp(-pq);
+    o.e = exp_neg(pq);
     const double fac = (pq < 16.0) ? o.e * o.e : 0.0;
     o.c = (1.0 + fac) * 0.5;
     const double s = (1.0 - fac) * 0.5;
@@ -226,7 +231,14 @@ RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2
   const double n2 = (e0 * C.c13 + e1 * C.c23) + (e2 * C.c33 + e3 * C.c43) + e4 * C.c53;
   const double n3 = (e0 * C.c14 + e1 * C.c24) + (e2 * C.c34 + e3 * C.c22) + e4 * C.c21;
   const double n4 = (e0 * C.c15 + e1 * C.c14) + (e2 * C.c35 + e3 * C.c12) + e4 * C.c11;
-  double t1 = fmax(fmax(fmax(fabs(n0), fabs(n1)), fmax(fabs(n2), fabs(n3))), fabs(n4));
+  // max |n_i| on the integer pipe: the bit patterns of non-negative doubles order like unsigned
+  // integers (a NaN wins and poisons the vector one layer earlier than fmax would)
+#define RFS_ABSBITS(v) \
+  (((unsigned long long)((unsigned)__double2hiint(v) & 0x7fffffffu) << 32) | (unsigned)__double2loint(v))
+  const unsigned long long u0 = RFS_ABSBITS(n0), u1 = RFS_ABSBITS(n1), u2 = RFS_ABSBITS(n2),
+                           u3 = RFS_ABSBITS(n3), u4 = RFS_ABSBITS(n4);
+#undef RFS_ABSBITS
+  double t1 = __longlong_as_double((long long)max(max(max(u0, u1), max(u2, u3)), u4));
   if (t1 < 1.e-40) t1 = 1.0;
   const double it1 = 1.0 / t1;
   e0 = n0 * it1;
