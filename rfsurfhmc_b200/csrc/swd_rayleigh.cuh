@@ -284,8 +284,9 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     const double xka = omega * M.ld(F_IA, m, b), xkb = wat ? 0.0 : omega * M.ld(F_IB, m, b);
     const double sa = wvno2 - xka * xka, sb = wvno2 - xkb * xkb;
     const double rom2 = zr * om2, irho = M.ld(F_IRHO, m, b), irom2 = irho * iom2;
-    const double ixmu = wat ? 0.0 : 1.0 / xmu;        // 1/(rho b^2)
-    const double ixl2m = 1.0 / (xlam + xmu + xmu);    // 1/(rho a^2)
+    // 1/(rho b^2), 1/(rho a^2) from the reciprocals of the model block (no divisions)
+    const double ibm = wat ? 0.0 : M.ld(F_IB, m, b), iam = M.ld(F_IA, m, b);
+    const double ixmu = irho * ibm * ibm, ixl2m = irho * iam * iam;
 
     // ---- boundary term of dc/dh at the top of layer m (getdcdh :1436-1535)
     double gsum;
@@ -508,28 +509,42 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
         const cd H2 = (norm2(dab) < 1.0e-16)
                           ? cd(zd)
                           : (((argb.x < 40.0) ? ebx : cd(0.0)) - ((arga.x < 40.0) ? ea : cd(0.0))) * cinv(dab);
-        // INT_ij = a_i^T W a_j,  W = [[FA,H1,GA,H2],[H1,FB,H2,GB],[GA,H2,FA,H1],[H2,GB,H1,FB]]
-#define RFS_WJ(j, b1, b2, b3, b4)                                     \
-  const cd b1 = FA * a1[j] + H1 * a2[j] + GA * a3[j] + H2 * a4[j];   \
-  const cd b2 = H1 * a1[j] + FB * a2[j] + H2 * a3[j] + GB * a4[j];   \
-  const cd b3 = GA * a1[j] + H2 * a2[j] + FA * a3[j] + H1 * a4[j];   \
-  const cd b4 = H2 * a1[j] + GB * a2[j] + H1 * a3[j] + FB * a4[j];
-#define RFS_DOT(i, b1, b2, b3, b4) (a1[i] * b1 + a2[i] * b2 + a3[i] * b3 + a4[i] * b4).x
+        // INT_ij = a_i^T W a_j,  W = [[P,Q],[Q,P]], P = [[FA,H1],[H1,FB]], Q = [[GA,H2],[H2,GB]].
+        // With s = up + down, t = up - down:  a_i^T W a_j = (s_i^T (P+Q) s_j + t_i^T (P-Q) t_j)/2,
+        // two 2x2 forms instead of one 4x4 (56 instead of 88 complex products per layer).
+        const cd pa = FA + GA, ph = H1 + H2, pb = FB + GB, ma = FA - GA, mh = H1 - H2, mb = FB - GB;
+        cd s1[4], s2[4], t1[4], t2[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          s1[q] = a1[q] + a3[q];
+          s2[q] = a2[q] + a4[q];
+          t1[q] = a1[q] - a3[q];
+          t2[q] = a2[q] - a4[q];
+        }
+#define RFS_WJ(j)                                   \
+  const cd bs1 = pa * s1[j] + ph * s2[j];           \
+  const cd bs2 = ph * s1[j] + pb * s2[j];           \
+  const cd bt1 = ma * t1[j] + mh * t2[j];           \
+  const cd bt2 = mh * t1[j] + mb * t2[j];
+#define RFS_RE(u_, v_) ((u_).x * (v_).x - (u_).y * (v_).y)
+#define RFS_DOT(i) \
+  (0.5 * (RFS_RE(s1[i], bs1) + RFS_RE(s2[i], bs2) + RFS_RE(t1[i], bt1) + RFS_RE(t2[i], bt2)))
         {
-          RFS_WJ(0, p1, p2, p3, p4) I11 = RFS_DOT(0, p1, p2, p3, p4);
+          RFS_WJ(0) I11 = RFS_DOT(0);
         }
         {
-          RFS_WJ(1, p1, p2, p3, p4) I22 = RFS_DOT(1, p1, p2, p3, p4);
+          RFS_WJ(1) I22 = RFS_DOT(1);
         }
         {
-          RFS_WJ(2, p1, p2, p3, p4) I13 = RFS_DOT(0, p1, p2, p3, p4);
-          I33 = RFS_DOT(2, p1, p2, p3, p4);
+          RFS_WJ(2) I13 = RFS_DOT(0);
+          I33 = RFS_DOT(2);
         }
         {
-          RFS_WJ(3, p1, p2, p3, p4) I24 = RFS_DOT(1, p1, p2, p3, p4);
-          I44 = RFS_DOT(3, p1, p2, p3, p4);
+          RFS_WJ(3) I24 = RFS_DOT(1);
+          I44 = RFS_DOT(3);
         }
 #undef RFS_WJ
+#undef RFS_RE
 #undef RFS_DOT
       }
       // ---- energy integrals and un-normalised partials (energy :1144-1183, getmat :1537-1589)

@@ -102,7 +102,7 @@ struct VarHalf {
 // oscillatory (c > v) and grazing (c == v) cases are patched afterwards.
 RFS_DEVINL void var_pair(double wvno, double xka, double xkb, double dpth, VarHalf &P, VarHalf &S) {
   const double x2a = (wvno + xka) * fabs(wvno - xka), x2b = (wvno + xkb) * fabs(wvno - xkb);
-  const double ria = (x2a > 0.0) ? rsqrt(x2a) : 0.0, rib = (x2b > 0.0) ? rsqrt(x2b) : 0.0;
+  const double ria = (x2a > 0.0) ? rsqrt_pos(x2a) : 0.0, rib = (x2b > 0.0) ? rsqrt_pos(x2b) : 0.0;
   const double ra = x2a * ria, rb = x2b * rib;
   const double pa = ra * dpth, pb = rb * dpth;
   const double ea = exp_neg(pa), eb = exp_neg(pb);

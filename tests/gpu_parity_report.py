@@ -86,3 +86,16 @@ for which in (1, 2):
     print("which", which, "flags", np.array_equal(fa, fb), "U", rel(Ub[mm], Ua[mm]), "g",
           np.max(np.abs(gb[mm] - ga[mm]) / np.max(np.abs(ga[mm]), axis=1, keepdims=True)))
 print("launches", ctx.launches)
+
+# ---- wild models (velocity inversions, thin layers): error quantiles instead of maxima
+ctx.config_obs(dobs)
+Xw = np.random.default_rng(13).uniform(0.5, 1.5, (B, 14)) * x0 + 0.01
+U0, g0, d0, f0 = O.joint_batch(Xw, dobs, cfg, nthreads=8)
+U1, g1, d1, f1 = ctx.misfit_grad_host(Xw)
+m = f0 & f1
+ed = np.abs(d1[m, 125:] - d0[m, 125:]) / np.abs(d0[m, 125:])
+eg = (np.abs(g1[m] - g0[m]) / np.max(np.abs(g0[m]), axis=1, keepdims=True)).max(1)
+print("wild: flags equal", np.array_equal(f0, f1), "ok", int(m.sum()), "of", B)
+print("wild: dsyn swd rel  max %.3e  99%% %.3e  median %.3e" % (ed.max(), np.quantile(ed.max(1), 0.99), np.median(ed.max(1))))
+print("wild: grad err/max|g| max %.3e  99%% %.3e  median %.3e  frac>1e-4 %.4f" %
+      (eg.max(), np.quantile(eg, 0.99), np.median(eg), np.mean(eg > 1e-4)))

@@ -19,6 +19,8 @@ __global__ void k(const double *x, int n, unsigned long long *bad) {
   rfs::sincos_cb(t, &s1, &c1);
   if (__double_as_longlong(s0) != __double_as_longlong(s1)) atomicAdd(bad + 1, 1ULL);
   if (__double_as_longlong(c0) != __double_as_longlong(c1)) atomicAdd(bad + 2, 1ULL);
+  const double q0 = rsqrt(v + 1e-300 + t * 1e-9), q1 = rfs::rsqrt_pos(v + 1e-300 + t * 1e-9);
+  if (__double_as_longlong(q0) != __double_as_longlong(q1)) atomicAdd(bad + 5, 1ULL);
   sincos(v * 0.01, &s0, &c0);
   rfs::sincos_cb(v * 0.01, &s1, &c1);
   if (__double_as_longlong(s0) != __double_as_longlong(s1)) atomicAdd(bad + 3, 1ULL);
@@ -35,7 +37,7 @@ int main() {
   }
   h[0] = 0.0;
   double *d;
-  unsigned long long *bad, hb[5];
+  unsigned long long *bad, hb[6];
   cudaMalloc(&d, sizeof(double) * n);
   cudaMalloc(&bad, sizeof(hb));
   cudaMemset(bad, 0, sizeof(hb));
@@ -43,7 +45,7 @@ int main() {
   k<<<(n + 255) / 256, 256>>>(d, n, bad);
   if (cudaDeviceSynchronize() != cudaSuccess) { printf("cuda error\n"); return 2; }
   cudaMemcpy(hb, bad, sizeof(hb), cudaMemcpyDeviceToHost);
-  printf("n=%d mismatches: exp %llu  sin(big) %llu cos(big) %llu  sin(small) %llu cos(small) %llu\n", n,
-         hb[0], hb[1], hb[2], hb[3], hb[4]);
-  return (hb[0] | hb[1] | hb[2] | hb[3] | hb[4]) ? 1 : 0;
+  printf("n=%d mismatches: exp %llu  sin(big) %llu cos(big) %llu  sin(small) %llu cos(small) %llu  rsqrt %llu\n",
+         n, hb[0], hb[1], hb[2], hb[3], hb[4], hb[5]);
+  return (hb[0] | hb[1] | hb[2] | hb[3] | hb[4] | hb[5]) ? 1 : 0;
 }
