@@ -129,6 +129,9 @@ int rfs_count_evals(rfs_ctx *ctx, int enable);
 long long rfs_read_evals(rfs_ctx *ctx);
 int rfs_read_eval_stats(rfs_ctx *ctx, long long *out3); /* total, slowest thread, threads > 2000 */
 int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops);
+/* self-test: the constant-bank exp / sincos / rsqrt of the root search against the CUDA math library
+ * on n device-generated arguments; mismatches[6] = exp, sin/cos (large args), sin/cos (small), rsqrt */
+int rfs_selftest_math(rfs_ctx *ctx, long long n, long long *mismatches);
 
 #ifdef __cplusplus
 }

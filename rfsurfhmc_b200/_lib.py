@@ -88,6 +88,8 @@ def load_library():
         L.rfs_read_eval_stats.argtypes = [_vp, _llp]
         L.rfs_measure_fp64_peak.restype = C.c_int
         L.rfs_measure_fp64_peak.argtypes = [_vp, _dp]
+        L.rfs_selftest_math.restype = C.c_int
+        L.rfs_selftest_math.argtypes = [_vp, C.c_longlong, _llp]
         _lib = L
         return _lib
 
@@ -99,7 +101,7 @@ def exported_symbols():
             "rfs_misfit_grad_host", "rfs_surf_forward", "rfs_surf_adjoint_kernel",
             "rfs_surf_adjoint_kernel_modes", "rfs_rf_forward", "rfs_rf_kernel", "rfs_rf_kernel_all",
             "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
-            "rfs_measure_fp64_peak", "rfs_read_eval_stats"]
+            "rfs_measure_fp64_peak", "rfs_read_eval_stats", "rfs_selftest_math"]
 
 
 def _f64(a):
@@ -158,6 +160,13 @@ class Context:
         v = (C.c_longlong * 3)()
         self._ck(self.L.rfs_read_eval_stats(self.h, v))
         return int(v[0]), int(v[1]), int(v[2])
+
+    def selftest_math(self, n=1 << 22):
+        """Mismatch counts (exp, sin/cos large, sin/cos small, rsqrt) of the constant-bank math of the
+        root search against the CUDA math library; all zero = bit-identical."""
+        v = (C.c_longlong * 6)()
+        self._ck(self.L.rfs_selftest_math(self.h, int(n), v))
+        return [int(x) for x in v]
 
     def measure_fp64_peak(self):
         v = C.c_double(0.0)

@@ -880,6 +880,36 @@ int rfs_read_eval_stats(rfs_ctx *ctx, long long *out3) {
   return RFS_OK;
 }
 
+// see rfs_selftest_math
+__global__ void math_selftest_kernel(long long n, unsigned long long *bad) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // splitmix64 -> u in [0,1)
+  unsigned long long z = (unsigned long long)i * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+  const double v = (i & 1) ? 708.0 * u : 40.0 * u * u;  // dense near 0, covers the fast-path range
+  const double e0 = exp(-v), e1 = rfs::exp_neg(v);
+  if (__double_as_longlong(e0) != __double_as_longlong(e1)) atomicAdd(bad + 0, 1ULL);
+  const double x0 = exp(v - 300.0), x1 = rfs::exp_cb(v - 300.0);
+  if (__double_as_longlong(x0) != __double_as_longlong(x1)) atomicAdd(bad + 0, 1ULL);
+  double s0, c0, s1, c1;
+  const double t = v * 1531.7;  // up to ~1.1e6 rad
+  sincos(t, &s0, &c0);
+  rfs::sincos_cb(t, &s1, &c1);
+  if (__double_as_longlong(s0) != __double_as_longlong(s1)) atomicAdd(bad + 1, 1ULL);
+  if (__double_as_longlong(c0) != __double_as_longlong(c1)) atomicAdd(bad + 2, 1ULL);
+  sincos(v * 0.01, &s0, &c0);
+  rfs::sincos_cb(v * 0.01, &s1, &c1);
+  if (__double_as_longlong(s0) != __double_as_longlong(s1)) atomicAdd(bad + 3, 1ULL);
+  if (__double_as_longlong(c0) != __double_as_longlong(c1)) atomicAdd(bad + 4, 1ULL);
+  const double w = v * v * 1e-6 + 1e-290 + t * 1e-9;
+  const double q0 = rsqrt(w), q1 = rfs::rsqrt_pos(w);
+  if (__double_as_longlong(q0) != __double_as_longlong(q1)) atomicAdd(bad + 5, 1ULL);
+}
+
 __global__ void dfma_peak_kernel(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
          a6 = a0 + 6, a7 = a0 + 7;
@@ -924,6 +954,26 @@ int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *tflops = best;
+  return RFS_OK;
+}
+
+// Self-test of the constant-bank math used by the root search: exp_neg / sincos_cb / rsqrt_pos must be
+// bit-identical to the CUDA math library on their fast-path ranges.  n pseudo-random arguments are
+// generated on the device; mismatches[0..5] = exp, sin (large), cos (large), sin (small),
+// cos (small), rsqrt.
+int rfs_selftest_math(rfs_ctx *ctx, long long n, long long *mismatches) {
+  if (!ctx || !mismatches || n <= 0) return RFS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure(ctx, ctx->io_a, sizeof(unsigned long long) * 6);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(ctx->io_a.p, 0, sizeof(unsigned long long) * 6, ctx->stream));
+  math_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      n, (unsigned long long *)ctx->io_a.p);
+  ctx->launches++;
+  unsigned long long h[6];
+  CK(cudaMemcpyAsync(h, ctx->io_a.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 6; i++) mismatches[i] = (long long)h[i];
   return RFS_OK;
 }
 

@@ -27,6 +27,13 @@ def test_native_library_is_loaded(ctx):
     assert ctx.launches > l0
 
 
+def test_constant_bank_math_is_bit_identical_to_the_cuda_library(ctx):
+    """The root search replaces exp / sincos / rsqrt by versions whose coefficients are constant-bank
+    operands (fewer issue slots); the phase velocities only stay bit-identical to the previous build
+    -- and as close to the oracle -- if these reproduce the CUDA library bit for bit."""
+    assert ctx.selftest_math(1 << 22) == [0, 0, 0, 0, 0, 0]
+
+
 def test_libsurf_dropin_vs_golden(ctx):
     g = np.load(os.path.join(G, "f1_dropin.npz"))
     thk, vs, vp, rho, T = g["thk"], g["vs"], g["vp"], g["rho"], g["T"]
