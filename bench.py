@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hmc", action="store_true", help="skip the short device-resident HMC leg")
+    ap.add_argument("--hmc-traj", type=int, default=10, help="trajectories per chain in the HMC leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -263,7 +264,7 @@ def main():
         from rfsurfhmc_b200.fixtures import driver_bounds
         from rfsurfhmc_b200.distributed import shard_chains
         ids = shard_chains(B * world, rank, world)
-        ntraj = 4
+        ntraj = args.hmc_traj
         barrier()
         t0 = time.perf_counter()
         ho = ctx.hmc_run(0, ids, driver_bounds(x0), 0.02, Lrange=(20, 20), seed=991206, nsamples=ntraj,
@@ -285,7 +286,7 @@ def main():
             dist.all_reduce(hv, op=dist.ReduceOp.SUM)
         th = float(hmax[0])
         hmc = {"sampler": "HamitonianMC, L=20, dt=0.02, %d chains/GPU, %d trajectories each (initial models, "
-                          "includes chain initialisation and the first evaluation)" % (B, 4),
+                          "includes chain initialisation and the first evaluation)" % (B, args.hmc_traj),
                "trajectories_per_s": float(hv[1]) / th, "accepted_samples_per_s": float(hv[2]) / th,
                "evals_per_s": float(hv[3]) / th, "seconds": th}
     value = world * B * args.steps / (ms * 1e-3)

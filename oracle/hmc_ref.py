@@ -12,6 +12,7 @@ very stream the reference draws from, so it pins the device MT19937 + Box-Muller
 implementation as well as the accept/reject logic.  Unlike the reference it returns the per-iteration
 accept flags and stops after `max_iters` trajectories.
 """
+import math
 import numpy as np
 
 
@@ -48,6 +49,7 @@ def _mirror(x, p, bounds):
     lo, hi = bounds[:, 0], bounds[:, 1]
     i1 = x > hi
     i2 = x < lo
+    it = 0
     while np.sum(np.logical_or(i1, i2)) > 0:
         x[i1] = 2 * hi[i1] - x[i1]
         p[i1] = -p[i1]
@@ -55,6 +57,24 @@ def _mirror(x, p, bounds):
         p[i2] = -p[i2]
         i1 = x > hi
         i2 = x < lo
+        it += 1
+        if it >= 64:
+            # the reference keeps bouncing (|x|/(hi-lo) passes, forever for +-inf); fold the
+            # remainder in closed form exactly as rfsurfhmc_b200/csrc/hmc_kernels.cuh does
+            for j in np.nonzero(np.logical_or(i1, i2))[0]:
+                w = hi[j] - lo[j]
+                u = x[j] - lo[j]
+                if u < 0.0:
+                    u = -u
+                    p[j] = -p[j]
+                y = math.fmod(u, 2.0 * w) if np.isfinite(u) and w != 0.0 else np.nan
+                if y > w:
+                    y = 2.0 * w - y
+                    p[j] = -p[j]
+                x[j] = lo[j] + y
+                if not (lo[j] <= x[j] <= hi[j]):
+                    x[j] = np.nan
+            break
     return x, p
 
 

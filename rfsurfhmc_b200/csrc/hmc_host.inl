@@ -132,7 +132,7 @@ int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_i
   LAUNCH(hmc_init_kernel, gridFor(C, 64), 64, 0, st, D, cfg, C, (const long long *)d_ids, seed);
   int h_active = 1;
   long long steps = 0;
-  const int check_every = 16;
+  const int check_every = 4;  // one stream sync per 4 global steps: at most 3 wasted steps at the end
   while (h_active > 0) {
     for (int s = 0; s < check_every; s++) {
       rc = rfs_misfit_grad_dev(ctx, C, D.xeval, 0, (double *)ctx->io_U.p, (double *)ctx->io_grad.p,

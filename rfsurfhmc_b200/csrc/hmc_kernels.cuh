@@ -170,8 +170,25 @@ RFS_DEVINL bool hmc_mirror(const HmcDev &D, const HmcCfg &cfg, long long c) {
         x = 2 * lo - x;
         p = -p;
       }
-      if (++it > 100000) {  // +-inf would bounce forever in the reference; poison instead
-        x = nan("");
+      if (++it >= 64 && (x > hi || x < lo)) {
+        // A state with a huge gradient throws x out by many box widths; the reference would bounce
+        // |x|/(hi-lo) times (effectively forever).  After 64 exact bounces fold the rest in closed
+        // form: same position up to rounding, same momentum sign, and the trajectory carries on to
+        // its (certain) rejection with the RNG stream intact.  +-inf and hi==lo give NaN here
+        // (the reference never returns).
+        const double w = hi - lo;
+        double u = x - lo;
+        if (u < 0.0) {
+          u = -u;
+          p = -p;
+        }
+        double y = fmod(u, 2.0 * w);
+        if (y > w) {
+          y = 2.0 * w - y;
+          p = -p;
+        }
+        x = lo + y;
+        if (!(x >= lo && x <= hi)) x = nan("");
         break;
       }
     }
