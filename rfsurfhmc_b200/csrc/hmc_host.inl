@@ -44,6 +44,9 @@ void carve_hmc(Carver &cv, HmcDev &D, long long C, int n2, int nd) {
   D.nevals = cv.take<long long>(C);
   D.mt = cv.take<unsigned int>(C * 624);
   D.n_active = cv.take<int>(4);
+  D.slot = cv.take<int>(C);
+  D.idx = cv.take<int>(C);
+  D.xg = cv.take<double>(C * n2);
 }
 
 }  // namespace
@@ -132,18 +135,28 @@ int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_i
   LAUNCH(hmc_init_kernel, gridFor(C, 64), 64, 0, st, D, cfg, C, (const long long *)d_ids, seed);
   int h_active = 1;
   long long steps = 0;
+  long long Ba = C;      // rows of the evaluated batch
+  bool packed = false;   // false: row == chain
   const int check_every = 4;  // one stream sync per 4 global steps: at most 3 wasted steps at the end
   while (h_active > 0) {
     for (int s = 0; s < check_every; s++) {
-      rc = rfs_misfit_grad_dev(ctx, C, D.xeval, 0, (double *)ctx->io_U.p, (double *)ctx->io_grad.p,
-                               (double *)ctx->io_dsyn.p, (unsigned char *)ctx->io_flag.p, st);
+      if (packed) LAUNCH(hmc_gather_kernel, gridFor(Ba * n2, 256), 256, 0, st, D, n2, Ba);
+      rc = rfs_misfit_grad_dev(ctx, Ba, packed ? D.xg : D.xeval, 0, (double *)ctx->io_U.p,
+                               (double *)ctx->io_grad.p, (double *)ctx->io_dsyn.p,
+                               (unsigned char *)ctx->io_flag.p, st);
       if (rc) return rc;
-      if (s == check_every - 1) CK(cudaMemsetAsync(D.n_active, 0, sizeof(int), st));
+      if (s == check_every - 1) CK(cudaMemsetAsync(D.n_active, 0, 2 * sizeof(int), st));
       LAUNCH(hmc_advance_kernel, gridFor(C, 64), 64, 0, st, D, cfg, C);
       steps++;
     }
     CK(cudaMemcpyAsync(&h_active, D.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    // re-pack once at least 1/16 of the evaluated rows belong to finished chains
+    if (h_active > 0 && (long long)h_active <= Ba - std::max<long long>(1, Ba / 16)) {
+      LAUNCH(hmc_compact_kernel, gridFor(C, 256), 256, 0, st, D, C);
+      Ba = h_active;
+      packed = true;
+    }
   }
   // results
   std::vector<long long> nev(C);

@@ -47,7 +47,11 @@ struct HmcDev {
   double *samples, *misfit, *syn, *initmodel;
   signed char *alog;
   const double *bounds;  // [n2][2]
-  int *n_active;
+  int *n_active;         // [0] chains still running after the last advance, [1] compaction counter
+  // compaction of the evaluation batch once chains have finished: slot[c] = row of chain c in the
+  // evaluated batch (-1: finished), idx[j] = chain of row j, xg = gathered positions [Ba][n2]
+  int *slot, *idx;
+  double *xg;
 };
 
 struct Rng {
@@ -238,6 +242,7 @@ __global__ void hmc_init_kernel(HmcDev D, HmcCfg cfg, long long C, const long lo
     if (D.initmodel) D.initmodel[c * n2 + i] = x[i];
   }
   D.phase[c] = HP_INIT;
+  D.slot[c] = (int)c;
   D.istep[c] = 0;
   D.L[c] = 0;
   D.okcur[c] = 0;
@@ -256,6 +261,28 @@ __global__ void hmc_init_kernel(HmcDev D, HmcCfg cfg, long long C, const long lo
   rng_store(D, r);
 }
 
+// Chains finish at different times (random L, rejections, stuck chains): re-pack the running ones so
+// that the forward model is only evaluated for them.  Row order is arbitrary (atomic counter); every
+// chain's results are independent of its row.
+__global__ void hmc_compact_kernel(HmcDev D, long long C) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (D.phase[c] != HP_DONE) {
+    const int j = atomicAdd(D.n_active + 1, 1);
+    D.slot[c] = j;
+    D.idx[j] = (int)c;
+  } else {
+    D.slot[c] = -1;
+  }
+}
+__global__ void hmc_gather_kernel(HmcDev D, int n2, long long Ba) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= Ba * n2) return;
+  const long long j = t / n2;
+  const int i = (int)(t % n2);
+  D.xg[t] = D.xeval[(long long)D.idx[j] * n2 + i];
+}
+
 RFS_DEVINL bool any_nan(const double *v, int n) {
   bool f = false;
   for (int i = 0; i < n; i++) f = f || isnan(v[i]);
@@ -272,9 +299,10 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
   Rng r = rng_load(D, C, c);
   double *xcur = D.xcur + c * n2, *xnew = D.xnew + c * n2, *pnew = D.pnew + c * n2,
          *gcur = D.gcur + c * n2, *dcur = D.dcur + c * nd, *xev = D.xeval + c * n2;
-  const double *ge = D.ge + c * n2, *de = D.de + c * nd;
-  const double Ue = D.Ue[c];
-  const bool fe = D.fe[c] != 0;
+  const long long e = D.slot[c];  // row of this chain in the evaluated batch
+  const double *ge = D.ge + e * n2, *de = D.de + e * nd;
+  const double Ue = D.Ue[e];
+  const bool fe = D.fe[e] != 0;
   D.nevals[c] += 1;
   double dt = D.dt[c];
   const double log_half = log(0.5);

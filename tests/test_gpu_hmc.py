@@ -55,6 +55,22 @@ def test_dual_averaging_sampler_parity(ctx, oracle):
         assert np.isclose(out["dt"][i], R.dt, rtol=1e-6)
 
 
+def test_batch_compaction_leaves_every_chain_unchanged(ctx):
+    """Chains draw different L and reject differently, so they finish at different global steps;
+    the driver re-packs the evaluated batch as they finish.  A chain's samples must not depend on
+    which other chains ran beside it: 48 chains together == the same chains in two smaller runs."""
+    cfg, dobs, bounds = _setup(ctx)
+    ids = np.arange(48)
+    kw = dict(seed=991206, nsamples=6, ndraws=1, max_iters=14, want_samples=True, log_accepts=14)
+    full = ctx.hmc_run(0, ids, bounds, 0.1, Lrange=(5, 20), **kw)
+    assert len(set(full["n_iter"].tolist())) > 1  # chains really do finish at different times
+    for part in (ids[:5], ids[29:48]):
+        sub = ctx.hmc_run(0, part, bounds, 0.1, Lrange=(5, 20), **kw)
+        for k in ("samples", "misfit", "n_iter", "n_acc", "accept_seq", "initmodel"):
+            if k in full and full[k] is not None:
+                assert np.array_equal(np.asarray(full[k])[part], np.asarray(sub[k]), equal_nan=True), k
+
+
 def test_sampler_front_ends_and_result_files(ctx, tmp_path):
     import yaml
     from rfsurfhmc_b200 import driver
