@@ -143,3 +143,20 @@ def test_hmc_reference_restatement_on_quadratic_model():
     R2 = hmc_ref.run_da(f, bounds, 0.1, 10, 0.65, 43, nsamples=300, ndraws=100)
     assert R2.n_acc == 400
     assert 0.4 < np.mean(R2.accepts[150:]) < 0.9
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs the CPU restatement on the host cores (no GPU needed) and
+    prints ONE JSON line with the keys the driver reads."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["value"] > 0
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
