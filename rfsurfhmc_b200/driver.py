@@ -90,6 +90,9 @@ def main():
         print("chains %d, accepted samples %d, mean accept ratio %.3f" %
               (misfit.shape[0], misfit.size, (misfit.shape[1] + param['hmc']['ndraws']) / n_iter.mean()))
         print("time elapse: {}".format(time.time() - tic))
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
