@@ -26,14 +26,16 @@ struct VSV {
   double c, rs, sr, ex;  // cos-like, r*sinh-like, sinh-like/r, exponent
   bool imag;             // vertical wavenumber purely imaginary (oscillatory)
   double r;              // |nu|
+  double ri;             // 1/|nu| (0 when nu = 0)
   double e;              // exp(-ex): exp(-2 ex) = e*e and exp(-(ex_p+ex_s)) = e_p*e_s (one exp per half)
 };
 RFS_DEVINL VSV varsv_half(double s, double zd) {
   VSV o;
   const double small = (double)1.0e-5f;
   const double as = fabs(s);
-  const double ri = (as > 0.0) ? rsqrt(as) : 0.0;  // r = |s| rsqrt(|s|), 1/r = rsqrt(|s|)
+  const double ri = (as > 0.0) ? rsqrt_pos(as) : 0.0;  // r = |s| rsqrt(|s|), 1/r = rsqrt(|s|)
   o.r = as * ri;
+  o.ri = ri;
   if (s >= 0.0) {
     o.imag = false;
     const double pr = o.r * zd;
@@ -160,8 +162,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   const double iwv = 1.0 / wvno, iwv2 = iwv * iwv, iomega = 1.0 / omega, iom2 = iomega * iomega;
   const double slow = wvno * iomega;  // 1/c
   double cdl[NMAX * 6];  // [m][0..4] = cd, [m][5] = exe   (thread-local, L1-backed)
-  double vsl[NMAX * 10]; // varsv results of the up-sweep, reused by the down-sweep:
-                         // [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S; r < 0 <=> imaginary
+  double vsl[NMAX * 12]; // varsv results of the up-sweep, reused by the down-sweep:
+                         // [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S (r < 0 <=> imaginary), [m][10..11] = 1/r
 
   // ---------------- up-sweep (:404-492): half-space vector from evalg (:736-768)
   {
@@ -202,21 +204,24 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       S.sr = 0.0;
       S.ex = 0.0;
       S.r = 0.0;
+      S.ri = 0.0;
       S.e = 1.0;
       S.imag = false;
     } else {
       S = varsv_half(wvno2 - xkb * xkb, zd);
     }
-    vsl[m * 10 + 0] = P.c;
-    vsl[m * 10 + 1] = P.rs;
-    vsl[m * 10 + 2] = P.sr;
-    vsl[m * 10 + 3] = P.ex;
-    vsl[m * 10 + 4] = P.imag ? -P.r : P.r;
-    vsl[m * 10 + 5] = S.c;
-    vsl[m * 10 + 6] = S.rs;
-    vsl[m * 10 + 7] = S.sr;
-    vsl[m * 10 + 8] = S.ex;
-    vsl[m * 10 + 9] = S.imag ? -S.r : S.r;
+    vsl[m * 12 + 0] = P.c;
+    vsl[m * 12 + 1] = P.rs;
+    vsl[m * 12 + 2] = P.sr;
+    vsl[m * 12 + 3] = P.ex;
+    vsl[m * 12 + 4] = P.imag ? -P.r : P.r;
+    vsl[m * 12 + 5] = S.c;
+    vsl[m * 12 + 6] = S.rs;
+    vsl[m * 12 + 7] = S.sr;
+    vsl[m * 12 + 8] = S.ex;
+    vsl[m * 12 + 9] = S.imag ? -S.r : S.r;
+    vsl[m * 12 + 10] = P.ri;
+    vsl[m * 12 + 11] = S.ri;
     const double d0 = cdl[(m + 1) * 6 + 0], d1 = cdl[(m + 1) * 6 + 1], d2 = cdl[(m + 1) * 6 + 2],
                  d3 = cdl[(m + 1) * 6 + 3], d4 = cdl[(m + 1) * 6 + 4];
     double n0, n1, n2, n3, n4;
@@ -326,27 +331,34 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
 
     // ---- nu_a, nu_b of this layer; they come from the up-sweep when available
     cd ra, rb;
+    double ria, rib;  // 1/|nu_a|, 1/|nu_b| (0 for a vanishing wavenumber)
     if (!half) {
-      const double sra = vsl[m * 10 + 4], srb = vsl[m * 10 + 9];
+      const double sra = vsl[m * 12 + 4], srb = vsl[m * 12 + 9];
       ra = mk(sra < 0.0 || (sra == 0.0 && sa < 0.0), fabs(sra));
       rb = mk(srb < 0.0 || (srb == 0.0 && sb < 0.0), fabs(srb));
+      ria = vsl[m * 12 + 10];
+      rib = vsl[m * 12 + 11];
     } else {
-      ra = mk(sa < 0.0, sqrt(fabs(sa)));
-      rb = mk(sb < 0.0, sqrt(fabs(sb)));
+      const double asa = fabs(sa), asb = fabs(sb);
+      ria = (asa > 0.0) ? rsqrt_pos(asa) : 0.0;
+      rib = (asb > 0.0) ? rsqrt_pos(asb) : 0.0;
+      ra = mk(sa < 0.0, asa * ria);
+      rb = mk(sb < 0.0, asb * rib);
     }
-    const cd ira = cinv(ra);
+    // 1/nu for a real or purely imaginary nu: 1/r or -i/r
+    const cd ira = (ra.y != 0.0) ? cd(0.0, -ria) : cd(ria, 0.0);
 
     Eig4 eb = et;  // eigenfunction at the bottom of the layer (top of m+1)
     VSV P, S;
     if (!half) {
-      P.c = vsl[m * 10 + 0];
-      P.rs = vsl[m * 10 + 1];
-      P.sr = vsl[m * 10 + 2];
-      P.ex = vsl[m * 10 + 3];
-      S.c = vsl[m * 10 + 5];
-      S.rs = vsl[m * 10 + 6];
-      S.sr = vsl[m * 10 + 7];
-      S.ex = vsl[m * 10 + 8];
+      P.c = vsl[m * 12 + 0];
+      P.rs = vsl[m * 12 + 1];
+      P.sr = vsl[m * 12 + 2];
+      P.ex = vsl[m * 12 + 3];
+      S.c = vsl[m * 12 + 5];
+      S.rs = vsl[m * 12 + 6];
+      S.sr = vsl[m * 12 + 7];
+      S.ex = vsl[m * 12 + 8];
       double w0, w1, w2, w3;
       if (wat) {
         // fluid Haskell step (hska :930-944)
@@ -444,7 +456,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       double gam = zb * slow;
       gam = 2.0 * (gam * gam);
       const double gamm1 = gam - 1.0;
-      const cd irb = cinv(rb);
+      const cd irb = (rb.y != 0.0) ? cd(0.0, -rib) : cd(rib, 0.0);
       // EINV rows (acting on [ur, uz, tz, tr])
       const double ei11 = 0.5 * gam * iwv, ei13 = -0.5 * irom2;
       const cd ei12 = (-0.5 * gamm1) * ira, ei14 = (0.5 * wvno * irom2) * ira;
