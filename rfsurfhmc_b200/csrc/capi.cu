@@ -56,6 +56,8 @@ struct rfs_ctx {
   Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
   Buf w_rstat;
   Buf w_rfl;  // RfLayer table [B][n]
+  Buf d_tw;   // FFT twiddle factors exp(-i pi j/(nft/2)), j < nft/2
+  int tw_nft = 0;
   Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
       w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
@@ -298,7 +300,7 @@ int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, doub
   LAUNCH(rf_decon_kernel, (unsigned)B, decon_threads(ctx->nft), sm, st,
          (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt,
          ctx->nft, ctx->logn, ctx->dt, ctx->gauss, tshift, ctx->water, sigma, d_dobs, d_rf, ldrf,
-         d_U, d_grad);
+         d_U, d_grad, (const double2 *)ctx->d_tw.p);
   return RFS_OK;
 }
 
@@ -316,7 +318,8 @@ int run_rf_time(rfs_ctx *ctx, long long B, int nrow, double *d_rf, long long ldr
     CK(cudaFuncSetAttribute(rf_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   LAUNCH(rf_time_kernel, (unsigned)(B * (nrow + 1)), decon_threads(ctx->nft), sm, st,
          (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt, ctx->nft,
-         ctx->logn, ctx->dt, ctx->gauss, tshift, d_rf, ldrf, (double *)ctx->w_rftr.p);
+         ctx->logn, ctx->dt, ctx->gauss, tshift, d_rf, ldrf, (double *)ctx->w_rftr.p,
+         (const double2 *)ctx->d_tw.p);
   return RFS_OK;
 }
 
@@ -349,6 +352,15 @@ int set_rf_cfg(rfs_ctx *ctx, int n, double ray_p, int nt, double dt, double gaus
   ctx->n2 = nft / 2 + 1;
   if (std::max(decon_smem(nft, ctx->n2), time_smem(nft, ctx->n2)) > 220 * 1024)
     return fail(ctx, RFS_E_ARG, "nt too large (max 4096 samples after padding)");
+  if (ctx->tw_nft != nft) {  // FFT twiddle factors of this transform length
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure(ctx, ctx->d_tw, sizeof(double2) * (size_t)(nft / 2));
+    if (rc) return rc;
+    fft_twiddle_kernel<<<(nft / 2 + 127) / 128, 128, 0, ctx->stream>>>(nft, (double2 *)ctx->d_tw.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tw_nft = nft;
+  }
   return RFS_OK;
 }
 
@@ -406,7 +418,7 @@ int rfs_create(rfs_ctx **out, int device) {
 void rfs_destroy(rfs_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain, &ctx->w_rfl,
+  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain, &ctx->w_rfl, &ctx->d_tw,
                 &ctx->w_croot, &ctx->w_cwork, &ctx->w_ugr, &ctx->w_kern, &ctx->w_ierr,
                 &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
@@ -813,7 +825,8 @@ static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const 
         CK(cudaFuncSetAttribute(rf_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
       LAUNCH(rf_trace_kernel, (unsigned)(B * nrow), decon_threads(ctx->nft), sm, st,
              (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, nt, ctx->nft,
-             ctx->logn, dt, gauss, tshift, water, sigma, (double *)ctx->w_rftr.p);
+             ctx->logn, dt, gauss, tshift, water, sigma, (double *)ctx->w_rftr.p,
+             (const double2 *)ctx->d_tw.p);
     }
     if (nq == 4) {
       CK(cudaMemcpyAsync(drf, ctx->w_rftr.p, sizeof(double) * (size_t)B * nrow * nt,

@@ -431,7 +431,16 @@ __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
 // ------------------------------------------------------------------ shared-memory FFT
 // In-place radix-2 DIT on `buf[N]` (N power of two), executed by the whole block.
 // sign = -1: forward (e^{-i..}), +1: backward; unnormalised (FFTW convention).
-RFS_DEVINL void block_fft(cd *buf, int N, int logN, int sign) {
+// tw[j] = exp(-i pi j / (N/2)), j < N/2 (fft_twiddle_kernel): the butterflies look their factors
+// up instead of evaluating sincospi per butterfly and stage (the same values, bit for bit).
+__global__ void fft_twiddle_kernel(int N, double2 *__restrict__ tw) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N / 2) return;
+  double sn, cs;
+  sincospi(-(double)j / (double)(N / 2), &sn, &cs);
+  tw[j] = make_double2(cs, sn);
+}
+RFS_DEVINL void block_fft(cd *buf, int N, int logN, int sign, const double2 *__restrict__ tw) {
   const int tid = threadIdx.x, nth = blockDim.x;
   // bit reversal
   for (int i = tid; i < N; i += nth) {
@@ -448,9 +457,8 @@ RFS_DEVINL void block_fft(cd *buf, int N, int logN, int sign) {
     for (int t = tid; t < N / 2; t += nth) {
       const int grp = t >> (s - 1), pos = t & (half - 1);
       const int i0 = (grp << s) + pos, i1 = i0 + half;
-      double sn, cs;
-      sincospi((double)sign * (double)pos / (double)half, &sn, &cs);
-      const cd wv(cs, sn);
+      const double2 w = __ldg(tw + (pos << (logN - s)));
+      const cd wv(w.x, sign < 0 ? w.y : -w.y);
       const cd u = buf[i0], v = buf[i1] * wv;
       buf[i0] = u + v;
       buf[i1] = u - v;
@@ -491,7 +499,7 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
                                 double f0, double t0, double water, double sigma,
                                 const double *__restrict__ dobs, double *__restrict__ rf,
                                 long long ldrf, double *__restrict__ U,
-                                double *__restrict__ grad) {
+                                double *__restrict__ grad, const double2 *__restrict__ tw) {
   extern __shared__ double smem[];
   const int n2 = nft / 2 + 1;
   cd *buf = reinterpret_cast<cd *>(smem);
@@ -526,7 +534,7 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
     }
   }
   __syncthreads();
-  block_fft(buf, nft, logn, +1);
+  block_fft(buf, nft, logn, +1, tw);
   // trace, residual, weighted residual (:404-407 and the adjoint source)
   double lsum = 0.0;
   for (int it = tid; it < nft; it += nth) {
@@ -548,7 +556,7 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
   if (tid == 0) U[b] = 0.5 * ss;
   if (grad == nullptr) return;
   __syncthreads();
-  block_fft(buf, nft, logn, -1);
+  block_fft(buf, nft, logn, -1, tw);
   // second water level on |R21^2|^2 (:410-413) and adjoint weights
   double lmax2 = 0.0;
   for (int k = tid; k < n2; k += nth) {
@@ -589,7 +597,7 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
 __global__ void rf_trace_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
                                 long long B, int nrow, int nt, int nft, int logn, double dt,
                                 double f0, double t0, double water, double sigma,
-                                double *__restrict__ out) {
+                                double *__restrict__ out, const double2 *__restrict__ tw) {
   extern __shared__ double smem[];
   const int n2 = nft / 2 + 1;
   cd *buf = reinterpret_cast<cd *>(smem);
@@ -623,7 +631,7 @@ __global__ void rf_trace_kernel(const double2 *__restrict__ spec, const double2 
     }
   }
   __syncthreads();
-  block_fft(buf, nft, logn, +1);
+  block_fft(buf, nft, logn, +1, tw);
   for (int it = tid; it < nt; it += nth)
     out[(b * nrow + rr) * (long long)nt + it] = buf[it].x / nft / dt * exp(sigma * (-t0 + it * dt));
 }

@@ -31,7 +31,7 @@ RFS_DEVINL double half_power(const cd *X, int N, double *red) {
 __global__ void rf_time_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
                                long long B, int nrow, int nt, int nft, int logn, double dt,
                                double f0, double tshift, double *__restrict__ rf, long long ldrf,
-                               double *__restrict__ traces) {
+                               double *__restrict__ traces, const double2 *__restrict__ tw) {
   extern __shared__ double smem[];
   const int n2 = nft / 2 + 1;
   cd *buf = reinterpret_cast<cd *>(smem);
@@ -92,7 +92,7 @@ __global__ void rf_time_kernel(const double2 *__restrict__ spec, const double2 *
       }
     }
     __syncthreads();
-    block_fft(buf, nft, logn, +1);
+    block_fft(buf, nft, logn, +1, tw);
     // first maximum of |cuw| over the first nft/2 lags (maxloc, deconit.f90:178)
     double best = -1.0;
     int bi = 0x7fffffff;
@@ -139,10 +139,12 @@ __global__ void rf_time_kernel(const double2 *__restrict__ spec, const double2 *
     // P += amp * rfft(delta_idx);  new residual power by Parseval
     double l = 0.0;
     for (int k = tid; k < n2; k += nth) {
-      double sn, cs;
-      const long long kk = ((long long)k * idx) % nft;
-      sincospi(-2.0 * (double)kk / (double)nft, &sn, &cs);
-      const cd pk = P[k] + amp * cd(cs, sn);
+      // exp(-2 pi i k idx / nft) from the twiddle table (second half of the circle by symmetry)
+      const int kk = (int)(((long long)k * idx) % nft);
+      const int hN = nft >> 1;
+      const double2 tf = __ldg(tw + (kk < hN ? kk : kk - hN));
+      const cd ph = (kk < hN) ? cd(tf.x, tf.y) : cd(-tf.x, -tf.y);
+      const cd pk = P[k] + amp * ph;
       P[k] = pk;
       const cd R = Uf[k] - dt * (pk * Wc[k]);
       const double w = (k == 0 || k == nft / 2) ? 1.0 : 2.0;
@@ -168,7 +170,7 @@ __global__ void rf_time_kernel(const double2 *__restrict__ spec, const double2 *
     }
   }
   __syncthreads();
-  block_fft(buf, nft, logn, +1);
+  block_fft(buf, nft, logn, +1, tw);
   double *dst = (r == 0) ? rf + b * ldrf : traces + (b * (long long)nrow + (r - 1)) * nt;
   for (int t = tid; t < nt; t += nth) dst[t] = buf[t].x / nft;
 }

@@ -80,6 +80,15 @@ def main():
         print(f"# C3 p={p}: {t*1e3:.1f} ms", file=sys.stderr)
     print(json.dumps({"config": "C3 RF-only forward+Frechet (freq): n=40, nt=2048, a=2.5, 3 ray parameters (3 calls)",
                       "batch": B, "models_per_s": B / tot, "seconds": tot}))
+    # ---- C3, time-domain method (iterative deconvolution of the forward trace and of all 4n Frechet
+    # traces, <= 200 iterations each): a bounded sub-batch, one ray parameter
+    Bt = min(B, 256)
+    ctx.config_rf(n, 0.06, nt, 0.05, 2.5, 5.0, 1e-3, "P", "time")
+    ctx.config_obs(np.zeros(nt))
+    t = timed(lambda: ctx.misfit_grad_dev(Bt, xd.data_ptr(), 1, U.data_ptr(), G.data_ptr(), D3.data_ptr(),
+                                          Fl.data_ptr(), st), reps=1)
+    print(json.dumps({"config": "C3 RF-only forward+Frechet (time-domain deconvolution): n=40, nt=2048, 1 ray parameter",
+                      "batch": Bt, "models_per_s": Bt / t, "seconds": t}))
 
 
 def cpu_leg():
