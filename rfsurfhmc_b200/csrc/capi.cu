@@ -295,8 +295,11 @@ int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, doub
                  long long ldrf, double *d_U, double *d_grad, double sigma, double tshift,
                  cudaStream_t st) {
   const size_t sm = decon_smem(ctx->nft, ctx->n2);
-  if (sm > 48 * 1024)
+  if (sm > 48 * 1024) {
     CK(cudaFuncSetAttribute(rf_decon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    CK(cudaFuncSetAttribute(rf_decon_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+  }
   LAUNCH(rf_decon_kernel, (unsigned)B, decon_threads(ctx->nft), sm, st,
          (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt,
          ctx->nft, ctx->logn, ctx->dt, ctx->gauss, tshift, ctx->water, sigma, d_dobs, d_rf, ldrf,
@@ -314,8 +317,12 @@ int run_rf_time(rfs_ctx *ctx, long long B, int nrow, double *d_rf, long long ldr
   if (nrow > 0)
     if ((rc = ensure(ctx, ctx->w_rftr, sizeof(double) * (size_t)B * nrow * ctx->nt))) return rc;
   const size_t sm = time_smem(ctx->nft, ctx->n2);
-  if (sm > 48 * 1024)
+  if (sm > 48 * 1024) {
     CK(cudaFuncSetAttribute(rf_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    // ask for the full shared-memory carve-out: two ~100 KB blocks per SM instead of one
+    CK(cudaFuncSetAttribute(rf_time_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            cudaSharedmemCarveoutMaxShared));
+  }
   LAUNCH(rf_time_kernel, (unsigned)(B * (nrow + 1)), decon_threads(ctx->nft), sm, st,
          (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt, ctx->nft,
          ctx->logn, ctx->dt, ctx->gauss, tshift, d_rf, ldrf, (double *)ctx->w_rftr.p,
@@ -821,8 +828,11 @@ static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const 
     if (method != 0) {
       if ((rc = ensure(ctx, ctx->w_rftr, sizeof(double) * (size_t)B * nrow * nt))) return done(rc);
       const size_t sm = decon_smem(ctx->nft, ctx->n2);
-      if (sm > 48 * 1024)
+      if (sm > 48 * 1024) {
         CK(cudaFuncSetAttribute(rf_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        CK(cudaFuncSetAttribute(rf_trace_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
+      }
       LAUNCH(rf_trace_kernel, (unsigned)(B * nrow), decon_threads(ctx->nft), sm, st,
              (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, nt, ctx->nft,
              ctx->logn, dt, gauss, tshift, water, sigma, (double *)ctx->w_rftr.p,

@@ -28,7 +28,7 @@ RFS_DEVINL double half_power(const cd *X, int N, double *red) {
 }
 
 // dynamic smem: cd buf[nft] + cd Uf[n2] + cd Wf[n2] + cd Wc[n2] + cd P[n2] + 64 doubles
-__global__ void rf_time_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
+__global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
                                long long B, int nrow, int nt, int nft, int logn, double dt,
                                double f0, double tshift, double *__restrict__ rf, long long ldrf,
                                double *__restrict__ traces, const double2 *__restrict__ tw) {
