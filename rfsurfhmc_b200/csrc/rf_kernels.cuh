@@ -440,6 +440,8 @@ __global__ void fft_twiddle_kernel(int N, double2 *__restrict__ tw) {
   sincospi(-(double)j / (double)(N / 2), &sn, &cs);
   tw[j] = make_double2(cs, sn);
 }
+// TW_SMEM: the table has been copied to shared memory by the caller (kernels that run many FFTs)
+template <bool TW_SMEM = false>
 RFS_DEVINL void block_fft(cd *buf, int N, int logN, int sign, const double2 *__restrict__ tw) {
   const int tid = threadIdx.x, nth = blockDim.x;
   // bit reversal
@@ -457,7 +459,7 @@ RFS_DEVINL void block_fft(cd *buf, int N, int logN, int sign, const double2 *__r
     for (int t = tid; t < N / 2; t += nth) {
       const int grp = t >> (s - 1), pos = t & (half - 1);
       const int i0 = (grp << s) + pos, i1 = i0 + half;
-      const double2 w = __ldg(tw + (pos << (logN - s)));
+      const double2 w = TW_SMEM ? tw[pos << (logN - s)] : __ldg(tw + (pos << (logN - s)));
       const cd wv(w.x, sign < 0 ? w.y : -w.y);
       const cd u = buf[i0], v = buf[i1] * wv;
       buf[i0] = u + v;

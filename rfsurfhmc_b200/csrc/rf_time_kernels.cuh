@@ -27,7 +27,7 @@ RFS_DEVINL double half_power(const cd *X, int N, double *red) {
   return block_reduce(l, red, false) / (double)N;
 }
 
-// dynamic smem: cd buf[nft] + cd Uf[n2] + cd Wf[n2] + cd Wc[n2] + cd P[n2] + 64 doubles
+// dynamic smem: cd buf[nft] + cd Uf[n2] + cd Wf[n2] + double2 twiddle[n2] + cd P[n2] + 64 doubles
 __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
                                long long B, int nrow, int nt, int nft, int logn, double dt,
                                double f0, double tshift, double *__restrict__ rf, long long ldrf,
@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
   cd *buf = reinterpret_cast<cd *>(smem);
   cd *Uf = buf + nft;
   cd *Wf = Uf + n2;
-  cd *Wc = Wf + n2;
-  cd *P = Wc + n2;
+  double2 *tws = reinterpret_cast<double2 *>(Wf + n2);  // twiddle table, nft/2 entries
+  cd *P = Wf + 2 * n2;
   double *red = reinterpret_cast<double *>(P + n2);
   const int nrow1 = nrow + 1;
   const long long b = blockIdx.x / nrow1;
@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     const double gx = 2 * RFS_PI32 * freq / f0;
     const double g = exp(-0.25 * (gx * gx));
     Uf[k] = su * g;
-    Wf[k] = sw * g;
-    Wc[k] = sw * g;  // G * rfft(wcopy): the factor G of apply_gaussian(temp1) is folded in here
+    Wf[k] = sw * g;  // also G * rfft(wcopy): the factor G of apply_gaussian(temp1) is the same g
     P[k] = cd(0.0, 0.0);
+    if (k < nft / 2) tws[k] = tw[k];
   }
   __syncthreads();
   const double pw = half_power(Wf, nft, red);
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     if (fabs(d_error) <= minderr) break;
     // cuw = irfft( rfft(rflt) conj(rfft(wflt)) ) dt ,  rfft(rflt) = Uf - dt P Wc
     for (int k = tid; k < n2; k += nth) {
-      const cd R = Uf[k] - dt * (P[k] * Wc[k]);
+      const cd R = Uf[k] - dt * (P[k] * Wf[k]);
       const cd c = R * conj(Wf[k]);
       if (k == 0 || k == nft / 2) {
         buf[k] = cd(c.x, 0.0);
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
       }
     }
     __syncthreads();
-    block_fft(buf, nft, logn, +1, tw);
+    block_fft<true>(buf, nft, logn, +1, tws);
     // first maximum of |cuw| over the first nft/2 lags (maxloc, deconit.f90:178)
     double best = -1.0;
     int bi = 0x7fffffff;
@@ -140,13 +140,13 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     double l = 0.0;
     for (int k = tid; k < n2; k += nth) {
       // exp(-2 pi i k idx / nft) from the twiddle table (second half of the circle by symmetry)
-      const int kk = (int)(((long long)k * idx) % nft);
+      const int kk = (k * idx) & (nft - 1);  // nft is a power of two, k*idx < 2^24
       const int hN = nft >> 1;
-      const double2 tf = __ldg(tw + (kk < hN ? kk : kk - hN));
+      const double2 tf = tws[kk < hN ? kk : kk - hN];
       const cd ph = (kk < hN) ? cd(tf.x, tf.y) : cd(-tf.x, -tf.y);
       const cd pk = P[k] + amp * ph;
       P[k] = pk;
-      const cd R = Uf[k] - dt * (pk * Wc[k]);
+      const cd R = Uf[k] - dt * (pk * Wf[k]);
       const double w = (k == 0 || k == nft / 2) ? 1.0 : 2.0;
       l += w * (k == 0 || k == nft / 2 ? R.x * R.x : norm2(R));
     }
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     }
   }
   __syncthreads();
-  block_fft(buf, nft, logn, +1, tw);
+  block_fft<true>(buf, nft, logn, +1, tws);
   double *dst = (r == 0) ? rf + b * ldrf : traces + (b * (long long)nrow + (r - 1)) * nt;
   for (int t = tid; t < nt; t += nth) dst[t] = buf[t].x / nft;
 }
