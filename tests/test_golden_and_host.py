@@ -160,3 +160,21 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_chain_result_file_and_best_mean_model(tmp_path):
+    """Per-chain result file (logical HDF5 layout of pyhmc/hmc.py:203-226 in an .npz) and the
+    nbest-average model (hmc.py:266-270); samplers refuse models without a device context."""
+    from rfsurfhmc_b200.pyhmc._common import write_chain_file, best_mean_model, require_device_model
+    rng = np.random.default_rng(3)
+    samples, syn = rng.random((12, 6)), rng.random((12, 9))
+    misfit = rng.random(12)
+    xm = best_mean_model(misfit, samples, 4)
+    assert np.allclose(xm, samples[np.argsort(misfit)[:4]].mean(axis=0))
+    path = tmp_path / "sub" / "chain_x.0.npz"
+    write_chain_file(str(path), samples[0], syn[0], xm, syn.mean(0), samples, syn)
+    z = np.load(path)
+    assert sorted(z.files) == sorted(["initmodel", "obs", "mean/model", "mean/syn", "models", "syn"])
+    assert np.array_equal(z["models"], samples) and np.array_equal(z["mean/model"], xm)
+    with pytest.raises(TypeError):
+        require_device_model(object())
