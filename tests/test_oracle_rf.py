@@ -87,3 +87,32 @@ def test_s_type_and_time_method_run(oracle):
     assert np.max(np.abs(rft - rff)) < 0.15 * np.max(np.abs(rff))
     with pytest.raises(ValueError):
         oracle.rf_forward(THK, RHO, VP, VS, Q, Q, 0.045, 125, 0.4, 1.5, 5.0, "freq", 0.001, "X")
+
+
+def test_layer_over_halfspace_conversion_and_multiple_times(oracle):
+    """Independent of any reference code: for one layer over a half-space the P receiver function
+    has its Ps conversion at H(eta_b - eta_a), the PpPs multiple at H(eta_b + eta_a) (both positive
+    for a velocity increase) and the PpSs+PsPs multiple at 2 H eta_b (negative), with
+    eta = sqrt(1/v^2 - p^2).  Pins timing, polarity and the time_shift convention of the trace."""
+    H, p, dt, nt, tshift = 35.0, 0.06, 0.05, 1024, 5.0
+    vs = np.array([3.5, 4.5]); vp = np.array([6.1, 8.0]); rho = np.array([2.7, 3.3])
+    thk = np.array([H, 0.0])
+    q = thk * 0 + 9999.
+    for method in ("freq", "time"):
+        rf = oracle.rf_forward(thk, rho, vp, vs, q, q, p, nt, dt, 3.0, tshift, method, 0.001, "P")
+        t = np.arange(nt) * dt - tshift
+        eta_a, eta_b = np.sqrt(1 / vp[0]**2 - p**2), np.sqrt(1 / vs[0]**2 - p**2)
+        t_ps, t_ppps, t_ppss = H * (eta_b - eta_a), H * (eta_b + eta_a), 2 * H * eta_b
+
+        def extremum(t0, sign):
+            w = np.abs(t - t0) < 0.6
+            k = np.argmax(sign * rf[w])
+            return t[w][k], rf[w][k]
+        k0 = np.argmax(rf)
+        assert abs(t[k0]) < 1.5 * dt and rf[k0] > 0           # direct P at t = 0
+        tp, ap = extremum(t_ps, +1)
+        assert abs(tp - t_ps) <= 2 * dt and 0.05 * rf[k0] < ap < rf[k0], method
+        tm, am = extremum(t_ppps, +1)
+        assert abs(tm - t_ppps) <= 2 * dt and am > 0.02 * rf[k0], method
+        tn, an = extremum(t_ppss, -1)
+        assert abs(tn - t_ppss) <= 2 * dt and an < -0.02 * rf[k0], method

@@ -39,6 +39,70 @@ def test_rayleigh_homogeneous_halfspace(oracle):
     assert ok and np.all(np.abs(u - cr) / cr < 5e-6)  # U == c without dispersion
 
 
+def test_rayleigh_layer_over_halfspace_limits_and_exact_secular_root(oracle):
+    """Layer over a half-space, independent of the reference code:
+    (i) short periods see only the layer, long periods only the half-space: c -> the analytic
+        Rayleigh speeds of the two media; the curve is monotonic in between;
+    (ii) at an intermediate period the root must annihilate the textbook 4x4 boundary-condition
+         determinant (free surface + welded interface + radiation), written here from scratch with
+         potentials in numpy -- a different formulation than the Dunkin compound matrix."""
+    H = 10.0
+    vs = np.array([3.0, 4.2]); vp = np.array([5.2, 7.4]); rho = np.array([2.5, 3.2]); thk = np.array([H, 0.0])
+    T = np.array([0.4, 1.0, 3.0, 8.0, 15.0, 40.0, 150.0, 600.0])
+    c, ok = oracle.surf_forward(thk, vp, vs, rho, T, "Rc")
+    assert ok and np.all(np.diff(c) > -1e-5)   # flat (non-dispersive) in the short-period limit
+    f32 = lambda v: float(np.float32(v))
+    assert abs(c[0] - rayleigh_halfspace_speed(f32(vp[0]), f32(vs[0]))) < 2e-4 * c[0]
+    assert abs(c[-1] - rayleigh_halfspace_speed(f32(vp[1]), f32(vs[1]))) < 5e-3 * c[-1]  # H/lambda = 0.4 %
+
+    def det(cc, Tp):
+        # P-SV potentials: layer phi = A e^{-ra z} + B e^{ra z}, psi = C e^{-rb z} + D e^{rb z};
+        # half-space: decaying only.  Unknowns (A,B,C,D,E,F); 6 conditions: 2 stress-free at z=0,
+        # 4 continuity at z=H.  cc below both half-space speeds; layer terms may be oscillatory.
+        w = 2 * np.pi / Tp
+        k = w / cc
+        a1, b1, a2, b2 = (f32(v) for v in (vp[0], vs[0], vp[1], vs[1]))
+        r1, r2 = f32(rho[0]), f32(rho[1])
+        ra1 = np.sqrt(complex(k * k - (w / a1)**2)); rb1 = np.sqrt(complex(k * k - (w / b1)**2))
+        ra2 = np.sqrt(complex(k * k - (w / a2)**2)); rb2 = np.sqrt(complex(k * k - (w / b2)**2))
+        mu1, mu2 = r1 * b1 * b1, r2 * b2 * b2
+
+        def col_p(r, mu, bvel, z, sgn):   # phi = e^{sgn r z}: (ux, uz, tzz, txz)/e^{..}, e^{i(kx-wt)} dropped
+            e = np.exp(sgn * r * z)
+            lam2mu_term = mu * (2 * k * k - (w / bvel)**2)   # lambda*laplacian + 2 mu d2/dz2 of phi
+            return np.array([1j * k, sgn * r, lam2mu_term, 2j * mu * k * sgn * r]) * e
+
+        def col_s(r, mu, bvel, z, sgn):   # psi = e^{sgn r z}: ux = -dpsi/dz, uz = dpsi/dx
+            e = np.exp(sgn * r * z)
+            return np.array([-sgn * r, 1j * k, 2j * mu * k * sgn * r, -mu * (2 * k * k - (w / bvel)**2)]) * e
+        M = np.zeros((6, 6), dtype=complex)
+        cols0 = [col_p(ra1, mu1, b1, 0.0, -1), col_p(ra1, mu1, b1, 0.0, +1),
+                 col_s(rb1, mu1, b1, 0.0, -1), col_s(rb1, mu1, b1, 0.0, +1)]
+        colsH = [col_p(ra1, mu1, b1, H, -1), col_p(ra1, mu1, b1, H, +1),
+                 col_s(rb1, mu1, b1, H, -1), col_s(rb1, mu1, b1, H, +1)]
+        half = [col_p(ra2, mu2, b2, 0.0, -1), col_s(rb2, mu2, b2, 0.0, -1)]
+        for j in range(4):
+            M[0, j], M[1, j] = cols0[j][2], cols0[j][3]          # tzz = txz = 0 at the surface
+            M[2:6, j] = colsH[j]                                   # continuity of (ux, uz, tzz, txz)
+        for j in range(2):
+            M[2:6, 4 + j] = -half[j]
+        # scale the growing columns so that the determinant stays O(1)
+        M[:, 1] /= np.exp(ra1.real * H) if ra1.real > 0 else 1.0
+        M[:, 3] /= np.exp(rb1.real * H) if rb1.real > 0 else 1.0
+        return np.linalg.det(M)
+
+    for Tp, ck in ((3.0, c[2]), (8.0, c[3]), (15.0, c[4])):
+        cs = ck * (1 + np.array([-2e-4, -1e-4, 0.0, 1e-4, 2e-4]))
+        d = np.array([det(x, Tp) for x in cs])
+        # the determinant is (up to a constant phase) real and changes sign at the root:
+        ph = d[0] / abs(d[0])
+        dr = (d / ph).real
+        assert np.sign(dr[0]) != np.sign(dr[-1]), (Tp, dr)
+        # linear interpolation of the sign change lands on the reported root within float32 + 1e-6
+        root = cs[0] + (cs[-1] - cs[0]) * (0 - dr[0]) / (dr[-1] - dr[0])
+        assert abs(root - ck) < 3e-6 * ck, (Tp, root, ck)
+
+
 def test_love_layer_over_halfspace(oracle):
     # tan(q h) = mu2 nu2 / (mu1 q): residual of the classical dispersion relation at the oracle roots
     thk = np.array([20., 0.]); vs = np.array([3.0, 4.5]); vp = vs * 1.75; rho = np.array([2.5, 3.2])
