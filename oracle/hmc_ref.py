@@ -19,6 +19,9 @@ import numpy as np
 class ChainResult:
     def __init__(self):
         self.accepts = []
+        # per-trajectory trace (for the fixtures made from the reference's own Python):
+        # L, dt used, alpha (dual averaging), x returned by _leapfrog
+        self.trace_L, self.trace_dt, self.trace_alpha, self.trace_x = [], [], [], []
         self.misfit = None
         self.samples = None
         self.syn = None
@@ -143,6 +146,9 @@ def run_base(f, bounds, dt, Lrange, seed, nsamples, ndraws, max_iters=None):
                     R.syn[i - ndraws] = dn
                 i += 1
         R.accepts.append(1 if acc else 0)
+        R.trace_L.append(L)
+        R.trace_dt.append(dt)
+        R.trace_x.append(np.array(x, dtype=float).copy())
         ncount += 1
     R.n_acc = i
     R.n_iter = ncount
@@ -203,6 +209,10 @@ def run_da(f, bounds, dt_cfg, L0, target, seed, nsamples, ndraws, max_iters=None
         if t is not None:
             xn, Un, dn, Hc, Hn = t
             alpha = min(1., np.exp(-(Hn - Hc)))
+        R.trace_L.append(L)
+        R.trace_dt.append(dt)
+        R.trace_alpha.append(float(alpha))
+        R.trace_x.append(np.array(xn if t is not None else x, dtype=float).copy())
         u = rs.rand()
         acc = False
         if u < alpha:

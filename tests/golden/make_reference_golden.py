@@ -1,0 +1,204 @@
+"""Golden vectors from the REFERENCE'S OWN Python code, run in the build container:
+
+    python tests/golden/make_reference_golden.py        ->  tests/golden/ref_python.npz
+
+What runs unmodified from /root/reference (imported, never copied):
+  * model/model_surf.py, model/model_rf.py, model/model_rf_swd_vs_thk.py  -- Brocher relations,
+    chain rule, residual contraction, joint weighting, failure convention   
+  * pyhmc/hmc.py  (HamitonianMC)  and  pyhmc/hmcda.py  (HMCDualAveraging)  -- initial model,
+    leapfrog, reflections, Metropolis, dual averaging, _find_initial_dt, NumPy's legacy global
+    RNG stream                                                             
+What is stubbed, because it cannot exist here (gfortran / FFTW3 / h5py absent):
+  * `model.lib.libsurf` / `model.lib.librf` (the compiled pybind11 modules) -> thin adapters onto
+    the CPU oracle (oracle/), which therefore stays the unpinned part;
+  * `h5py` -> an in-memory stand-in (the samplers only write results through it).
+The fixtures pin oracle.joint_batch (the restated glue) and oracle/hmc_ref.py (the restated
+samplers) against the reference's real Python on top of the same numerics; tests never need
+/root/reference.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+from oracle.oracle import Oracle  # noqa: E402
+
+O = Oracle()
+
+
+# ---------------------------------------------------------------- stubs
+class _FakeH5File(dict):
+    def __init__(self, *a, **k):
+        super().__init__()
+
+    def create_group(self, name):
+        return None
+
+    def create_dataset(self, name, data=None, dtype=None, shape=None):
+        self[name] = np.array(data, dtype="f8") if data is not None else np.zeros(shape)
+        return self[name]
+
+    def close(self):
+        pass
+
+
+h5 = types.ModuleType("h5py")
+h5.File = _FakeH5File
+sys.modules["h5py"] = h5
+
+libsurf = types.ModuleType("model.lib.libsurf")
+libsurf.forward = lambda thk, vp, vs, rho, period, wavetype, mode=0, sphere=False: \
+    O.surf_forward(thk, vp, vs, rho, period, wavetype, mode, sphere)
+libsurf.adjoint_kernel = lambda thk, vp, vs, rho, period, wavetype, mode=0, sphere=False: \
+    O.surf_adjoint_kernel(thk, vp, vs, rho, period, wavetype, mode, sphere)
+librf = types.ModuleType("model.lib.librf")
+librf.forward = lambda thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method="time", \
+    water=0.001, rf_type="P": O.rf_forward(thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift,
+                                             method, water, rf_type)
+librf.kernel_all = lambda thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method="time", \
+    water=0.001, rf_type="P": O.rf_kernel_all(thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss,
+                                                time_shift, method, water, rf_type)
+librf.kernel = lambda thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method="time", \
+    water=0.001, rf_type="P", par_type="vs": O.rf_kernel(thk, rho, vp, vs, qa, qb, ray_p, nt, dt,
+                                                          gauss, time_shift, method, water, rf_type, par_type)
+lib = types.ModuleType("model.lib")
+lib.__path__ = []
+lib.libsurf, lib.librf = libsurf, librf
+sys.path.insert(0, REF)
+import model  # noqa: E402  (the reference's package)
+sys.modules["model.lib"] = lib
+sys.modules["model.lib.libsurf"] = libsurf
+sys.modules["model.lib.librf"] = librf
+model.lib = lib
+from model.model_rf import ReceiverFunc  # noqa: E402
+from model.model_surf import SurfWD  # noqa: E402
+from model.model_rf_swd_vs_thk import Joint_RF_SWD  # noqa: E402
+from pyhmc.hmc import HamitonianMC  # noqa: E402
+from pyhmc.hmcda import HMCDualAveraging  # noqa: E402
+import yaml  # noqa: E402
+
+
+def build_model(param):
+    """main_base.py:23-58, verbatim in behaviour"""
+    model_swd = SurfWD.init(**param["swd"])
+    model_rf = ReceiverFunc.init(**param["rf"])
+    thk = np.asarray(param["true_model"]["thk"], dtype=float)
+    vs = np.asarray(param["true_model"]["vs"], dtype=float)
+    model_swd.set_thk(thk)
+    model_rf.set_thk(thk)
+    m = Joint_RF_SWD(1.0, 1.0, model_rf, model_swd)
+    x = np.hstack((vs, thk))
+    drsyn, dssyn, _ = m.forward(x)
+    dobs = np.zeros(m.ndata)
+    dobs[:m.rfmodel.nt] = drsyn
+    dobs[m.rfmodel.nt:] = dssyn
+    m.set_obsdata(dobs[:m.rfmodel.nt], dobs[m.rfmodel.nt:])
+    n = len(x)
+    b = np.ones((n, 2))
+    for i in range(len(thk)):   # main_base.py:65-77
+        b[i, 0] = max(vs[i] - vs[i] * 0.8, 1.5)
+        b[i, 1] = min(vs[i] + vs[i] * 0.8, 5.0)
+        b[i + len(thk), 0] = thk[i] - thk[i] * 0.2
+        b[i + len(thk), 1] = thk[i] + thk[i] * 0.2
+    b[-1, :] = 0.0, 2.0
+    return m, x, dobs, b
+
+
+def run_sampler(cls, m, b, rank, hparam, max_traj):
+    """sample() of the reference class with its per-trajectory decisions recorded; the run is cut
+    after max_traj trajectories by raising from the instrumented _leapfrog."""
+    chain = cls.init(m, b, rank, **hparam)
+    rec = {"accepts": [], "L": [], "dt": [], "x_after": []}
+    orig = chain._leapfrog
+
+    class _Stop(Exception):
+        pass
+
+    if cls is HamitonianMC:
+        def wrapped(x, dt, L):
+            if len(rec["accepts"]) >= max_traj:
+                raise _Stop()
+            out = orig(x, dt, L)
+            rec["accepts"].append(1 if out[3] else 0)
+            rec["L"].append(L)
+            rec["dt"].append(dt)
+            rec["x_after"].append(np.array(out[0], dtype=float).copy())
+            return out
+    else:
+        # dual averaging: _leapfrog returns alpha; the accept draw happens in sample()
+        state = {"pending": None}
+        orig_rand = np.random.rand
+
+        def wrapped(x, dt, L):
+            if len(rec["L"]) >= max_traj:
+                raise _Stop()
+            out = orig(x, dt, L)
+            rec["L"].append(L)
+            rec["dt"].append(dt)
+            rec["x_after"].append(np.array(out[0], dtype=float).copy())
+            rec.setdefault("alpha", []).append(float(out[3]))
+            return out
+    chain._leapfrog = wrapped
+    with contextlib.redirect_stdout(io.StringIO()):
+        try:
+            chain.sample()
+        except _Stop:
+            pass
+    init = np.array(chain.fio["initmodel"], dtype=float)
+    return chain, rec, init
+
+
+def main():
+    param = yaml.safe_load(open(os.path.join(REF, "param.yaml")))
+    param["hmc"]["OUTPUT_DIR"] = "/tmp/rfs_ref_golden/"
+    os.makedirs(param["hmc"]["OUTPUT_DIR"], exist_ok=True)
+    m, x0, dobs, b = build_model(param)
+    out = {"x_true": x0, "dobs": dobs, "bounds": b}
+
+    # ---- glue: Joint / RF-only / SWD-only misfit_and_grad at a handful of models
+    rng = np.random.default_rng(20240917)
+    X = np.vstack((x0 * 1.02, x0 * (1 + 0.05 * rng.uniform(-1, 1, (6, x0.size))),
+                   b[:, 0] + (b[:, 1] - b[:, 0]) * np.sort(rng.random((3, x0.size)), axis=1)))
+    X[:, -1] = rng.uniform(0, 2, X.shape[0])
+    U, G, D, F = [], [], [], []
+    Ur, Gr, Us, Gs = [], [], [], []
+    for x in X:
+        u, g, d, f = m.misfit_and_grad(x)
+        U.append(u); G.append(g); D.append(d); F.append(bool(f))
+        ur, gr, _ = m.rfmodel.misfit_and_grad(x)
+        us, gs, _, _ = m.swdmodel.misfit_and_grad(x)
+        Ur.append(ur); Gr.append(gr); Us.append(us); Gs.append(gs)
+    out.update(glue_X=X, glue_U=np.array(U), glue_grad=np.array(G), glue_dsyn=np.array(D),
+               glue_flag=np.array(F), glue_U_rf=np.array(Ur), glue_grad_rf=np.array(Gr),
+               glue_U_swd=np.array(Us), glue_grad_swd=np.array(Gs))
+
+    # ---- samplers on the real joint model (short runs: the point is the decision sequence)
+    hp = dict(param["hmc"], nsamples=40, ndraws=5)
+    for rank in (0, 3):
+        chain, rec, init = run_sampler(HamitonianMC, m, b, rank, hp, max_traj=14)
+        out[f"base{rank}_init"] = init
+        out[f"base{rank}_accepts"] = np.array(rec["accepts"])
+        out[f"base{rank}_L"] = np.array(rec["L"])
+        out[f"base{rank}_x"] = np.array(rec["x_after"])
+    hp = dict(param["hmc"], nsamples=20, ndraws=4, dt=0.02)
+    for rank in (0, 5):
+        chain, rec, init = run_sampler(HMCDualAveraging, m, b, rank, hp, max_traj=8)
+        out[f"da{rank}_init"] = init
+        out[f"da{rank}_L"] = np.array(rec["L"])
+        out[f"da{rank}_dt"] = np.array(rec["dt"])
+        out[f"da{rank}_alpha"] = np.array(rec["alpha"])
+        out[f"da{rank}_x"] = np.array(rec["x_after"])
+    out["base_hparam"] = np.array([0.1, 5, 20, 991206, 40, 5], dtype=float)
+    out["da_hparam"] = np.array([0.02, 10, 0.65, 991206, 20, 4], dtype=float)
+    np.savez_compressed(os.path.join(HERE, "ref_python.npz"), **out)
+    print("wrote ref_python.npz:", {k: np.shape(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

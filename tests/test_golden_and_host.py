@@ -178,3 +178,57 @@ def test_chain_result_file_and_best_mean_model(tmp_path):
     assert np.array_equal(z["models"], samples) and np.array_equal(z["mean/model"], xm)
     with pytest.raises(TypeError):
         require_device_model(object())
+
+
+def _ref_python_golden():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python.npz"))
+
+
+def test_restated_glue_matches_the_references_own_python(oracle):
+    """tests/golden/ref_python.npz was produced by the reference's UNMODIFIED model/*.py classes
+    (imported from /root/reference by tests/golden/make_reference_golden.py) on top of oracle-backed
+    libsurf/librf stubs.  The restated glue of the oracle (Brocher relations, chain rule, residual
+    contraction, 125/72 joint weighting, failure convention) must give the same numbers."""
+    z = _ref_python_golden()
+    cfg = f1_config()
+    X, dobs = z["glue_X"], z["dobs"]
+    U, g, d, f = oracle.joint_batch(X, dobs, cfg, which=0)
+    assert np.array_equal(f, z["glue_flag"])
+    assert np.allclose(U, z["glue_U"], rtol=1e-12, atol=0)
+    assert np.allclose(g, z["glue_grad"], rtol=1e-10, atol=1e-12 * np.abs(z["glue_grad"]).max())
+    assert np.allclose(d, z["glue_dsyn"], rtol=1e-13, atol=1e-15)
+    Ur, gr, _, _ = oracle.joint_batch(X, dobs[:125], cfg, which=1)
+    Us, gs, _, _ = oracle.joint_batch(X, dobs[125:], cfg, which=2)
+    assert np.allclose(Ur, z["glue_U_rf"], rtol=1e-12) and np.allclose(Us, z["glue_U_swd"], rtol=1e-12)
+    assert np.allclose(gr, z["glue_grad_rf"], rtol=1e-10, atol=1e-12 * np.abs(z["glue_grad_rf"]).max())
+    assert np.allclose(gs, z["glue_grad_swd"], rtol=1e-10, atol=1e-12 * np.abs(z["glue_grad_swd"]).max())
+
+
+def test_restated_samplers_match_the_references_own_python(oracle):
+    """Same fixture: HamitonianMC.sample / HMCDualAveraging.sample of the reference ran on the joint
+    model; oracle/hmc_ref.py (the checker of the device sampler) must reproduce the initial model,
+    every L, every step size, every acceptance probability / decision and every returned state."""
+    from oracle import hmc_ref
+    z = _ref_python_golden()
+    cfg = f1_config()
+    f = hmc_ref.oracle_joint_f(oracle, z["dobs"], cfg)
+    b = z["bounds"]
+    assert np.array_equal(b, driver_bounds(z["x_true"]))
+    dt, l0, l1, seed, ns, ndr = z["base_hparam"]
+    for rank in (0, 3):
+        acc = z[f"base{rank}_accepts"]
+        R = hmc_ref.run_base(f, b, float(dt), (int(l0), int(l1)), int(seed) + rank, nsamples=int(ns),
+                             ndraws=int(ndr), max_iters=len(acc))
+        assert np.array_equal(R.initmodel, z[f"base{rank}_init"])
+        assert R.accepts == acc.tolist() and R.trace_L == z[f"base{rank}_L"].tolist()
+        assert np.allclose(np.array(R.trace_x), z[f"base{rank}_x"], rtol=1e-12, atol=1e-13)
+    dt, L0, target, seed, ns, ndr = z["da_hparam"]
+    for rank in (0, 5):
+        Ls = z[f"da{rank}_L"]
+        R = hmc_ref.run_da(f, b, float(dt), int(L0), float(target), int(seed) + rank, nsamples=int(ns),
+                           ndraws=int(ndr), max_iters=len(Ls))
+        assert np.array_equal(R.initmodel, z[f"da{rank}_init"])
+        assert R.trace_L == Ls.tolist()
+        assert np.allclose(R.trace_dt, z[f"da{rank}_dt"], rtol=1e-12)
+        assert np.allclose(R.trace_alpha, z[f"da{rank}_alpha"], rtol=1e-9, atol=1e-300)
+        assert np.allclose(np.array(R.trace_x), z[f"da{rank}_x"], rtol=1e-12, atol=1e-13)
