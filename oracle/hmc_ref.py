@@ -1,4 +1,7 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY (PARITY UNPINNED, see oracle/README.md).
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  This file IS pinned against the reference: the reference's own
+samplers, imported unmodified, reproduce its decisions and states (tests/golden/ref_python.npz,
+tests/golden/make_reference_golden.py); the forward model underneath stays PARITY UNPINNED
+(oracle/README.md).
 
 NumPy restatement of the reference samplers, one chain at a time, driven by any
 `misfit_and_grad(x) -> (U, grad, dsyn, flag)` callable (in the tests: the C++ oracle):
