@@ -1,5 +1,5 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  This file IS pinned against the reference: the reference's own
-samplers, imported unmodified, reproduce its decisions and states (tests/golden/ref_python.npz,
+samplers, imported unmodified, reproduce its decisions and states (tests/golden/reference_code.npz,
 tests/golden/make_reference_golden.py); the forward model underneath stays PARITY UNPINNED
 (oracle/README.md).
 

@@ -1,6 +1,6 @@
 """Golden vectors from the REFERENCE'S OWN Python code, run in the build container:
 
-    python tests/golden/make_reference_golden.py        ->  tests/golden/ref_python.npz
+    python tests/golden/make_reference_golden.py        ->  tests/golden/reference_code.npz
 
 What runs unmodified from /root/reference (imported, never copied):
   * model/model_surf.py, model/model_rf.py, model/model_rf_swd_vs_thk.py  -- Brocher relations,
@@ -8,13 +8,17 @@ What runs unmodified from /root/reference (imported, never copied):
   * pyhmc/hmc.py  (HamitonianMC)  and  pyhmc/hmcda.py  (HMCDualAveraging)  -- initial model,
     leapfrog, reflections, Metropolis, dual averaging, _find_initial_dt, NumPy's legacy global
     RNG stream                                                             
+  * src/SWD/main.cpp, src/SWD/surfdisp.cpp, src/RF/main.cpp -- the pybind11 modules `libsurf` and
+    `librf` themselves (float32 casts, retry loop, _RayleighGroup/_LoveGroup, _SurfKernel,
+    _flat2sphere), compiled in place by `make -C oracle ref` into oracle/_ref/    (rows a5, a10, b)
 What is stubbed, because it cannot exist here (gfortran / FFTW3 / h5py absent):
-  * `model.lib.libsurf` / `model.lib.librf` (the compiled pybind11 modules) -> thin adapters onto
-    the CPU oracle (oracle/), which therefore stays the unpinned part;
+  * the Fortran entry points those modules call (surfdisp96_, sregn96_, slegn96_, sregnpu_,
+    slegnpu_, cal_rf_*_) -> oracle/ref_fortran_shims.cpp forwards them to the C++ restatements of
+    oracle/, which therefore stay the unpinned part;
   * `h5py` -> an in-memory stand-in (the samplers only write results through it).
-The fixtures pin oracle.joint_batch (the restated glue) and oracle/hmc_ref.py (the restated
-samplers) against the reference's real Python on top of the same numerics; tests never need
-/root/reference.
+The fixture pins oracle.surf_* / rf_* (the restated C++ layers), oracle.joint_batch (the restated
+glue) and oracle/hmc_ref.py (the restated samplers) against the reference's real code on top of
+the same numerics; tests never need /root/reference.
 """
 import contextlib
 import io
@@ -52,21 +56,11 @@ h5 = types.ModuleType("h5py")
 h5.File = _FakeH5File
 sys.modules["h5py"] = h5
 
-libsurf = types.ModuleType("model.lib.libsurf")
-libsurf.forward = lambda thk, vp, vs, rho, period, wavetype, mode=0, sphere=False: \
-    O.surf_forward(thk, vp, vs, rho, period, wavetype, mode, sphere)
-libsurf.adjoint_kernel = lambda thk, vp, vs, rho, period, wavetype, mode=0, sphere=False: \
-    O.surf_adjoint_kernel(thk, vp, vs, rho, period, wavetype, mode, sphere)
-librf = types.ModuleType("model.lib.librf")
-librf.forward = lambda thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method="time", \
-    water=0.001, rf_type="P": O.rf_forward(thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift,
-                                             method, water, rf_type)
-librf.kernel_all = lambda thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method="time", \
-    water=0.001, rf_type="P": O.rf_kernel_all(thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss,
-                                                time_shift, method, water, rf_type)
-librf.kernel = lambda thk, rho, vp, vs, qa, qb, ray_p, nt, dt, gauss, time_shift, method="time", \
-    water=0.001, rf_type="P", par_type="vs": O.rf_kernel(thk, rho, vp, vs, qa, qb, ray_p, nt, dt,
-                                                          gauss, time_shift, method, water, rf_type, par_type)
+import subprocess  # noqa: E402
+subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+import libsurf  # noqa: E402  (the reference's own pybind11 module, built from /root/reference)
+import librf  # noqa: E402
 lib = types.ModuleType("model.lib")
 lib.__path__ = []
 lib.libsurf, lib.librf = libsurf, librf
@@ -161,6 +155,45 @@ def main():
     m, x0, dobs, b = build_model(param)
     out = {"x_true": x0, "dobs": dobs, "bounds": b}
 
+    # ---- the compiled modules themselves: every wave type, mode, flat / spherical earth; RF both
+    # methods, both types, all parameter kernels
+    thk, vs = x0[7:], x0[:7]
+    vp, rho = m.swdmodel.empirical_relation(vs)
+    T = np.asarray(param["swd"]["tRc"], dtype=float)
+    models = [(thk, vp, vs, rho)]
+    rr = np.random.default_rng(7)
+    for _ in range(3):
+        v = vs * (1 + 0.08 * rr.uniform(-1, 1, 7))
+        a, r = m.swdmodel.empirical_relation(v)
+        models.append((thk * (1 + 0.15 * rr.uniform(-1, 1, 7)) * (thk > 0), a, v, r))
+    out["cpp_models"] = np.array([np.vstack(mm) for mm in models])
+    out["cpp_T"] = T
+    for im, (h, a, v, r) in enumerate(models):
+        for wt in ("Rc", "Rg", "Lc", "Lg"):
+            for mode in (0, 1, 2):
+                for sph in (False, True):
+                    if im > 0 and (mode == 2 or sph):
+                        continue
+                    c, ok = libsurf.forward(h, a, v, r, T, wt, mode, sph)
+                    k = libsurf.adjoint_kernel(h, a, v, r, T, wt, mode, sph)
+                    key = f"cpp{im}_{wt}_{mode}_{int(sph)}"
+                    out[key + "_fwd"] = np.asarray(c)
+                    out[key + "_ok"] = np.array([bool(ok), bool(k[5])])
+                    for nm, arr in zip(("c", "da", "db", "dr", "dh"), k[:5]):
+                        if wt[0] == "L" and nm == "da":
+                            continue  # uninitialised memory in the reference (src/SWD/main.cpp:68)
+                        out[key + "_k" + nm] = np.asarray(arr)
+    q = thk * 0 + 9999.0
+    rfa = (0.045, 125, 0.4, 1.5, 5.0)
+    for method in ("freq", "time"):
+        for rft in ("P", "S"):
+            key = f"cpprf_{method}_{rft}"
+            out[key + "_fwd"] = np.asarray(librf.forward(thk, rho, vp, vs, q, q, *rfa, method, 0.001, rft))
+            d, kl = librf.kernel_all(thk, rho, vp, vs, q, q, *rfa, method, 0.001, rft)
+            out[key + "_all"] = np.asarray(kl)
+            for par in ("vs", "vp", "rho", "thick"):
+                out[key + "_k" + par] = np.asarray(librf.kernel(thk, rho, vp, vs, q, q, *rfa, method, 0.001, rft, par)[1])
+
     # ---- glue: Joint / RF-only / SWD-only misfit_and_grad at a handful of models
     rng = np.random.default_rng(20240917)
     X = np.vstack((x0 * 1.02, x0 * (1 + 0.05 * rng.uniform(-1, 1, (6, x0.size))),
@@ -196,8 +229,8 @@ def main():
         out[f"da{rank}_x"] = np.array(rec["x_after"])
     out["base_hparam"] = np.array([0.1, 5, 20, 991206, 40, 5], dtype=float)
     out["da_hparam"] = np.array([0.02, 10, 0.65, 991206, 20, 4], dtype=float)
-    np.savez_compressed(os.path.join(HERE, "ref_python.npz"), **out)
-    print("wrote ref_python.npz:", {k: np.shape(v) for k, v in out.items()})
+    np.savez_compressed(os.path.join(HERE, "reference_code.npz"), **out)
+    print("wrote reference_code.npz:", {k: np.shape(v) for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -181,11 +181,49 @@ def test_chain_result_file_and_best_mean_model(tmp_path):
 
 
 def _ref_python_golden():
-    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python.npz"))
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_code.npz"))
+
+
+def test_restated_cpp_layers_match_the_references_own_compiled_modules(oracle):
+    """The fixture holds the outputs of the reference's OWN pybind11 modules -- src/SWD/main.cpp +
+    surfdisp.cpp and src/RF/main.cpp compiled in place (`make -C oracle ref`), their Fortran entry
+    points forwarded to the restated routines.  The oracle's restatement of those C++ layers
+    (swd_driver.cpp, oracle_capi.cpp: float32 casts, retry loop, group-velocity drivers, kernel
+    driver, flat->sphere conversion, argument conventions) must agree bit for bit."""
+    z = _ref_python_golden()
+    T = z["cpp_T"]
+    n = 0
+    for im, (h, a, v, r) in enumerate(z["cpp_models"]):
+        for wt in ("Rc", "Rg", "Lc", "Lg"):
+            for mode in (0, 1, 2):
+                for sph in (False, True):
+                    key = f"cpp{im}_{wt}_{mode}_{int(sph)}"
+                    if key + "_fwd" not in z.files:
+                        continue
+                    c, ok = oracle.surf_forward(h, a, v, r, T, wt, mode, sph)
+                    k = oracle.surf_adjoint_kernel(h, a, v, r, T, wt, mode, sph)
+                    assert [ok, k[5]] == z[key + "_ok"].tolist(), key
+                    assert np.array_equal(c, z[key + "_fwd"], equal_nan=True), key
+                    for nm, arr in zip(("c", "da", "db", "dr", "dh"), k[:5]):
+                        if key + "_k" + nm in z.files:
+                            assert np.array_equal(arr, z[key + "_k" + nm], equal_nan=True), (key, nm)
+                    n += 1
+    assert n == 24 + 3 * 8
+    thk, vp, vs, rho = z["cpp_models"][0]
+    q = thk * 0 + 9999.0
+    rfa = (0.045, 125, 0.4, 1.5, 5.0)
+    for method in ("freq", "time"):
+        for rft in ("P", "S"):
+            key = f"cpprf_{method}_{rft}"
+            assert np.array_equal(oracle.rf_forward(thk, rho, vp, vs, q, q, *rfa, method, 0.001, rft), z[key + "_fwd"])
+            assert np.array_equal(oracle.rf_kernel_all(thk, rho, vp, vs, q, q, *rfa, method, 0.001, rft)[1], z[key + "_all"])
+            for par in ("vs", "vp", "rho", "thick"):
+                assert np.array_equal(oracle.rf_kernel(thk, rho, vp, vs, q, q, *rfa, method, 0.001, rft, par)[1],
+                                      z[key + "_k" + par])
 
 
 def test_restated_glue_matches_the_references_own_python(oracle):
-    """tests/golden/ref_python.npz was produced by the reference's UNMODIFIED model/*.py classes
+    """tests/golden/reference_code.npz was produced by the reference's UNMODIFIED model/*.py classes
     (imported from /root/reference by tests/golden/make_reference_golden.py) on top of oracle-backed
     libsurf/librf stubs.  The restated glue of the oracle (Brocher relations, chain rule, residual
     contraction, 125/72 joint weighting, failure convention) must give the same numbers."""
