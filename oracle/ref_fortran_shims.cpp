@@ -1,92 +1,68 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
-// Fortran entry points the reference's C++ expects (/root/reference/src/SWD/surfdisp.hpp:17-95,
-// /root/reference/src/RF/rf_cal.hpp:10-52), forwarded to the C++ restatements of those Fortran
-// routines in this directory.  With these shims the reference's OWN C++ -- src/SWD/main.cpp,
-// src/SWD/surfdisp.cpp, src/RF/main.cpp (pybind11 boundary, float32 casts, retry loop,
-// _RayleighGroup/_LoveGroup, _SurfKernel, _flat2sphere) -- compiles and runs here unmodified
-// (`make -C oracle ref` -> oracle/_ref/libsurf.so, librf.so).  gfortran and FFTW3 are absent, so
-// the Fortran underneath remains the restatement: _ref pins the restated C++ layers
-// (swd_driver.cpp, oracle_capi.cpp), not the numerics.
+// The reference's C++ (src/SWD/main.cpp, src/SWD/surfdisp.cpp, src/RF/main.cpp) calls eleven Fortran
+// routines through the C ABI (declared in src/SWD/surfdisp.hpp:17-95 and src/RF/rf_cal.hpp:10-52).
+// gfortran is absent here, so `make -C oracle ref` links that C++ -- compiled unmodified from
+// /root/reference -- against the forwarding functions below, which hand every call to the C++
+// restatement of the corresponding Fortran routine in this directory.  The result
+// (oracle/_ref/libsurf.so, librf.so) runs the reference's real pybind11 boundary, float32 casts,
+// retry loop, group-velocity / kernel drivers and flat->sphere conversion; it pins the restated C++
+// layers (swd_driver.cpp, oracle_capi.cpp), not the numerics underneath.
 #include "oracle.hpp"
+
+namespace orc = oracle;
+using F = float *;
+using D = double *;
+using CD = const double *;
 
 extern "C" {
 
-void surfdisp96_(float *thkm, float *vpm, float *vsm, float *rhom, int nlayer, int iflsph, int iwave,
-                 int mode, int igr, int kmax, double *t, double *cg, int *ierr) {
-  oracle::surfdisp96(thkm, vpm, vsm, rhom, nlayer, iflsph, iwave, mode, igr, kmax, t, cg, ierr);
+// ---- src/SWD/surfdisp96.f, sregn96.f90, slegn96.f90
+void surfdisp96_(F h, F a, F b, F r, int n, int sph, int wave, int mode, int igr, int nper, D per,
+                 D vel, int *err) {
+  orc::surfdisp96(h, a, b, r, n, sph, wave, mode, igr, nper, per, vel, err);
+}
+void sregn96_(F h, F a, F b, F r, int n, D per, D c, D u, D ur, D uz, D tr, D tz, D ka, D kb, D kh,
+              D kr, int sph) {
+  orc::sregn96(h, a, b, r, n, per, c, u, ur, uz, tr, tz, ka, kb, kh, kr, sph);
+}
+void slegn96_(F h, F b, F r, int n, D per, D c, D u, D ut, D tt, D kb, D kh, D kr, int sph) {
+  orc::slegn96(h, b, r, n, per, c, u, ut, tt, kb, kh, kr, sph);
+}
+void sregnpu_(F h, F a, F b, F r, int n, D per, D c, D u, D ur, D uz, D tr, D tz, D p1, D c1, D p2,
+              D c2, D ka, D kb, D kh, D kr, D ga, D gb, D gh, D gr, int sph) {
+  orc::sregnpu(h, a, b, r, n, per, c, u, ur, uz, tr, tz, p1, c1, p2, c2, ka, kb, kh, kr, ga, gb, gh, gr,
+               sph, /*stale_first_term=*/true);
+}
+void slegnpu_(F h, F b, F r, int n, D per, D c, D u, D ut, D tt, D p1, D c1, D p2, D c2, D kb, D kh,
+              D kr, D gb, D gh, D gr, int sph) {
+  orc::slegnpu(h, b, r, n, per, c, u, ut, tt, p1, c1, p2, c2, kb, kh, kr, gb, gh, gr, sph,
+               /*stale_first_term=*/true);
 }
 
-void sregn96_(float *thk, float *vp, float *vs, float *rhom, int nlayer, double *t, double *cp,
-              double *cg, double *dispu, double *dispw, double *stressu, double *stressw,
-              double *dc2da, double *dc2db, double *dc2dh, double *dc2dr, int iflsph) {
-  oracle::sregn96(thk, vp, vs, rhom, nlayer, t, cp, cg, dispu, dispw, stressu, stressw, dc2da, dc2db,
-                  dc2dh, dc2dr, iflsph);
+// ---- src/RF/RFModule.f90 (argument order of the Fortran bind(C) interfaces: thk, vp, vs, rho)
+void cal_rf_time_(CD h, CD a, CD b, CD r, CD qa, CD qb, int n, int nt, double dt, double p, double g,
+                  double t0, int type, D rf) {
+  orc::cal_rf_time(h, a, b, r, qa, qb, n, nt, dt, p, g, t0, type, rf);
 }
-
-void slegn96_(float *thk, float *vs, float *rhom, int nlayer, double *t, double *cp, double *cg,
-              double *disp, double *stress, double *dc2db, double *dc2dh, double *dc2dr, int iflsph) {
-  oracle::slegn96(thk, vs, rhom, nlayer, t, cp, cg, disp, stress, dc2db, dc2dh, dc2dr, iflsph);
+void cal_rf_freq_(CD h, CD a, CD b, CD r, CD qa, CD qb, int n, int nt, double dt, double p, double g,
+                  double t0, double wl, int type, D rf) {
+  orc::cal_rf_freq(h, a, b, r, qa, qb, n, nt, dt, p, g, t0, wl, type, rf);
 }
-
-void slegnpu_(float *thk, float *vs, float *rhom, int nlayer, double *t, double *cp, double *cg,
-              double *disp, double *stress, double *t1, double *cp1, double *t2, double *cp2,
-              double *dc2db, double *dc2dh, double *dc2dr, double *du2db, double *du2dh,
-              double *du2dr, int iflsph) {
-  oracle::slegnpu(thk, vs, rhom, nlayer, t, cp, cg, disp, stress, t1, cp1, t2, cp2, dc2db, dc2dh, dc2dr,
-                  du2db, du2dh, du2dr, iflsph, true);
+void cal_rf_par_freq_(CD h, CD a, CD b, CD r, CD qa, CD qb, int n, int nt, double dt, double p,
+                      double g, double t0, double wl, int type, int par, D rf, D drf) {
+  orc::cal_rf_par_freq(h, a, b, r, qa, qb, n, nt, dt, p, g, t0, wl, type, par, rf, drf);
 }
-
-void sregnpu_(float *thk, float *vp, float *vs, float *rhom, int nlayer, double *t, double *cp,
-              double *cg, double *dispu, double *dispw, double *stressu, double *stressw, double *t1,
-              double *cp1, double *t2, double *cp2, double *dc2da, double *dc2db, double *dc2dh,
-              double *dc2dr, double *du2da, double *du2db, double *du2dh, double *du2dr, int iflsph) {
-  oracle::sregnpu(thk, vp, vs, rhom, nlayer, t, cp, cg, dispu, dispw, stressu, stressw, t1, cp1, t2, cp2,
-                  dc2da, dc2db, dc2dh, dc2dr, du2da, du2db, du2dh, du2dr, iflsph, true);
+void cal_rf_par_freq_all_(CD h, CD a, CD b, CD r, CD qa, CD qb, int n, int nt, double dt, double p,
+                          double g, double t0, double wl, int type, D rf, D drf) {
+  orc::cal_rf_par_freq_all(h, a, b, r, qa, qb, n, nt, dt, p, g, t0, wl, type, rf, drf);
 }
-
-void cal_rf_time_(const double *thk, const double *vp, const double *vs, const double *rho,
-                  const double *qa, const double *qb, int nlayer, int nt, double dt, double ray_p,
-                  double gauss, double time_shift, int rf_type, double *rcv_fun) {
-  oracle::cal_rf_time(thk, vp, vs, rho, qa, qb, nlayer, nt, dt, ray_p, gauss, time_shift, rf_type, rcv_fun);
+void cal_rf_par_time_(CD h, CD a, CD b, CD r, CD qa, CD qb, int n, int nt, double dt, double p,
+                      double g, double t0, int type, int par, D rf, D drf) {
+  orc::cal_rf_par_time(h, a, b, r, qa, qb, n, nt, dt, p, g, t0, type, par, rf, drf);
 }
-
-void cal_rf_freq_(const double *thk, const double *vp, const double *vs, const double *rho,
-                  const double *qa, const double *qb, int nlayer, int nt, double dt, double ray_p,
-                  double gauss, double time_shift, double water, int rf_type, double *rcv_fun) {
-  oracle::cal_rf_freq(thk, vp, vs, rho, qa, qb, nlayer, nt, dt, ray_p, gauss, time_shift, water, rf_type,
-                      rcv_fun);
-}
-
-void cal_rf_par_freq_(const double *thk, const double *vp, const double *vs, const double *rho,
-                      const double *qa, const double *qb, int nlayer, int nt, double dt, double ray_p,
-                      double gauss, double time_shift, double water, int rf_type, int par_type,
-                      double *rcv_fun, double *rcv_fun_p) {
-  oracle::cal_rf_par_freq(thk, vp, vs, rho, qa, qb, nlayer, nt, dt, ray_p, gauss, time_shift, water,
-                          rf_type, par_type, rcv_fun, rcv_fun_p);
-}
-
-void cal_rf_par_freq_all_(const double *thk, const double *vp, const double *vs, const double *rho,
-                          const double *qa, const double *qb, int nlayer, int nt, double dt,
-                          double ray_p, double gauss, double time_shift, double water, int rf_type,
-                          double *rcv_fun, double *rcv_fun_p) {
-  oracle::cal_rf_par_freq_all(thk, vp, vs, rho, qa, qb, nlayer, nt, dt, ray_p, gauss, time_shift, water,
-                              rf_type, rcv_fun, rcv_fun_p);
-}
-
-void cal_rf_par_time_(const double *thk, const double *vp, const double *vs, const double *rho,
-                      const double *qa, const double *qb, int nlayer, int nt, double dt, double ray_p,
-                      double gauss, double time_shift, int rf_type, int par_type, double *rcv_fun,
-                      double *rcv_fun_p) {
-  oracle::cal_rf_par_time(thk, vp, vs, rho, qa, qb, nlayer, nt, dt, ray_p, gauss, time_shift, rf_type,
-                          par_type, rcv_fun, rcv_fun_p);
-}
-
-void cal_rf_par_time_all_(const double *thk, const double *vp, const double *vs, const double *rho,
-                          const double *qa, const double *qb, int nlayer, int nt, double dt,
-                          double ray_p, double gauss, double time_shift, int rf_type, double *rcv_fun,
-                          double *rcv_fun_p) {
-  oracle::cal_rf_par_time_all(thk, vp, vs, rho, qa, qb, nlayer, nt, dt, ray_p, gauss, time_shift, rf_type,
-                              rcv_fun, rcv_fun_p);
+void cal_rf_par_time_all_(CD h, CD a, CD b, CD r, CD qa, CD qb, int n, int nt, double dt, double p,
+                          double g, double t0, int type, D rf, D drf) {
+  orc::cal_rf_par_time_all(h, a, b, r, qa, qb, n, nt, dt, p, g, t0, type, rf, drf);
 }
 
 }  // extern "C"
