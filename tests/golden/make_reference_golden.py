@@ -148,6 +148,50 @@ def run_sampler(cls, m, b, rank, hparam, max_traj):
     return chain, rec, init
 
 
+def run_driver(script, sampler_cls, nsamples, ndraws, workdir):
+    """Run the reference's main_base.py / main_DA.py UNMODIFIED as __main__ (single MPI rank) on a
+    copy of its param.yaml with a short chain; returns what it wrote plus the bounds it built."""
+    import runpy
+
+    class _Comm:
+        def Get_rank(self): return 0
+        def Get_size(self): return 1
+        def bcast(self, x, root=0): return x
+        def Gather(self, src, dst, root=0): dst[0, :] = src
+
+    mpi = types.ModuleType("mpi4py")
+    mpi.MPI = types.SimpleNamespace(COMM_WORLD=_Comm())
+    sys.modules["mpi4py"] = mpi
+    for name in ("matplotlib", "matplotlib.colors", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib.colors"].BoundaryNorm = object
+    param = yaml.safe_load(open(os.path.join(REF, "param.yaml")))
+    param["hmc"].update(nsamples=nsamples, ndraws=ndraws, OUTPUT_DIR=os.path.join(workdir, "results") + "/")
+    if sampler_cls is HMCDualAveraging:
+        param["hmc"]["dt"] = 0.02
+    os.makedirs(workdir, exist_ok=True)
+    yaml.safe_dump(param, open(os.path.join(workdir, "param.yaml"), "w"))
+    seen = {}
+    orig_init = sampler_cls.__dict__["init"].__func__
+
+    def spy(cls, model_, boundaries, rank, **kw):
+        seen["bounds"] = np.array(boundaries, dtype=float).copy()
+        return orig_init(cls, model_, boundaries, rank, **kw)
+    sampler_cls.init = classmethod(spy)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            runpy.run_path(os.path.join(REF, script), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+        sampler_cls.init = classmethod(orig_init)
+    res = os.path.join(workdir, "results")
+    return dict(bounds=seen["bounds"], real_syn=np.load(os.path.join(res, "real_syn.npy")),
+                misfit=np.load(os.path.join(res, "misfit.npy")), dt=float(param["hmc"]["dt"]))
+
+
 def main():
     param = yaml.safe_load(open(os.path.join(REF, "param.yaml")))
     param["hmc"]["OUTPUT_DIR"] = "/tmp/rfs_ref_golden/"
@@ -227,6 +271,12 @@ def main():
         out[f"da{rank}_dt"] = np.array(rec["dt"])
         out[f"da{rank}_alpha"] = np.array(rec["alpha"])
         out[f"da{rank}_x"] = np.array(rec["x_after"])
+    # ---- the drivers themselves, end to end (main_base.py / main_DA.py as __main__, one rank)
+    for tag, script, cls, ns, ndr in (("drvbase", "main_base.py", HamitonianMC, 10, 3),
+                                      ("drvda", "main_DA.py", HMCDualAveraging, 6, 3)):
+        r = run_driver(script, cls, ns, ndr, f"/tmp/rfs_ref_golden/{tag}")
+        out[tag + "_bounds"], out[tag + "_real_syn"], out[tag + "_misfit"] = r["bounds"], r["real_syn"], r["misfit"]
+        out[tag + "_cfg"] = np.array([ns, ndr, r["dt"]], dtype=float)
     out["base_hparam"] = np.array([0.1, 5, 20, 991206, 40, 5], dtype=float)
     out["da_hparam"] = np.array([0.02, 10, 0.65, 991206, 20, 4], dtype=float)
     np.savez_compressed(os.path.join(HERE, "reference_code.npz"), **out)

@@ -270,3 +270,27 @@ def test_restated_samplers_match_the_references_own_python(oracle):
         assert np.allclose(R.trace_dt, z[f"da{rank}_dt"], rtol=1e-12)
         assert np.allclose(R.trace_alpha, z[f"da{rank}_alpha"], rtol=1e-9, atol=1e-300)
         assert np.allclose(np.array(R.trace_x), z[f"da{rank}_x"], rtol=1e-12, atol=1e-13)
+
+
+def test_reference_drivers_end_to_end_match_the_restatement(oracle):
+    """main_base.py and main_DA.py of the reference ran UNMODIFIED as __main__ (one MPI rank, short
+    chains) for the fixture: the bounds they build, the observations they synthesise (real_syn.npy)
+    and the misfit history they save (misfit.npy) must come out of driver_bounds, the oracle's
+    forward and hmc_ref."""
+    from oracle import hmc_ref
+    z = _ref_python_golden()
+    cfg = f1_config()
+    x0 = f1_true_model()
+    for tag in ("drvbase", "drvda"):
+        assert np.array_equal(z[tag + "_bounds"], driver_bounds(x0))
+        _, _, d0, f0 = oracle.joint_batch(x0[None, :], np.zeros(197), cfg, which=0)
+        assert f0[0] and np.allclose(d0[0], z[tag + "_real_syn"], rtol=1e-13, atol=1e-15)
+    f = hmc_ref.oracle_joint_f(oracle, z["drvbase_real_syn"], cfg)
+    ns, ndr, dt = z["drvbase_cfg"]
+    R = hmc_ref.run_base(f, driver_bounds(x0), float(dt), (5, 20), 991206, nsamples=int(ns), ndraws=int(ndr))
+    assert R.n_acc == int(ns + ndr)
+    assert np.allclose(R.misfit, z["drvbase_misfit"][0], rtol=1e-9)
+    ns, ndr, dt = z["drvda_cfg"]
+    R = hmc_ref.run_da(f, driver_bounds(x0), float(dt), 10, 0.65, 991206, nsamples=int(ns), ndraws=int(ndr))
+    assert R.n_acc == int(ns + ndr)
+    assert np.allclose(R.misfit, z["drvda_misfit"][0], rtol=1e-9)

@@ -82,3 +82,26 @@ def test_sampler_front_ends_and_result_files(ctx, tmp_path):
     z = np.load(tmp_path / "chain_joint.1.npz")
     assert z["models"].shape == (6, 14) and z["syn"].shape == (6, 197) and z["mean/model"].shape == (14,)
     assert np.allclose(z["obs"], np.load(tmp_path / "real_syn.npy"))
+
+
+def test_device_samplers_reproduce_the_reference_drivers_own_output(ctx):
+    """tests/golden/reference_code.npz holds real_syn.npy and misfit.npy written by the reference's
+    main_base.py and main_DA.py, run unmodified (tests/golden/make_reference_golden.py).  The device
+    samplers, given the same observations, bounds, seed and settings, must reproduce those misfit
+    histories -- no restatement in between."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_code.npz"))
+    cfg = f1_config()
+    ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"])
+    ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"],
+                  cfg["rf_type"], cfg["method"])
+    ctx.config_obs(z["drvbase_real_syn"])
+    b = z["drvbase_bounds"]
+    ns, ndr, dt = z["drvbase_cfg"]
+    out = ctx.hmc_run(0, [0], b, float(dt), Lrange=(5, 20), seed=991206, nsamples=int(ns), ndraws=int(ndr))
+    assert out["n_acc"][0] == int(ns + ndr)
+    assert np.allclose(out["misfit"][0], z["drvbase_misfit"][0], rtol=1e-4)
+    ns, ndr, dt = z["drvda_cfg"]
+    out = ctx.hmc_run(1, [0], b, float(dt), L0=10, target_ratio=0.65, seed=991206, nsamples=int(ns),
+                      ndraws=int(ndr))
+    assert out["n_acc"][0] == int(ns + ndr)
+    assert np.allclose(out["misfit"][0], z["drvda_misfit"][0], rtol=1e-4)
