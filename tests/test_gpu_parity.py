@@ -86,6 +86,57 @@ def test_librf_dropin_vs_golden(ctx):
     assert np.max(np.abs(rf - g["f2_rf_freq"])) <= TOL_RF * np.max(np.abs(g["f2_rf_freq"]))
 
 
+def test_dropins_vs_the_references_own_compiled_modules(ctx):
+    """Same calls as the reference's pybind11 modules answered in tests/golden/reference_code.npz
+    (src/SWD/main.cpp + surfdisp.cpp and src/RF/main.cpp compiled in place, Fortran entry points
+    forwarded to the restated routines): every wave type x modes 0-2 x flat / spherical earth for
+    four models, RF forward / kernel / kernel_all for both methods and both types."""
+    z = np.load(os.path.join(G, "reference_code.npz"))
+    from rfsurfhmc_b200.model.lib import libsurf, librf
+    T = z["cpp_T"]
+    n = 0
+    for im, (h, a, v, r) in enumerate(z["cpp_models"]):
+        for wt in ("Rc", "Rg", "Lc", "Lg"):
+            for mode in (0, 1, 2):
+                for sph in (False, True):
+                    key = f"cpp{im}_{wt}_{mode}_{int(sph)}"
+                    if key + "_fwd" not in z.files:
+                        continue
+                    ref = z[key + "_fwd"]
+                    c, ok = libsurf.forward(h, a, v, r, T, wt, mode, sph)
+                    assert ok == bool(z[key + "_ok"][0]), key
+                    assert np.array_equal(ref == 0, c == 0) and np.array_equal(np.isnan(ref), np.isnan(c)), key
+                    m = np.isfinite(ref) & (ref != 0)
+                    assert rel(c[m], ref[m]) <= TOL_C, key
+                    k = libsurf.adjoint_kernel(h, a, v, r, T, wt, mode, sph)
+                    assert k[5] == bool(z[key + "_ok"][1]), key
+                    kc = z[key + "_kc"]
+                    m = np.isfinite(kc) & (kc != 0)
+                    assert rel(k[0][m], kc[m]) <= TOL_C, key
+                    for got, nm in zip(k[1:5], ("da", "db", "dr", "dh")):
+                        if key + "_k" + nm not in z.files:
+                            continue
+                        rk = z[key + "_k" + nm][m]
+                        sc = np.max(np.abs(rk)) if rk.size else 0.0
+                        if sc > 0 and np.isfinite(sc):
+                            assert np.nanmax(np.abs(got[m] - rk)) / sc <= TOL_G, (key, nm)
+                    n += 1
+    assert n == 48
+    thk, vp, vs, rho = z["cpp_models"][0]
+    q = thk * 0 + 9999.
+    for method in ("freq", "time"):
+        for rft in ("P", "S"):
+            key = f"cpprf_{method}_{rft}"
+            a = (thk, rho, vp, vs, q, q, 0.045, 125, 0.4, 1.5, 5.0, method, 0.001, rft)
+            ref = z[key + "_fwd"]
+            peak = np.max(np.abs(ref))
+            assert np.max(np.abs(librf.forward(*a) - ref)) <= TOL_RF * peak, key
+            _, kl = librf.kernel_all(*a)
+            tol = TOL_G if method == "freq" else 1e-3   # deconit picks spikes: nonlinear in rounding
+            for ip in range(4):
+                assert np.max(np.abs(kl[ip] - z[key + "_all"][ip])) <= tol * np.max(np.abs(z[key + "_all"][ip])), (key, ip)
+
+
 def test_error_conventions(ctx):
     from rfsurfhmc_b200._lib import RfsError
     from rfsurfhmc_b200.model.lib import libsurf, librf
