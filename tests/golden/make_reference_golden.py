@@ -192,6 +192,36 @@ def run_driver(script, sampler_cls, nsamples, ndraws, workdir):
                 misfit=np.load(os.path.join(res, "misfit.npy")), dt=float(param["hmc"]["dt"]))
 
 
+def run_test_forward(workdir):
+    """The reference's only test script, test_forward.py (time-domain RF, nt=500, and Rc/Rg of a
+    second model), run UNMODIFIED; the three curves it plots are captured from a stand-in pyplot."""
+    import runpy
+    calls = []
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.plot = lambda x, y, *a, **k: calls.append((np.array(x, dtype=float), np.array(y, dtype=float)))
+    for name in ("figure", "subplot", "title", "savefig", "show", "legend", "xlabel", "ylabel"):
+        setattr(plt, name, lambda *a, **k: None)
+    mpl = types.ModuleType("matplotlib")
+    colors = types.ModuleType("matplotlib.colors")
+    colors.BoundaryNorm = object
+    saved = {k: sys.modules.get(k) for k in ("matplotlib", "matplotlib.colors", "matplotlib.pyplot")}
+    sys.modules.update({"matplotlib": mpl, "matplotlib.colors": colors, "matplotlib.pyplot": plt})
+    mpl.pyplot, mpl.colors = plt, colors
+    os.makedirs(workdir, exist_ok=True)
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            runpy.run_path(os.path.join(REF, "test_forward.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+    assert len(calls) == 3
+    return calls
+
+
 def main():
     param = yaml.safe_load(open(os.path.join(REF, "param.yaml")))
     param["hmc"]["OUTPUT_DIR"] = "/tmp/rfs_ref_golden/"
@@ -271,6 +301,10 @@ def main():
         out[f"da{rank}_dt"] = np.array(rec["dt"])
         out[f"da{rank}_alpha"] = np.array(rec["alpha"])
         out[f"da{rank}_x"] = np.array(rec["x_after"])
+    # ---- test_forward.py, the reference's own (and only) test script
+    (t_rf, rf), (tRc, rc), (tRg, rg) = run_test_forward("/tmp/rfs_ref_golden/test_forward")
+    out.update(tf_t=t_rf, tf_rf=rf, tf_tRc=tRc, tf_Rc=rc, tf_tRg=tRg, tf_Rg=rg)
+
     # ---- the drivers themselves, end to end (main_base.py / main_DA.py as __main__, one rank)
     for tag, script, cls, ns, ndr in (("drvbase", "main_base.py", HamitonianMC, 10, 3),
                                       ("drvda", "main_DA.py", HMCDualAveraging, 6, 3)):

@@ -294,3 +294,18 @@ def test_reference_drivers_end_to_end_match_the_restatement(oracle):
     R = hmc_ref.run_da(f, driver_bounds(x0), float(dt), 10, 0.65, 991206, nsamples=int(ns), ndraws=int(ndr))
     assert R.n_acc == int(ns + ndr)
     assert np.allclose(R.misfit, z["drvda_misfit"][0], rtol=1e-9)
+
+
+def test_references_own_test_script_curves(oracle):
+    """test_forward.py -- the only test the reference ships -- ran unmodified for the fixture
+    (time-domain RF with nt=500, dt=0.1, a=1.0; Rc and Rg at 5..40 s for its second model).  The
+    oracle's Python API must give the curves it plots."""
+    z = _ref_python_golden()
+    thk = np.array([6., 6, 13, 5, 10, 30, 0]); vs = np.array([3.2, 3.4, 3.46, 3.7, 3.9, 4.5, 4.7])
+    vp, rho = brocher(vs)
+    q = thk * 0 + 9999.
+    rf = oracle.rf_forward(thk, rho, vp, vs, q, q, 0.045, 500, 0.1, 1.0, 5.0, "time", 0.001, "P")
+    assert np.array_equal(rf, z["tf_rf"]) and np.allclose(z["tf_t"], np.arange(500) * 0.1 - 5.0)
+    T = z["tf_tRc"]
+    assert np.array_equal(oracle.surf_forward(thk, vp, vs, rho, T, "Rc")[0], z["tf_Rc"])
+    assert np.array_equal(oracle.surf_forward(thk, vp, vs, rho, T, "Rg")[0], z["tf_Rg"])

@@ -137,6 +137,27 @@ def test_dropins_vs_the_references_own_compiled_modules(ctx):
                 assert np.max(np.abs(kl[ip] - z[key + "_all"][ip])) <= tol * np.max(np.abs(z[key + "_all"][ip])), (key, ip)
 
 
+def test_references_own_test_script_on_the_gpu(ctx):
+    """The curves of the reference's test_forward.py (run unmodified for
+    tests/golden/reference_code.npz): time-domain receiver function (nt=500, dt=0.1, a=1.0) and the
+    Rayleigh phase / group dispersion of its model, through the reference-shaped Python classes."""
+    from rfsurfhmc_b200.model.model_rf import ReceiverFunc
+    from rfsurfhmc_b200.model.model_surf import SurfWD
+    from rfsurfhmc_b200.model.model_rf_swd_vs_thk import Joint_RF_SWD
+    z = np.load(os.path.join(G, "reference_code.npz"))
+    tRc = np.linspace(5, 40, 36)
+    model_swd = SurfWD(tRc=tRc, tRg=tRc.copy())
+    model_rf = ReceiverFunc(0.045, 500, 0.1, 1.0, 5.0, 0.001, 'P', "time")
+    thk = np.array([6, 6, 13, 5, 10, 30, 0]); vs = np.array([3.2, 3.4, 3.46, 3.7, 3.9, 4.5, 4.7])
+    model_swd.set_thk(thk)
+    model_rf.set_thk(thk)
+    model = Joint_RF_SWD(1.0, 1.0, model_rf, model_swd)
+    drsyn, dssyn, flag = model.forward(np.hstack((vs, thk)))
+    assert flag
+    assert np.max(np.abs(drsyn - z["tf_rf"])) <= TOL_RF * np.max(np.abs(z["tf_rf"]))
+    assert rel(dssyn[:36], z["tf_Rc"]) <= TOL_C and rel(dssyn[36:], z["tf_Rg"]) <= TOL_C
+
+
 def test_error_conventions(ctx):
     from rfsurfhmc_b200._lib import RfsError
     from rfsurfhmc_b200.model.lib import libsurf, librf
