@@ -57,6 +57,12 @@ def run(param, sampler="base", nchains=4, save_chains=True, max_iters=0, max_L=0
     if sampler == "da":
         chain.max_L = int(max_L)      # 0 = the reference's uncapped L = int(lambda/dt)
     ids = D.shard_chains(nchains)
+    if save_chains:
+        # per-chain files need every accepted sample's synthetics on the host: [chains, nsamples, ndata]
+        need = len(ids) * float(param['hmc']['nsamples']) * model.ndata * 8
+        if need > 8e9:
+            raise MemoryError("per-chain result files for %d chains need %.1f GB of synthetics per rank; "
+                              "run with --no-chain-files (misfit.npy is still written)" % (len(ids), need / 1e9))
     out = chain.sample_chains(ids, want_syn=save_chains, save=save_chains)
     misfit = D.gather_chains(out["misfit"], nchains)
     n_iter = D.gather_chains(out["n_iter"], nchains)
