@@ -116,3 +116,21 @@ def test_layer_over_halfspace_conversion_and_multiple_times(oracle):
         assert abs(tm - t_ppps) <= 2 * dt and am > 0.02 * rf[k0], method
         tn, an = extremum(t_ppss, -1)
         assert abs(tn - t_ppss) <= 2 * dt and an < -0.02 * rf[k0], method
+
+
+def test_halfspace_amplitude_is_the_free_surface_response_ratio(oracle):
+    """Independent of any reference code: a P wave with horizontal slowness p hitting the free surface of
+    a half-space gives radial / vertical displacement = 2 p eta_b / (1/b^2 - 2 p^2),
+    eta_b = sqrt(1/b^2 - p^2); the receiver function is that ratio times the Gaussian low-pass
+    exp(-w^2/4a^2), whose time-domain peak is a/sqrt(pi).  Pins the absolute amplitude convention."""
+    for vsv, p, a, tol in ((3.6, 0.06, 2.5, 1e-6), (4.0, 0.07, 3.0, 1e-6), (3.2, 0.045, 1.5, 3e-3)):
+        vs = np.full(3, vsv); thk = np.array([10., 10., 0.])
+        vp, rho = brocher(vs)
+        q = thk * 0 + 9999.
+        for method in ("freq", "time"):
+            rf = oracle.rf_forward(thk, rho, vp, vs, q, q, p, 512, 0.05, a, 5.0, method, 0.001, "P")
+            b = vs[0]
+            ratio = 2 * p * np.sqrt(1 / b**2 - p**2) / (1 / b**2 - 2 * p**2)
+            want = ratio * a / np.sqrt(np.pi)
+            t2 = 5e-3 if method == "time" else tol   # deconit represents the pulse by discrete spikes
+            assert abs(rf.max() - want) <= max(tol, t2) * want, (vsv, p, a, method, rf.max(), want)
