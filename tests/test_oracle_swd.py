@@ -102,6 +102,33 @@ def test_rayleigh_layer_over_halfspace_limits_and_exact_secular_root(oracle):
         root = cs[0] + (cs[-1] - cs[0]) * (0 - dr[0]) / (dr[-1] - dr[0])
         assert abs(root - ck) < 3e-6 * ck, (Tp, root, ck)
 
+    # (iii) higher modes: the first and second higher-mode roots annihilate the same determinant, and
+    # it has NO further sign change between consecutive returned roots (no mode is skipped).  Below
+    # and above the layer's S velocity the determinant is purely real resp. imaginary, so sign
+    # changes are counted per segment.
+    def sign_changes(lo, hi, Tp, step=2e-4):
+        g = np.arange(lo, hi, step)
+        d = np.array([det(x, Tp) for x in g])
+        r = d / (d[0] / abs(d[0]))
+        assert np.max(np.abs(r.imag)) < 1e-9 * np.max(np.abs(d))
+        return int(np.sum(np.diff(np.sign(r.real)) != 0))
+    Tm = np.array([0.8, 1.5, 2.5])
+    cm = [oracle.surf_forward(thk, vp, vs, rho, Tm, "Rc", mode)[0] for mode in (0, 1, 2)]
+    b1 = f32(vs[0])
+    for i, Tp in enumerate(Tm):
+        x0, x1, x2 = cm[0][i], cm[1][i], cm[2][i]
+        assert x0 < b1 < x1 < x2
+        for ck in (x1, x2):
+            cs = ck * (1 + np.array([-2e-4, 2e-4]))
+            d = np.array([det(x, Tp) for x in cs])
+            dr = (d / (d[0] / abs(d[0]))).real
+            assert np.sign(dr[0]) != np.sign(dr[1])
+            root = cs[0] + (cs[1] - cs[0]) * (0 - dr[0]) / (dr[1] - dr[0])
+            assert abs(root - ck) < 3e-6 * ck, (Tp, root, ck)
+        assert sign_changes(x0 + 3e-4, b1 - 3e-4, Tp) == 0
+        assert sign_changes(b1 + 3e-4, x1 - 3e-4, Tp) == 0
+        assert sign_changes(x1 + 3e-4, x2 - 3e-4, Tp) == 0
+
 
 def test_love_layer_over_halfspace(oracle):
     # tan(q h) = mu2 nu2 / (mu1 q): residual of the classical dispersion relation at the oracle roots
