@@ -39,6 +39,92 @@ def test_rayleigh_homogeneous_halfspace(oracle):
     assert ok and np.all(np.abs(u - cr) / cr < 5e-6)  # U == c without dispersion
 
 
+def rayleigh_det_2layer(cc, Tp, a1, b1, r1, H, a2, b2, r2):
+    """Textbook boundary-condition determinant of P-SV motion for ONE layer over a half-space, written
+    from scratch with potentials (independent of the Dunkin/Haskell formulation of the reference):
+    layer phi = A e^{-ra z} + B e^{ra z}, psi = C e^{-rb z} + D e^{rb z}; half-space decaying only.
+    Unknowns (A,B,C,D,E,F); stress-free surface (2 rows) + welded interface (4 rows)."""
+    w = 2 * np.pi / Tp
+    k = w / cc
+    ra1 = np.sqrt(complex(k * k - (w / a1)**2)); rb1 = np.sqrt(complex(k * k - (w / b1)**2))
+    ra2 = np.sqrt(complex(k * k - (w / a2)**2)); rb2 = np.sqrt(complex(k * k - (w / b2)**2))
+    mu1, mu2 = r1 * b1 * b1, r2 * b2 * b2
+
+    def col_p(r, mu, bvel, z, sgn):   # phi = e^{sgn r z}: (ux, uz, tzz, txz), e^{i(kx-wt)} dropped
+        e = np.exp(sgn * r * z)
+        return np.array([1j * k, sgn * r, mu * (2 * k * k - (w / bvel)**2), 2j * mu * k * sgn * r]) * e
+
+    def col_s(r, mu, bvel, z, sgn):   # psi = e^{sgn r z}: ux = -dpsi/dz, uz = dpsi/dx
+        e = np.exp(sgn * r * z)
+        return np.array([-sgn * r, 1j * k, 2j * mu * k * sgn * r, -mu * (2 * k * k - (w / bvel)**2)]) * e
+    M = np.zeros((6, 6), dtype=complex)
+    top = [col_p(ra1, mu1, b1, 0.0, -1), col_p(ra1, mu1, b1, 0.0, +1),
+           col_s(rb1, mu1, b1, 0.0, -1), col_s(rb1, mu1, b1, 0.0, +1)]
+    bot = [col_p(ra1, mu1, b1, H, -1), col_p(ra1, mu1, b1, H, +1),
+           col_s(rb1, mu1, b1, H, -1), col_s(rb1, mu1, b1, H, +1)]
+    half = [col_p(ra2, mu2, b2, 0.0, -1), col_s(rb2, mu2, b2, 0.0, -1)]
+    for j in range(4):
+        M[0, j], M[1, j] = top[j][2], top[j][3]
+        M[2:6, j] = bot[j]
+    for j in range(2):
+        M[2:6, 4 + j] = -half[j]
+    M[:, 1] /= np.exp(ra1.real * H) if ra1.real > 0 else 1.0   # keep the growing columns O(1)
+    M[:, 3] /= np.exp(rb1.real * H) if rb1.real > 0 else 1.0
+    return np.linalg.det(M)
+
+
+def rayleigh_root_2layer(c_guess, Tp, *par, width=3e-4):
+    """Root of the independent determinant next to c_guess, by bisection to machine precision."""
+    lo, hi = c_guess * (1 - width), c_guess * (1 + width)
+    d0 = rayleigh_det_2layer(lo, Tp, *par)
+    ph = d0 / abs(d0)
+    f = lambda x: (rayleigh_det_2layer(x, Tp, *par) / ph).real
+    flo, fhi = f(lo), f(hi)
+    assert np.sign(flo) != np.sign(fhi), (c_guess, Tp, flo, fhi)
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        fm = f(mid)
+        if np.sign(fm) == np.sign(flo):
+            lo, flo = mid, fm
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def test_rayleigh_kernels_and_group_velocity_against_the_independent_determinant(oracle):
+    """sregn96/sregnpu outputs for a layer over a half-space -- analytic group velocity (energy
+    integrals) and the phase-velocity kernels dc/dvp, dc/dvs, dc/drho, dc/dh -- against derivatives
+    of the roots of the from-scratch determinant above, taken in double precision around the
+    float32-rounded model the reference works on."""
+    H = 10.0
+    vs = np.array([3.0, 4.2]); vp = np.array([5.2, 7.4]); rho = np.array([2.5, 3.2]); thk = np.array([H, 0.0])
+    f32 = lambda v: float(np.float32(v))
+    base = [f32(vp[0]), f32(vs[0]), f32(rho[0]), f32(H), f32(vp[1]), f32(vs[1]), f32(rho[1])]
+    T = np.array([3.0, 8.0, 15.0])
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, "Rc")
+    u, ok2 = oracle.surf_forward(thk, vp, vs, rho, T, "Rg")
+    assert ok and ok2
+    # index of each parameter in `base` and the oracle array / layer it belongs to
+    wrt = [(0, da, 0), (1, db, 0), (2, dr, 0), (3, dh, 0), (4, da, 1), (5, db, 1), (6, dr, 1)]
+    for i, Tp in enumerate(T):
+        c0 = rayleigh_root_2layer(c[i], Tp, *base)
+        assert abs(c0 - c[i]) < 2e-6 * c0                      # float32 output + nevill's 1e-6 bracket
+        # group velocity U = c / (1 + (T/c) dc/dT) from the independent roots
+        e = 1e-4 * Tp
+        dcdT = (rayleigh_root_2layer(c0, Tp + e, *base) - rayleigh_root_2layer(c0, Tp - e, *base)) / (2 * e)
+        assert abs(u[i] - c0 / (1 + Tp / c0 * dcdT)) < 2e-5 * u[i], (Tp, u[i])
+        for j, arr, layer in wrt:
+            h = 1e-5 * base[j]
+            pp, pm = list(base), list(base)
+            pp[j] += h
+            pm[j] -= h
+            fd = (rayleigh_root_2layer(c0, Tp, *pp) - rayleigh_root_2layer(c0, Tp, *pm)) / (2 * h)
+            # the reference forms 2*b*b and rho*rho in REAL*4 inside dnka/hska: its eigenfunctions carry
+            # ~1e-7 relative noise, visible in the small (nearly cancelling) density kernels
+            big = max(np.max(np.abs(k_[i])) for k_ in (da, db, dr, dh))
+            assert abs(arr[i, layer] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (Tp, j, arr[i, layer], fd)
+
+
 def test_rayleigh_layer_over_halfspace_limits_and_exact_secular_root(oracle):
     """Layer over a half-space, independent of the reference code:
     (i) short periods see only the layer, long periods only the half-space: c -> the analytic
@@ -55,41 +141,8 @@ def test_rayleigh_layer_over_halfspace_limits_and_exact_secular_root(oracle):
     assert abs(c[0] - rayleigh_halfspace_speed(f32(vp[0]), f32(vs[0]))) < 2e-4 * c[0]
     assert abs(c[-1] - rayleigh_halfspace_speed(f32(vp[1]), f32(vs[1]))) < 5e-3 * c[-1]  # H/lambda = 0.4 %
 
-    def det(cc, Tp):
-        # P-SV potentials: layer phi = A e^{-ra z} + B e^{ra z}, psi = C e^{-rb z} + D e^{rb z};
-        # half-space: decaying only.  Unknowns (A,B,C,D,E,F); 6 conditions: 2 stress-free at z=0,
-        # 4 continuity at z=H.  cc below both half-space speeds; layer terms may be oscillatory.
-        w = 2 * np.pi / Tp
-        k = w / cc
-        a1, b1, a2, b2 = (f32(v) for v in (vp[0], vs[0], vp[1], vs[1]))
-        r1, r2 = f32(rho[0]), f32(rho[1])
-        ra1 = np.sqrt(complex(k * k - (w / a1)**2)); rb1 = np.sqrt(complex(k * k - (w / b1)**2))
-        ra2 = np.sqrt(complex(k * k - (w / a2)**2)); rb2 = np.sqrt(complex(k * k - (w / b2)**2))
-        mu1, mu2 = r1 * b1 * b1, r2 * b2 * b2
-
-        def col_p(r, mu, bvel, z, sgn):   # phi = e^{sgn r z}: (ux, uz, tzz, txz)/e^{..}, e^{i(kx-wt)} dropped
-            e = np.exp(sgn * r * z)
-            lam2mu_term = mu * (2 * k * k - (w / bvel)**2)   # lambda*laplacian + 2 mu d2/dz2 of phi
-            return np.array([1j * k, sgn * r, lam2mu_term, 2j * mu * k * sgn * r]) * e
-
-        def col_s(r, mu, bvel, z, sgn):   # psi = e^{sgn r z}: ux = -dpsi/dz, uz = dpsi/dx
-            e = np.exp(sgn * r * z)
-            return np.array([-sgn * r, 1j * k, 2j * mu * k * sgn * r, -mu * (2 * k * k - (w / bvel)**2)]) * e
-        M = np.zeros((6, 6), dtype=complex)
-        cols0 = [col_p(ra1, mu1, b1, 0.0, -1), col_p(ra1, mu1, b1, 0.0, +1),
-                 col_s(rb1, mu1, b1, 0.0, -1), col_s(rb1, mu1, b1, 0.0, +1)]
-        colsH = [col_p(ra1, mu1, b1, H, -1), col_p(ra1, mu1, b1, H, +1),
-                 col_s(rb1, mu1, b1, H, -1), col_s(rb1, mu1, b1, H, +1)]
-        half = [col_p(ra2, mu2, b2, 0.0, -1), col_s(rb2, mu2, b2, 0.0, -1)]
-        for j in range(4):
-            M[0, j], M[1, j] = cols0[j][2], cols0[j][3]          # tzz = txz = 0 at the surface
-            M[2:6, j] = colsH[j]                                   # continuity of (ux, uz, tzz, txz)
-        for j in range(2):
-            M[2:6, 4 + j] = -half[j]
-        # scale the growing columns so that the determinant stays O(1)
-        M[:, 1] /= np.exp(ra1.real * H) if ra1.real > 0 else 1.0
-        M[:, 3] /= np.exp(rb1.real * H) if rb1.real > 0 else 1.0
-        return np.linalg.det(M)
+    par = [f32(vp[0]), f32(vs[0]), f32(rho[0]), H, f32(vp[1]), f32(vs[1]), f32(rho[1])]
+    det = lambda cc, Tp: rayleigh_det_2layer(cc, Tp, *par)
 
     for Tp, ck in ((3.0, c[2]), (8.0, c[3]), (15.0, c[4])):
         cs = ck * (1 + np.array([-2e-4, -1e-4, 0.0, 1e-4, 2e-4]))
