@@ -206,6 +206,55 @@ def test_love_layer_over_halfspace(oracle):
             assert abs(q * 20.0 - ph) < 2e-4, (mode, t, cc, lhs, rhs)
 
 
+def test_love_kernels_and_group_velocity_against_the_analytic_dispersion_relation(oracle):
+    """slegn96/slegnpu outputs for a layer over a half-space against derivatives of the roots of the
+    closed-form Love dispersion relation mu1 q sin(qH) = mu2 nu2 cos(qH) (q = sqrt(w^2/b1^2 - k^2),
+    nu2 = sqrt(k^2 - w^2/b2^2)), taken in double precision around the float32-rounded model:
+    analytic group velocity, dc/dvs, dc/drho of both media and dc/dh, fundamental and first higher mode."""
+    f32 = lambda v: float(np.float32(v))
+    thk = np.array([20.0, 0.0]); vs = np.array([3.0, 4.5]); vp = np.array([5.2, 7.8]); rho = np.array([2.5, 3.2])
+    base = [f32(vs[0]), f32(rho[0]), f32(thk[0]), f32(vs[1]), f32(rho[1])]
+
+    def G(cc, Tp, b1, r1, H, b2, r2):
+        w = 2 * np.pi / Tp
+        k = w / cc
+        q = np.sqrt((w / b1)**2 - k * k)
+        nu2 = np.sqrt(k * k - (w / b2)**2)
+        return r1 * b1 * b1 * q * np.sin(q * H) - r2 * b2 * b2 * nu2 * np.cos(q * H)
+
+    def root(c_guess, Tp, *par):
+        lo, hi = c_guess * (1 - 3e-4), c_guess * (1 + 3e-4)
+        flo = G(lo, Tp, *par)
+        assert np.sign(flo) != np.sign(G(hi, Tp, *par))
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            fm = G(mid, Tp, *par)
+            if np.sign(fm) == np.sign(flo):
+                lo, flo = mid, fm
+            else:
+                hi = mid
+        return 0.5 * (lo + hi)
+    for mode, T in ((0, np.array([4.0, 10.0, 25.0])), (1, np.array([3.0, 6.0]))):
+        c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, "Lc", mode)
+        u, ok2 = oracle.surf_forward(thk, vp, vs, rho, T, "Lg", mode)
+        assert ok and ok2 and np.all(c > 0)
+        wrt = [(0, db, 0), (1, dr, 0), (2, dh, 0), (3, db, 1), (4, dr, 1)]
+        for i, Tp in enumerate(T):
+            c0 = root(c[i], Tp, *base)
+            assert abs(c0 - c[i]) < 2e-6 * c0
+            e = 1e-4 * Tp
+            dcdT = (root(c0, Tp + e, *base) - root(c0, Tp - e, *base)) / (2 * e)
+            assert abs(u[i] - c0 / (1 + Tp / c0 * dcdT)) < 2e-5 * u[i], (mode, Tp)
+            big = max(np.max(np.abs(k_[i])) for k_ in (db, dr, dh))
+            for j, arr, layer in wrt:
+                h = 1e-5 * base[j]
+                pp, pm = list(base), list(base)
+                pp[j] += h
+                pm[j] -= h
+                fd = (root(c0, Tp, *pp) - root(c0, Tp, *pm)) / (2 * h)
+                assert abs(arr[i, layer] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (mode, Tp, j, arr[i, layer], fd)
+
+
 def test_f1_values_and_modes(oracle):
     T = np.arange(5., 41.)
     c, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Rc")
