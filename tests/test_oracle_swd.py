@@ -125,6 +125,46 @@ def test_rayleigh_kernels_and_group_velocity_against_the_independent_determinant
             assert abs(arr[i, layer] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (Tp, j, arr[i, layer], fd)
 
 
+def test_group_velocity_kernels_against_the_independent_determinant(oracle):
+    """sregnpu builds dU/dm from three solves at T, 1.05 T and 0.95 T (a +-5 % period difference),
+    and the reference takes the first term from the wrong solve (the "stale array" defect,
+    sregn96.f90:1841-1844).  Against derivatives of U computed from the from-scratch determinant:
+    the corrected form (stale=False) is the +-5 % difference approximation of the true kernel
+    (within 5 % of the largest kernel of the period), and the reference's form is measurably
+    further away -- which is why it is reproduced by switch, not by accident."""
+    H = 10.0
+    vs = np.array([3.0, 4.2]); vp = np.array([5.2, 7.4]); rho = np.array([2.5, 3.2]); thk = np.array([H, 0.0])
+    f32 = lambda v: float(np.float32(v))
+    base = [f32(vp[0]), f32(vs[0]), f32(rho[0]), f32(H), f32(vp[1]), f32(vs[1]), f32(rho[1])]
+    T = np.array([3.0, 8.0, 15.0])
+    c, _ = oracle.surf_forward(thk, vp, vs, rho, T, "Rc")
+
+    def U_ind(cg, Tp, par):
+        c0 = rayleigh_root_2layer(cg, Tp, *par)
+        e = 1e-4 * Tp
+        d = (rayleigh_root_2layer(c0, Tp + e, *par) - rayleigh_root_2layer(c0, Tp - e, *par)) / (2 * e)
+        return c0 / (1 + Tp / c0 * d)
+    err = {}
+    for stale in (False, True):
+        u, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, "Rg", 0, False, stale)
+        assert ok
+        worst = 0.0
+        for i, Tp in enumerate(T):
+            fds, got = [], []
+            for j, (arr, layer) in enumerate([(da, 0), (db, 0), (dr, 0), (dh, 0), (da, 1), (db, 1), (dr, 1)]):
+                h = 1e-4 * base[j]
+                pp, pm = list(base), list(base)
+                pp[j] += h
+                pm[j] -= h
+                fds.append((U_ind(c[i], Tp, pp) - U_ind(c[i], Tp, pm)) / (2 * h))
+                got.append(arr[i, layer])
+            fds, got = np.array(fds), np.array(got)
+            worst = max(worst, np.max(np.abs(got - fds)) / np.max(np.abs(fds)))
+        err[stale] = worst
+    assert err[False] < 0.05, err
+    assert err[True] > 1.5 * err[False], err
+
+
 def test_rayleigh_layer_over_halfspace_limits_and_exact_secular_root(oracle):
     """Layer over a half-space, independent of the reference code:
     (i) short periods see only the layer, long periods only the half-space: c -> the analytic
