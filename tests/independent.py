@@ -1,0 +1,81 @@
+"""From-scratch plane-wave solutions of the layered elastic half-space (NumPy only), used as
+INDEPENDENT checks of the oracle: nothing here follows the reference's formulation (Haskell / Dunkin
+propagators); every layer simply carries four potentials and all boundary conditions are assembled
+into one linear system."""
+import numpy as np
+
+
+def layer_system(w, p, thk, vp, vs, rho):
+    """Boundary-condition matrix M, right-hand side for a unit up-going P wave in the half-space, and
+    the four solution columns (ux, uz, tzz, txz) of the top layer at z = 0.
+    Plane waves exp(i w (p x - t)), z down.  Unknowns: (P down, P up, S down, S up) per finite layer,
+    (P down, S down) in the half-space.  Rows: tzz = txz = 0 at the surface, continuity of
+    (ux, uz, tzz, txz) at every interface.  thk[-1] is ignored (half-space)."""
+    n = len(thk)
+    k = w * p
+
+    def cols(a, b, r, z):
+        nua = np.sqrt(complex((w / a)**2 - k * k))
+        nub = np.sqrt(complex((w / b)**2 - k * k))
+        if nua.imag < 0:
+            nua = -nua
+        if nub.imag < 0:
+            nub = -nub
+        mu = r * b * b
+        lam = r * a * a - 2 * mu
+        out = []
+        for s, nu, kind in ((+1, nua, 'p'), (-1, nua, 'p'), (+1, nub, 's'), (-1, nub, 's')):
+            e = np.exp(1j * s * nu * z)
+            kz = s * nu
+            if kind == 'p':   # u = grad(phi), phi = exp(i (k x + kz z))
+                ux, uz = 1j * k, 1j * kz
+            else:             # u = curl(psi y): ux = -dpsi/dz, uz = dpsi/dx
+                ux, uz = -1j * kz, 1j * k
+            dux_dz, duz_dz, dux_dx, duz_dx = 1j * kz * ux, 1j * kz * uz, 1j * k * ux, 1j * k * uz
+            tzz = lam * (dux_dx + duz_dz) + 2 * mu * duz_dz
+            txz = mu * (dux_dz + duz_dx)
+            out.append(np.array([ux, uz, tzz, txz]) * e)
+        return out
+    N = 4 * (n - 1) + 2
+    M = np.zeros((N, N), dtype=complex)
+    rhs = np.zeros(N, dtype=complex)
+    c0 = cols(vp[0], vs[0], rho[0], 0.0)
+    for j in range(4):
+        M[0, j] = c0[j][2]
+        M[1, j] = c0[j][3]
+    row = 2
+    for m in range(n - 1):
+        cb = cols(vp[m], vs[m], rho[m], thk[m])
+        for j in range(4):
+            M[row:row + 4, 4 * m + j] = cb[j]
+        if m + 1 < n - 1:
+            ct = cols(vp[m + 1], vs[m + 1], rho[m + 1], 0.0)
+            for j in range(4):
+                M[row:row + 4, 4 * (m + 1) + j] = -ct[j]
+        else:
+            ch = cols(vp[n - 1], vs[n - 1], rho[n - 1], 0.0)
+            M[row:row + 4, 4 * (n - 1) + 0] = -ch[0]   # P leaving downwards
+            M[row:row + 4, 4 * (n - 1) + 1] = -ch[2]   # S leaving downwards
+            rhs[row:row + 4] = ch[1]                   # the incident P, amplitude 1
+        row += 4
+    return M, rhs, c0
+
+
+def surface_response(w, p, thk, vp, vs, rho):
+    """(ux, uz) at the free surface for a unit P wave incident from the half-space."""
+    M, rhs, c0 = layer_system(w, p, thk, vp, vs, rho)
+    sc = np.max(np.abs(M), axis=0)
+    sc[sc == 0] = 1
+    x = np.linalg.solve(M / sc, rhs) / sc
+    u = sum(x[j] * c0[j][:2] for j in range(4))
+    return u[0], u[1]
+
+
+def rayleigh_secular(c, T, thk, vp, vs, rho):
+    """Determinant of the homogeneous system (no incident wave) at phase velocity c and period T,
+    columns scaled to unit max-norm (positive factors: the phase of the determinant is untouched).
+    Free Rayleigh modes are its zeros for c below the half-space S velocity."""
+    M, _, _ = layer_system(2 * np.pi / T, 1.0 / c, thk, vp, vs, rho)
+    sc = np.max(np.abs(M), axis=0)
+    sc[sc == 0] = 1
+    return np.linalg.det(M / sc)

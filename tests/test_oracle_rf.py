@@ -1,6 +1,7 @@
 """Pins of the RF oracle: FFT vs NumPy, analytic half-space answer, finite differences, invariance."""
 import numpy as np
 import pytest
+from independent import surface_response
 from oracle.oracle import brocher
 from rfsurfhmc_b200.fixtures import f1_true_model
 
@@ -134,3 +135,34 @@ def test_halfspace_amplitude_is_the_free_surface_response_ratio(oracle):
             want = ratio * a / np.sqrt(np.pi)
             t2 = 5e-3 if method == "time" else tol   # deconit represents the pulse by discrete spikes
             assert abs(rf.max() - want) <= max(tol, t2) * want, (vsv, p, a, method, rf.max(), want)
+
+
+def test_multilayer_rf_against_an_independent_plane_wave_solution(oracle):
+    """cal_rf_freq for layered models against a from-scratch solution of the same physics: every
+    layer carries four plane-wave potentials (P/S, up/down), the half-space the incident P plus two
+    radiating waves; stress-free surface and welded interfaces give ONE linear system (NumPy), whose
+    surface displacement ratio ux/uz is the receiver-function spectrum.  Conventions shared with the
+    reference: Gaussian exp(-w^2/4a^2), complex frequency w - i sigma with sigma = 4/(nft dt) undone
+    by exp(sigma (t - t_shift)), velocities v (1 + 1/(8Q^2) + i/(2Q)) with the reference's dummy
+    Q = 9999.  Agreement: 3e-7 of the peak on the 7-layer F1 model (float32 pi, water level)."""
+    cases = [(np.array([6., 6, 13, 5, 10, 30, 0]), np.array([3.2, 2.8, 3.46, 3.3, 3.9, 4.5, 4.7]), 0.045, 125, 0.4, 1.5),
+             (np.array([4., 18., 12., 0.]), np.array([2.6, 3.5, 3.9, 4.6]), 0.07, 250, 0.2, 2.0)]
+    for thk, vs, p, nt, dt, a in cases:
+        vp, rho = brocher(vs)
+        q = thk * 0 + 9999.
+        tshift = 5.0
+        rf = oracle.rf_forward(thk, rho, vp, vs, q, q, p, nt, dt, a, tshift, "freq", 0.001, "P")
+        nft = 1
+        while nft < nt:
+            nft *= 2
+        sigma = 4.0 / (nft * dt)
+        qf = 1 + 1 / (8 * 9999.**2) + 1j / (2 * 9999.)
+        H = np.zeros(nft // 2 + 1, dtype=complex)
+        for kf in range(nft // 2 + 1):
+            w = 2 * np.pi * kf / (nft * dt) - 1j * sigma
+            ux, uz = surface_response(w, p, thk, vp * qf, vs * qf, rho)
+            H[kf] = ux / uz
+        wr = 2 * np.pi * np.arange(nft // 2 + 1) / (nft * dt)
+        spec = H * np.exp(-wr**2 / (4 * a * a)) * np.exp(-1j * wr * tshift)
+        tr = np.fft.irfft(spec, nft)[:nt] / dt * np.exp(sigma * (np.arange(nt) * dt - tshift))
+        assert np.max(np.abs(tr - rf)) <= 2e-6 * np.max(np.abs(rf)), (p, np.max(np.abs(tr - rf)) / np.max(np.abs(rf)))

@@ -125,6 +125,58 @@ def test_rayleigh_kernels_and_group_velocity_against_the_independent_determinant
             assert abs(arr[i, layer] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (Tp, j, arr[i, layer], fd)
 
 
+def _independent_root(c_guess, Tp, par, width=3e-4):
+    from independent import rayleigh_secular
+    lo, hi = c_guess * (1 - width), c_guess * (1 + width)
+    d0 = rayleigh_secular(lo, Tp, *par)
+    ph = d0 / abs(d0)
+    f = lambda x: (rayleigh_secular(x, Tp, *par) / ph).real
+    flo = f(lo)
+    assert np.sign(flo) != np.sign(f(hi)), (c_guess, Tp)
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        fm = f(mid)
+        if np.sign(fm) == np.sign(flo):
+            lo, flo = mid, fm
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def test_f1_rayleigh_against_the_independent_multilayer_system(oracle):
+    """The reference's default 7-layer model (param.yaml) against tests/independent.py: one linear
+    system of plane-wave potentials with all boundary conditions (26 x 26), nothing of the
+    Haskell/Dunkin machinery.  Roots of the fundamental and first higher mode (1.5e-6: nevill's
+    bracket + float32 output), analytic group velocity, and dc/dvs, dc/dh of EVERY layer at 20 s."""
+    f32 = lambda a: np.float32(a).astype(float)
+    par = [f32(THK), f32(VP), f32(VS), f32(RHO)]
+    T = np.array([5., 8., 12., 20., 30., 40.])
+    for mode in (0, 1):
+        c, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Rc", mode)
+        assert ok
+        for Tp, ck in zip(T, c):
+            if ck == 0.0:
+                continue   # mode does not exist at this period
+            assert abs(_independent_root(ck, Tp, par) - ck) < 1.5e-6 * ck, (mode, Tp)
+    Tp = 20.0
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, np.array([Tp]), "Rc")
+    u, _ = oracle.surf_forward(THK, VP, VS, RHO, np.array([Tp]), "Rg")
+    c0 = _independent_root(c[0], Tp, par)
+    e = 1e-4 * Tp
+    dcdT = (_independent_root(c0, Tp + e, par) - _independent_root(c0, Tp - e, par)) / (2 * e)
+    assert abs(u[0] - c0 / (1 + Tp / c0 * dcdT)) < 2e-5 * u[0]
+    big = max(np.max(np.abs(k_)) for k_ in (da, db, dr, dh))
+    for which, arr in ((2, db), (0, dh)):        # index into par: 2 = vs, 0 = thickness
+        for m in range(7 if which == 2 else 6):
+            h = 1e-5 * max(par[which][m], 1.0)
+            pp = [a.copy() for a in par]
+            pm = [a.copy() for a in par]
+            pp[which][m] += h
+            pm[which][m] -= h
+            fd = (_independent_root(c0, Tp, pp) - _independent_root(c0, Tp, pm)) / (2 * h)
+            assert abs(arr[0, m] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (which, m, arr[0, m], fd)
+
+
 def test_group_velocity_kernels_against_the_independent_determinant(oracle):
     """sregnpu builds dU/dm from three solves at T, 1.05 T and 0.95 T (a +-5 % period difference),
     and the reference takes the first term from the wrong solve (the "stale array" defect,
