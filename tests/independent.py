@@ -79,3 +79,37 @@ def rayleigh_secular(c, T, thk, vp, vs, rho):
     sc = np.max(np.abs(M), axis=0)
     sc[sc == 0] = 1
     return np.linalg.det(M / sc)
+
+
+def love_secular(c, T, thk, vs, rho):
+    """SH analogue of rayleigh_secular: two plane waves per finite layer (down, up), one decaying wave
+    in the half-space; tau_yz = 0 at the surface, (u_y, tau_yz) continuous at the interfaces."""
+    n = len(thk)
+    w = 2 * np.pi / T
+    k = w / c
+
+    def cols(b, r, z):
+        nu = np.sqrt(complex((w / b)**2 - k * k))
+        if nu.imag < 0:
+            nu = -nu
+        mu = r * b * b
+        return [np.array([1.0, mu * 1j * s * nu]) * np.exp(1j * s * nu * z) for s in (+1, -1)]
+    N = 2 * (n - 1) + 1
+    M = np.zeros((N, N), dtype=complex)
+    c0 = cols(vs[0], rho[0], 0.0)
+    M[0, 0], M[0, 1] = c0[0][1], c0[1][1]
+    row = 1
+    for m in range(n - 1):
+        cb = cols(vs[m], rho[m], thk[m])
+        M[row:row + 2, 2 * m] = cb[0]
+        M[row:row + 2, 2 * m + 1] = cb[1]
+        if m + 1 < n - 1:
+            ct = cols(vs[m + 1], rho[m + 1], 0.0)
+            M[row:row + 2, 2 * (m + 1)] = -ct[0]
+            M[row:row + 2, 2 * (m + 1) + 1] = -ct[1]
+        else:
+            M[row:row + 2, 2 * (n - 1)] = -cols(vs[n - 1], rho[n - 1], 0.0)[0]
+        row += 2
+    sc = np.max(np.abs(M), axis=0)
+    sc[sc == 0] = 1
+    return np.linalg.det(M / sc)

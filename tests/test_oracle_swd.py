@@ -177,6 +177,54 @@ def test_f1_rayleigh_against_the_independent_multilayer_system(oracle):
             assert abs(arr[0, m] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (which, m, arr[0, m], fd)
 
 
+def test_f1_love_against_the_independent_multilayer_system(oracle):
+    """Same model, Love waves: roots of modes 0 and 1, analytic group velocity and dc/dvs, dc/drho,
+    dc/dh of every layer at 20 s against the from-scratch SH system of tests/independent.py."""
+    from independent import love_secular
+    f32 = lambda a: np.float32(a).astype(float)
+    par = [f32(THK), f32(VS), f32(RHO)]
+
+    def root(c_guess, Tp, pr, width=3e-4):
+        lo, hi = c_guess * (1 - width), c_guess * (1 + width)
+        d0 = love_secular(lo, Tp, *pr)
+        ph = d0 / abs(d0)
+        f = lambda x: (love_secular(x, Tp, *pr) / ph).real
+        flo = f(lo)
+        assert np.sign(flo) != np.sign(f(hi)), (c_guess, Tp)
+        for _ in range(50):
+            mid = 0.5 * (lo + hi)
+            fm = f(mid)
+            if np.sign(fm) == np.sign(flo):
+                lo, flo = mid, fm
+            else:
+                hi = mid
+        return 0.5 * (lo + hi)
+    T = np.array([5., 8., 12., 20., 30., 40.])
+    for mode in (0, 1):
+        c, ok = oracle.surf_forward(THK, VP, VS, RHO, T, "Lc", mode)
+        assert ok
+        for Tp, ck in zip(T, c):
+            if ck != 0.0:
+                assert abs(root(ck, Tp, par) - ck) < 1.5e-6 * ck, (mode, Tp)
+    Tp = 20.0
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(THK, VP, VS, RHO, np.array([Tp]), "Lc")
+    u, _ = oracle.surf_forward(THK, VP, VS, RHO, np.array([Tp]), "Lg")
+    c0 = root(c[0], Tp, par)
+    e = 1e-4 * Tp
+    dcdT = (root(c0, Tp + e, par) - root(c0, Tp - e, par)) / (2 * e)
+    assert abs(u[0] - c0 / (1 + Tp / c0 * dcdT)) < 2e-5 * u[0]
+    big = max(np.max(np.abs(k_)) for k_ in (db, dr, dh))
+    for which, arr, nl in ((1, db, 7), (2, dr, 7), (0, dh, 6)):
+        for m in range(nl):
+            h = 1e-5 * max(par[which][m], 1.0)
+            pp = [a.copy() for a in par]
+            pm = [a.copy() for a in par]
+            pp[which][m] += h
+            pm[which][m] -= h
+            fd = (root(c0, Tp, pp) - root(c0, Tp, pm)) / (2 * h)
+            assert abs(arr[0, m] - fd) < 2e-4 * abs(fd) + 1e-5 * big, (which, m, arr[0, m], fd)
+
+
 def test_group_velocity_kernels_against_the_independent_determinant(oracle):
     """sregnpu builds dU/dm from three solves at T, 1.05 T and 0.95 T (a +-5 % period difference),
     and the reference takes the first term from the wrong solve (the "stale array" defect,
