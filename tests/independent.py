@@ -113,3 +113,72 @@ def love_secular(c, T, thk, vs, rho):
     sc = np.max(np.abs(M), axis=0)
     sc[sc == 0] = 1
     return np.linalg.det(M / sc)
+
+
+def rayleigh_secular_ocean(c, T, thk, vp, vs, rho):
+    """rayleigh_secular for a model whose TOP layer is a fluid (vs[0] == 0): the water carries two
+    compressional waves; pressure-free surface; at the sea floor u_z and tau_zz are continuous and the
+    shear traction of the solid vanishes."""
+    n = len(thk)
+    w = 2 * np.pi / T
+    k = w / c
+
+    def nu_of(v):
+        nu = np.sqrt(complex((w / v)**2 - k * k))
+        return -nu if nu.imag < 0 else nu
+
+    def fluid_cols(a, r, z):
+        nua = nu_of(a)
+        lam = r * a * a
+        out = []
+        for s in (+1, -1):
+            kz = s * nua
+            ux, uz = 1j * k, 1j * kz
+            tzz = lam * (1j * k * ux + 1j * kz * uz)
+            out.append(np.array([ux, uz, tzz, 0.0]) * np.exp(1j * kz * z))
+        return out
+
+    def solid_cols(a, b, r, z):
+        nua, nub = nu_of(a), nu_of(b)
+        mu = r * b * b
+        lam = r * a * a - 2 * mu
+        out = []
+        for s, nu, kind in ((+1, nua, 'p'), (-1, nua, 'p'), (+1, nub, 's'), (-1, nub, 's')):
+            kz = s * nu
+            ux, uz = (1j * k, 1j * kz) if kind == 'p' else (-1j * kz, 1j * k)
+            dux_dz, duz_dz, dux_dx, duz_dx = 1j * kz * ux, 1j * kz * uz, 1j * k * ux, 1j * k * uz
+            out.append(np.array([ux, uz, lam * (dux_dx + duz_dz) + 2 * mu * duz_dz, mu * (dux_dz + duz_dx)])
+                       * np.exp(1j * kz * z))
+        return out
+    N = 2 + 4 * (n - 2) + 2
+    M = np.zeros((N, N), dtype=complex)
+    f0, fb = fluid_cols(vp[0], rho[0], 0.0), fluid_cols(vp[0], rho[0], thk[0])
+    M[0, 0], M[0, 1] = f0[0][2], f0[1][2]                      # pressure-free sea surface
+
+    def place(row, col0, cs, sign, rows):
+        for j, cvec in enumerate(cs):
+            M[row:row + len(rows), col0 + j] = sign * cvec[rows]
+    row = 1
+    col = 2
+    # sea floor: uz, tzz continuous; txz of the solid = 0
+    top = solid_cols(vp[1], vs[1], rho[1], 0.0) if n > 2 else None
+    if n > 2:
+        place(row, 0, fb, +1, [1, 2])
+        place(row, col, top, -1, [1, 2])
+        for j in range(4):
+            M[row + 2, col + j] = top[j][3]
+        row += 3
+        for m in range(1, n - 1):
+            cb = solid_cols(vp[m], vs[m], rho[m], thk[m])
+            place(row, col, cb, +1, [0, 1, 2, 3])
+            if m + 1 < n - 1:
+                place(row, col + 4, solid_cols(vp[m + 1], vs[m + 1], rho[m + 1], 0.0), -1, [0, 1, 2, 3])
+            else:
+                ch = solid_cols(vp[n - 1], vs[n - 1], rho[n - 1], 0.0)
+                M[row:row + 4, col + 4] = -ch[0]
+                M[row:row + 4, col + 5] = -ch[2]
+            row += 4
+            col += 4
+    sc = np.max(np.abs(M), axis=0)
+    sc[sc == 0] = 1
+    return np.linalg.det(M / sc)

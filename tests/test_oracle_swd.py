@@ -504,6 +504,59 @@ def test_spherical_earth_oracle_sanity(oracle):
     assert ok and np.all(np.abs(ug - uf) / uf < 0.05)
 
 
+def test_water_layer_against_the_independent_ocean_system(oracle):
+    """Ocean model (fluid top layer) against tests/independent.py::rayleigh_secular_ocean -- two
+    compressional waves in the water, pressure-free surface, no shear traction at the sea floor:
+    roots at five periods, analytic group velocity, and at 15 s the kernels dc/dvp (water and solids),
+    dc/dvs (solids), dc/drho and dc/dh (including the water depth).  Pins the fluid branches of the
+    restated surfdisp96 (dltar4 water term) and sregn96 (dnka/hska/intijr/energy/getdcdh)."""
+    from independent import rayleigh_secular_ocean
+    thk = np.array([3.0, 2.0, 5.0, 12.0, 0.0])
+    vs = np.array([0.0, 2.2, 3.3, 3.9, 4.6])
+    vp = np.array([1.5, 4.2, 5.9, 6.8, 8.1])
+    rho = np.array([1.03, 2.3, 2.7, 2.9, 3.3])
+    f32 = lambda a: np.float32(a).astype(float)
+    par = [f32(thk), f32(vp), f32(vs), f32(rho)]
+
+    def root(c_guess, Tp, pr, width=3e-4):
+        lo, hi = c_guess * (1 - width), c_guess * (1 + width)
+        d0 = rayleigh_secular_ocean(lo, Tp, *pr)
+        ph = d0 / abs(d0)
+        f = lambda x: (rayleigh_secular_ocean(x, Tp, *pr) / ph).real
+        flo = f(lo)
+        assert np.sign(flo) != np.sign(f(hi)), (c_guess, Tp)
+        for _ in range(50):
+            mid = 0.5 * (lo + hi)
+            fm = f(mid)
+            if np.sign(fm) == np.sign(flo):
+                lo, flo = mid, fm
+            else:
+                hi = mid
+        return 0.5 * (lo + hi)
+    T = np.array([6., 10., 15., 25., 40.])
+    c, da, db, dr, dh, ok = oracle.surf_adjoint_kernel(thk, vp, vs, rho, T, "Rc")
+    u, ok2 = oracle.surf_forward(thk, vp, vs, rho, T, "Rg")
+    assert ok and ok2
+    for i, Tp in enumerate(T):
+        c0 = root(c[i], Tp, par)
+        assert abs(c0 - c[i]) < 1.5e-6 * c0, Tp
+        e = 1e-4 * Tp
+        dcdT = (root(c0, Tp + e, par) - root(c0, Tp - e, par)) / (2 * e)
+        assert abs(u[i] - c0 / (1 + Tp / c0 * dcdT)) < 3e-5 * u[i], Tp
+    i, Tp = 2, 15.0
+    c0 = root(c[i], Tp, par)
+    big = max(np.max(np.abs(k_[i])) for k_ in (da, db, dr, dh))
+    for which, arr, layers in ((1, da, range(5)), (2, db, range(1, 5)), (3, dr, range(5)), (0, dh, range(4))):
+        for m in layers:
+            h = 1e-5 * max(par[which][m], 1.0)
+            pp = [a.copy() for a in par]
+            pm = [a.copy() for a in par]
+            pp[which][m] += h
+            pm[which][m] -= h
+            fd = (root(c0, Tp, pp) - root(c0, Tp, pm)) / (2 * h)
+            assert abs(arr[i, m] - fd) < 3e-4 * abs(fd) + 1e-5 * big, (which, m, arr[i, m], fd)
+
+
 def test_water_layer_oracle_identities(oracle):
     """The fluid branches of the restated sregn96 satisfy the scaling identities; Love ignores water."""
     thk = np.array([3.0, 2.0, 5.0, 12.0, 0.0])
