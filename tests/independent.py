@@ -5,8 +5,8 @@ into one linear system."""
 import numpy as np
 
 
-def layer_system(w, p, thk, vp, vs, rho):
-    """Boundary-condition matrix M, right-hand side for a unit up-going P wave in the half-space, and
+def layer_system(w, p, thk, vp, vs, rho, incident="P"):
+    """Boundary-condition matrix M, right-hand side for a unit up-going P (or SV) wave in the half-space, and
     the four solution columns (ux, uz, tzz, txz) of the top layer at z = 0.
     Plane waves exp(i w (p x - t)), z down.  Unknowns: (P down, P up, S down, S up) per finite layer,
     (P down, S down) in the half-space.  Rows: tzz = txz = 0 at the surface, continuity of
@@ -56,14 +56,14 @@ def layer_system(w, p, thk, vp, vs, rho):
             ch = cols(vp[n - 1], vs[n - 1], rho[n - 1], 0.0)
             M[row:row + 4, 4 * (n - 1) + 0] = -ch[0]   # P leaving downwards
             M[row:row + 4, 4 * (n - 1) + 1] = -ch[2]   # S leaving downwards
-            rhs[row:row + 4] = ch[1]                   # the incident P, amplitude 1
+            rhs[row:row + 4] = ch[1] if incident == "P" else ch[3]   # the incident wave, amplitude 1
         row += 4
     return M, rhs, c0
 
 
-def surface_response(w, p, thk, vp, vs, rho):
-    """(ux, uz) at the free surface for a unit P wave incident from the half-space."""
-    M, rhs, c0 = layer_system(w, p, thk, vp, vs, rho)
+def surface_response(w, p, thk, vp, vs, rho, incident="P"):
+    """(ux, uz) at the free surface for a unit P (or SV) wave incident from the half-space."""
+    M, rhs, c0 = layer_system(w, p, thk, vp, vs, rho, incident)
     sc = np.max(np.abs(M), axis=0)
     sc[sc == 0] = 1
     x = np.linalg.solve(M / sc, rhs) / sc

@@ -166,3 +166,14 @@ def test_multilayer_rf_against_an_independent_plane_wave_solution(oracle):
         spec = H * np.exp(-wr**2 / (4 * a * a)) * np.exp(-1j * wr * tshift)
         tr = np.fft.irfft(spec, nft)[:nt] / dt * np.exp(sigma * (np.arange(nt) * dt - tshift))
         assert np.max(np.abs(tr - rf)) <= 2e-6 * np.max(np.abs(rf)), (p, np.max(np.abs(tr - rf)) / np.max(np.abs(rf)))
+        # S receiver function: incident SV wave, vertical over radial, time shift of opposite sign
+        # (src/RF/main.cpp:35); a ray parameter for which P is still propagating in the half-space
+        ps = 0.1
+        rfs = oracle.rf_forward(thk, rho, vp, vs, q, q, ps, nt, dt, a, tshift, "freq", 0.001, "S")
+        for kf in range(nft // 2 + 1):
+            w = 2 * np.pi * kf / (nft * dt) - 1j * sigma
+            ux, uz = surface_response(w, ps, thk, vp * qf, vs * qf, rho, incident="S")
+            H[kf] = uz / ux
+        spec = H * np.exp(-wr**2 / (4 * a * a)) * np.exp(+1j * wr * tshift)
+        tr = np.fft.irfft(spec, nft)[:nt] / dt * np.exp(sigma * (np.arange(nt) * dt + tshift))
+        assert np.max(np.abs(tr - rfs)) <= 2e-6 * np.max(np.abs(rfs)), ("S", np.max(np.abs(tr - rfs)) / np.max(np.abs(rfs)))
