@@ -158,6 +158,55 @@ def test_references_own_test_script_on_the_gpu(ctx):
     assert rel(dssyn[:36], z["tf_Rc"]) <= TOL_C and rel(dssyn[36:], z["tf_Rg"]) <= TOL_C
 
 
+def test_gpu_against_from_scratch_physics(ctx):
+    """No oracle and no reference code in this test: the CUDA path against tests/independent.py (one
+    linear system of plane-wave potentials per frequency / trial velocity) on the reference's default
+    model -- Rayleigh and Love phase velocities of modes 0 and 1, and the P receiver function."""
+    from independent import rayleigh_secular, love_secular, surface_response
+    from rfsurfhmc_b200.model.lib import libsurf, librf
+    x0 = f1_true_model()
+    vs, thk = x0[:7], x0[7:]
+    vp, rho = brocher(vs)
+    f32 = lambda a: np.float32(a).astype(float)
+
+    def root(fun, c_guess, Tp, par, width=3e-4):
+        lo, hi = c_guess * (1 - width), c_guess * (1 + width)
+        d0 = fun(lo, Tp, *par)
+        ph = d0 / abs(d0)
+        f = lambda x: (fun(x, Tp, *par) / ph).real
+        flo = f(lo)
+        assert np.sign(flo) != np.sign(f(hi)), (c_guess, Tp)
+        for _ in range(50):
+            mid = 0.5 * (lo + hi)
+            fm = f(mid)
+            if np.sign(fm) == np.sign(flo):
+                lo, flo = mid, fm
+            else:
+                hi = mid
+        return 0.5 * (lo + hi)
+    T = np.array([5., 8., 12., 20., 30., 40.])
+    for wt, fun, par in (("Rc", rayleigh_secular, [f32(thk), f32(vp), f32(vs), f32(rho)]),
+                         ("Lc", love_secular, [f32(thk), f32(vs), f32(rho)])):
+        for mode in (0, 1):
+            c, ok = libsurf.forward(thk, vp, vs, rho, T, wt, mode)
+            assert ok
+            for Tp, ck in zip(T, c):
+                if ck != 0.0:
+                    assert abs(root(fun, ck, Tp, par) - ck) < 1.5e-6 * ck, (wt, mode, Tp)
+    q = thk * 0 + 9999.
+    p, nt, dt, a, tshift = 0.045, 125, 0.4, 1.5, 5.0
+    rf = librf.forward(thk, rho, vp, vs, q, q, p, nt, dt, a, tshift, "freq", 0.001, "P")
+    nft = 128
+    sigma = 4.0 / (nft * dt)
+    qf = 1 + 1 / (8 * 9999.**2) + 1j / (2 * 9999.)
+    H = np.array([np.divide(*surface_response(2 * np.pi * kf / (nft * dt) - 1j * sigma, p, thk, vp * qf, vs * qf, rho))
+                  for kf in range(nft // 2 + 1)])
+    wr = 2 * np.pi * np.arange(nft // 2 + 1) / (nft * dt)
+    tr = np.fft.irfft(H * np.exp(-wr**2 / (4 * a * a)) * np.exp(-1j * wr * tshift), nft)[:nt] / dt \
+        * np.exp(sigma * (np.arange(nt) * dt - tshift))
+    assert np.max(np.abs(tr - rf)) <= 2e-6 * np.max(np.abs(rf))
+
+
 def test_error_conventions(ctx):
     from rfsurfhmc_b200._lib import RfsError
     from rfsurfhmc_b200.model.lib import libsurf, librf
