@@ -272,6 +272,17 @@ def main():
         barrier()
         th = time.perf_counter() - t0
         hmc = [th, float(ho["n_iter"].sum()), float(ho["n_acc"].sum()), float(ho["evals"])]
+        # C4 names the dual-averaging sampler (main_DA.py): lambda = L0*dt = 20*0.02, step size adapted
+        # during the first half of the trajectories; L = int(lambda/dt) capped at 40 (extension, see
+        # the reference's gamma = 0.05 lets L explode after one rejected warm-up trajectory)
+        barrier()
+        t0 = time.perf_counter()
+        hd = ctx.hmc_run(1, ids, driver_bounds(x0), 0.02, Lrange=(1, 40), L0=20, target_ratio=0.65,
+                         seed=991206, nsamples=ntraj - ntraj // 2, ndraws=ntraj // 2, max_iters=ntraj,
+                         want_samples=False, want_syn=False)
+        barrier()
+        td = time.perf_counter() - t0
+        hmc += [td, float(hd["n_iter"].sum()), float(hd["n_acc"].sum()), float(hd["evals"])]
 
     # max over ranks
     tt = torch.tensor([ms, t_e2e * 1e3, ms_noflush], dtype=torch.float64, device=dev)
@@ -289,6 +300,13 @@ def main():
                           "includes chain initialisation and the first evaluation)" % (B, args.hmc_traj),
                "trajectories_per_s": float(hv[1]) / th, "accepted_samples_per_s": float(hv[2]) / th,
                "evals_per_s": float(hv[3]) / th, "seconds": th}
+        td = float(hmax[4])
+        hmc["dual_averaging"] = {
+            "sampler": "HMCDualAveraging, L0=20, dt0=0.02, target 0.65, L capped at 40, %d chains/GPU, %d "
+                       "trajectories each (first half adapts the step size; includes _find_initial_dt)"
+                       % (B, args.hmc_traj),
+            "trajectories_per_s": float(hv[5]) / td, "accepted_samples_per_s": float(hv[6]) / td,
+            "evals_per_s": float(hv[7]) / td, "seconds": td}
     value = world * B * args.steps / (ms * 1e-3)
     e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
 
