@@ -126,9 +126,24 @@ long long rfs_hmc_last_evals(rfs_ctx *ctx);
  * (the algorithmic work of the root-search kernel); rfs_read_evals synchronises and reads it.
  * rfs_measure_fp64_peak runs a DFMA micro-benchmark: the roofline denominator of the FP64 path. */
 int rfs_count_evals(rfs_ctx *ctx, int enable);
+/* Root-search mapping (no reference counterpart; results are bit-identical for every mapping):
+ * T < 0 automatic by batch size (default), T = 0 one thread per (model, period sequence),
+ * T in {4,8,16,32}: a team of T lanes per sequence, S speculative scan points per round
+ * (csrc/swd_roots_team.cuh).  Environment override at rfs_create: RFS_ROOTS_TEAM="T,S". */
+int rfs_set_roots_team(rfs_ctx *ctx, int T, int S);
+int rfs_last_roots_team(rfs_ctx *ctx, int *T, int *S);
 long long rfs_read_evals(rfs_ctx *ctx);
 int rfs_read_eval_stats(rfs_ctx *ctx, long long *out3); /* total, slowest thread, threads > 2000 */
 int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops);
+/* One rfs_misfit_grad_dev call with CUDA events around every kernel launch (the RF branch is
+ * serialised behind the SWD branch for this call, so each kernel is timed alone).  ms[RFS_PROF_NK] =
+ * milliseconds per kernel class, launches[RFS_PROF_NK] (may be NULL) = launch counts;
+ * rfs_profile_kernel_name(i) names class i.  bench.py derives every roofline figure from this. */
+#define RFS_PROF_NK 10
+int rfs_profile_eval(rfs_ctx *ctx, long long B, const double *x, int which, double *U, double *grad,
+                     double *dsyn, unsigned char *flag, void *stream, double *ms,
+                     long long *launches);
+const char *rfs_profile_kernel_name(int i);
 /* self-test: the constant-bank exp / sincos / rsqrt of the root search against the CUDA math library
  * on n device-generated arguments; mismatches[6] = exp, sin/cos (large args), sin/cos (small), rsqrt */
 int rfs_selftest_math(rfs_ctx *ctx, long long n, long long *mismatches);

@@ -88,6 +88,14 @@ def load_library():
         L.rfs_read_eval_stats.argtypes = [_vp, _llp]
         L.rfs_measure_fp64_peak.restype = C.c_int
         L.rfs_measure_fp64_peak.argtypes = [_vp, _dp]
+        L.rfs_profile_eval.restype = C.c_int
+        L.rfs_profile_eval.argtypes = [_vp, C.c_longlong, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _dp, _llp]
+        L.rfs_profile_kernel_name.restype = C.c_char_p
+        L.rfs_profile_kernel_name.argtypes = [C.c_int]
+        L.rfs_set_roots_team.restype = C.c_int
+        L.rfs_set_roots_team.argtypes = [_vp, C.c_int, C.c_int]
+        L.rfs_last_roots_team.restype = C.c_int
+        L.rfs_last_roots_team.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.rfs_selftest_math.restype = C.c_int
         L.rfs_selftest_math.argtypes = [_vp, C.c_longlong, _llp]
         _lib = L
@@ -101,7 +109,8 @@ def exported_symbols():
             "rfs_misfit_grad_host", "rfs_surf_forward", "rfs_surf_adjoint_kernel",
             "rfs_surf_adjoint_kernel_modes", "rfs_rf_forward", "rfs_rf_kernel", "rfs_rf_kernel_all",
             "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
-            "rfs_measure_fp64_peak", "rfs_read_eval_stats", "rfs_selftest_math"]
+            "rfs_measure_fp64_peak", "rfs_read_eval_stats", "rfs_selftest_math",
+            "rfs_set_roots_team", "rfs_last_roots_team", "rfs_profile_eval", "rfs_profile_kernel_name"]
 
 
 def _f64(a):
@@ -161,6 +170,16 @@ class Context:
         self._ck(self.L.rfs_read_eval_stats(self.h, v))
         return int(v[0]), int(v[1]), int(v[2])
 
+    def set_roots_team(self, T=-1, S=1):
+        """Pin the root-search mapping: T<0 automatic, 0 thread-mapped, else T lanes per sequence with
+        S speculative scan points (results are bit-identical for every mapping)."""
+        self._ck(self.L.rfs_set_roots_team(self.h, int(T), int(S)))
+
+    def last_roots_team(self):
+        t, s = C.c_int(0), C.c_int(0)
+        self._ck(self.L.rfs_last_roots_team(self.h, C.byref(t), C.byref(s)))
+        return int(t.value), int(s.value)
+
     def selftest_math(self, n=1 << 22):
         """Mismatch counts (exp, sin/cos large, sin/cos small, rsqrt) of the constant-bank math of the
         root search against the CUDA math library; all zero = bit-identical."""
@@ -212,6 +231,17 @@ class Context:
     def misfit_grad_dev(self, B, x_ptr, which, U_ptr, g_ptr, d_ptr, f_ptr, stream_ptr):
         self._ck(self.L.rfs_misfit_grad_dev(self.h, int(B), _vp(x_ptr), int(which), _vp(U_ptr), _vp(g_ptr),
                                             _vp(d_ptr), _vp(f_ptr), _vp(stream_ptr)))
+
+    PROF_NK = 10
+
+    def profile_eval(self, B, x_ptr, which, U_ptr, g_ptr, d_ptr, f_ptr, stream_ptr):
+        """One evaluation with CUDA events around every kernel: {kernel class: (ms, launches)}."""
+        ms = (C.c_double * self.PROF_NK)()
+        nl = (C.c_longlong * self.PROF_NK)()
+        self._ck(self.L.rfs_profile_eval(self.h, int(B), _vp(x_ptr), int(which), _vp(U_ptr), _vp(g_ptr),
+                                         _vp(d_ptr), _vp(f_ptr), _vp(stream_ptr), ms, nl))
+        return {self.L.rfs_profile_kernel_name(i).decode(): (float(ms[i]), int(nl[i]))
+                for i in range(self.PROF_NK)}
 
     # ---- libsurf / librf drop-ins (batched)
     def surf_forward(self, thk, vp, vs, rho, period, wavetype, mode=0, sphere=False):

@@ -17,6 +17,7 @@
 #include "rf_kernels.cuh"
 #include "rf_time_kernels.cuh"
 #include "swd_kernels.cuh"
+#include "swd_roots_team.cuh"
 
 using namespace rfs;
 
@@ -67,6 +68,19 @@ struct rfs_ctx {
   size_t ws_budget = (size_t)24 << 30;  // workspace budget per chunk (bytes)
   Buf d_counter;                 // [0] secular-function evaluations (algorithmic-work counter)
   bool count_evals = false;
+  // root-search mapping: team_T < 0 automatic (by batch size), 0 thread-mapped, else T lanes per
+  // (model, sequence) with team_S speculative scan slots (swd_roots_team.cuh)
+  int team_T = -1, team_S = 1;
+  int last_team_T = 0, last_team_S = 1;  // what the last launch used (reported by bench.py)
+  // per-kernel timing (rfs_profile_eval): CUDA events around every launch while `prof` is set
+  struct ProfRec {
+    const char *name;
+    cudaEvent_t e0, e1;
+  };
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -80,10 +94,31 @@ namespace {
     }                                                                                    \
   } while (0)
 
+cudaEvent_t prof_event(rfs_ctx *ctx) {
+  if (ctx->prof_used == ctx->prof_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    ctx->prof_pool.push_back(e);
+  }
+  return ctx->prof_pool[ctx->prof_used++];
+}
+inline void prof_begin(rfs_ctx *ctx, const char *name, cudaStream_t st) {
+  if (!ctx->prof) return;
+  rfs_ctx::ProfRec r{name, prof_event(ctx), prof_event(ctx)};
+  cudaEventRecord(r.e0, st);
+  ctx->prof_recs.push_back(r);
+}
+inline void prof_end(rfs_ctx *ctx, cudaStream_t st) {
+  if (!ctx->prof) return;
+  cudaEventRecord(ctx->prof_recs.back().e1, st);
+}
+
 #define LAUNCH(kern, grid, block, smem, st, ...)                 \
   do {                                                           \
+    prof_begin(ctx, #kern, (st));                                \
     kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);        \
     ctx->launches++;                                             \
+    prof_end(ctx, (st));                                         \
     CK(cudaGetLastError());                                      \
   } while (0)
 
@@ -207,6 +242,80 @@ int make_blocks(rfs_ctx *ctx, const double *d_flat, long long B, int n, int sphe
   return RFS_OK;
 }
 
+// ---- root-search mapping (K1 thread-mapped / K1t team-mapped), chosen by the number of sequences in
+// flight.  Thread-mapped needs ~25 k sequences to fill 148 SMs; below that a team of T lanes per
+// sequence cuts the latency of every secular evaluation (layer-parallel) and of the bracketing scan
+// (S speculative grid points).  Thresholds measured on B200 (profiles/r02_roots_sweep.json).
+void pick_team(const rfs_ctx *ctx, long long jobs, int n, int &T, int &S) {
+  if (ctx->team_T >= 0) {
+    T = ctx->team_T;
+    S = ctx->team_T ? ctx->team_S : 1;
+    return;
+  }
+  T = 0;
+  S = 1;
+  if (n <= 8) {
+    if (jobs >= 24576) return;
+    if (jobs >= 8192) { T = 4; S = 1; return; }
+    if (jobs >= 2048) { T = 8; S = 1; return; }
+    T = 32; S = 4;
+    return;
+  }
+  if (n <= 16) {
+    if (jobs >= 24576) return;
+    if (jobs >= 4096) { T = 8; S = 1; return; }
+    if (jobs >= 1024) { T = 16; S = 1; return; }
+    T = 32; S = 2;
+    return;
+  }
+  // many layers: one warp per sequence as soon as the thread mapping cannot fill the machine
+  if (jobs >= 32768) return;
+  if (jobs >= 8192) { T = 8; S = 1; return; }
+  T = 32; S = 1;
+}
+
+bool team_supported(int T, int S) {
+  static const int ok[][2] = {{4, 1}, {4, 4}, {8, 1}, {8, 2}, {16, 1}, {16, 2}, {32, 1}, {32, 2}, {32, 4}};
+  for (auto &p : ok)
+    if (p[0] == T && p[1] == S) return true;
+  return false;
+}
+
+int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
+                 long long B, int n, int all_modes, cudaStream_t st) {
+  unsigned long long *cnt = ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr;
+  int T, S;
+  const long long jobs = B * P.nseq;
+  pick_team(ctx, jobs, n, T, S);
+  ctx->last_team_T = T;
+  ctx->last_team_S = S;
+  if (T == 0) {
+    LAUNCH(swd_roots_kernel, gridFor(jobs, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd, B, n,
+           d_periods, all_modes, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
+           (int *)ctx->w_ierr.p, cnt);
+    return RFS_OK;
+  }
+  // threads per block: as many teams as fit ~64 KB of staged layer parameters
+  int threads = 128;
+  const size_t per_team = sizeof(double) * RFS_TEAM_NF * (size_t)n;
+  while (threads > 32 && threads > T && (threads / T) * per_team > 64 * 1024) threads /= 2;
+  const size_t sm = (threads / T) * per_team;
+  const unsigned grid = gridFor(jobs, threads / T);
+#define TEAM(TT, SS)                                                                              \
+  if (T == TT && S == SS) {                                                                       \
+    if (sm > 48 * 1024)                                                                           \
+      CK(cudaFuncSetAttribute(swd_roots_team_kernel<TT, SS>,                                      \
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));             \
+    LAUNCH((swd_roots_team_kernel<TT, SS>), grid, threads, sm, st, P, d_swd, B, n, d_periods,     \
+           all_modes, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p,   \
+           cnt);                                                                                  \
+    return RFS_OK;                                                                                \
+  }
+  TEAM(4, 1) TEAM(4, 4) TEAM(8, 1) TEAM(8, 2) TEAM(16, 1) TEAM(16, 2) TEAM(32, 1) TEAM(32, 2) TEAM(32, 4)
+#undef TEAM
+  return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
+}
+
 // ---- SWD pipeline on a prepared model block: roots + eigen solves
 int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
             long long B, int n, bool all_modes, bool want_eigen, cudaStream_t st) {
@@ -218,11 +327,7 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
   if ((rc = ensure(ctx, ctx->w_croot, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_cwork, sizeof(double) * (size_t)P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
-  LAUNCH(swd_roots_kernel, gridFor(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd, B, n,
-         d_periods,
-         all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
-         (int *)ctx->w_ierr.p,
-         ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr);
+  if ((rc = launch_roots(ctx, P, d_periods, d_swd, B, n, all_modes ? 1 : 0, st))) return rc;
   // per-period retries of failed fundamental-mode searches (rare; idle warps exit at once)
   if ((rc = ensure(ctx, ctx->w_rstat, sizeof(int) * (size_t)P.nsolve * B))) return rc;
   LAUNCH(swd_retry_kernel, gridFor(B * P.nsolve, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd,
@@ -413,6 +518,14 @@ int rfs_create(rfs_ctx **out, int device) {
     return RFS_E_CUDA;
   }
   if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
+  // RFS_ROOTS_TEAM="T,S" pins the root-search mapping (0 = thread-mapped); default: by batch size
+  if (const char *e = getenv("RFS_ROOTS_TEAM")) {
+    int t = -1, s2 = 1;
+    if (sscanf(e, "%d,%d", &t, &s2) >= 1 && (t == 0 || team_supported(t, s2))) {
+      ctx->team_T = t;
+      ctx->team_S = s2;
+    }
+  }
   // workspace budget per chunk of the fused path (MiB); batches larger than what fits are chunked
   if (const char *e = getenv("RFS_WS_BUDGET_MB")) {
     const long long mb = atoll(e);
@@ -434,6 +547,7 @@ void rfs_destroy(rfs_ctx *ctx) {
                 &ctx->w_sph[2],  &ctx->w_sph[3], &ctx->w_rstat};
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);
+  for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -875,6 +989,66 @@ int rfs_rf_kernel_all(rfs_ctx *ctx, long long B, int n, const double *thk, const
 
 
 // ---- measurement helpers (bench.py) ---------------------------------------------------------
+// kernel classes of rfs_profile_eval
+static const char *const kProfNames[RFS_PROF_NK] = {
+    "prep_models",  "swd_roots", "swd_retry",      "swd_eigen", "rf_layer",
+    "rf_propagate", "rf_decon",  "rf_time_domain", "assemble",  "other"};
+static int prof_class(const char *name) {
+  if (strstr(name, "prep_")) return 0;
+  if (strstr(name, "swd_roots")) return 1;
+  if (strstr(name, "swd_retry")) return 2;
+  if (strstr(name, "swd_eigen")) return 3;
+  if (strstr(name, "rf_layer")) return 4;
+  if (strstr(name, "rf_propagate")) return 5;
+  if (strstr(name, "rf_decon")) return 6;
+  if (strstr(name, "rf_time") || strstr(name, "rf_trace")) return 7;
+  if (strstr(name, "joint_assemble")) return 8;
+  return 9;
+}
+const char *rfs_profile_kernel_name(int i) {
+  return (i >= 0 && i < RFS_PROF_NK) ? kProfNames[i] : "";
+}
+int rfs_profile_eval(rfs_ctx *ctx, long long B, const double *x, int which, double *U, double *grad,
+                     double *dsyn, unsigned char *flag, void *stream, double *ms,
+                     long long *launches) {
+  if (!ctx || !ms) return RFS_E_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const bool ov = ctx->overlap;
+  ctx->overlap = false;  // serialise the RF branch so that every kernel is timed alone
+  ctx->prof = true;
+  ctx->prof_recs.clear();
+  ctx->prof_used = 0;
+  int rc = rfs_misfit_grad_dev(ctx, B, x, which, U, grad, dsyn, flag, stream);
+  ctx->prof = false;
+  ctx->overlap = ov;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int i = 0; i < RFS_PROF_NK; i++) ms[i] = 0.0;
+  if (launches)
+    for (int i = 0; i < RFS_PROF_NK; i++) launches[i] = 0;
+  for (const auto &r : ctx->prof_recs) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    const int c = prof_class(r.name);
+    ms[c] += (double)t;
+    if (launches) launches[c]++;
+  }
+  return RFS_OK;
+}
+
+int rfs_set_roots_team(rfs_ctx *ctx, int T, int S) {
+  if (!ctx) return RFS_E_ARG;
+  if (T > 0 && !team_supported(T, S)) return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
+  ctx->team_T = T;
+  ctx->team_S = T > 0 ? S : 1;
+  return RFS_OK;
+}
+int rfs_last_roots_team(rfs_ctx *ctx, int *T, int *S) {
+  if (!ctx || !T || !S) return RFS_E_ARG;
+  *T = ctx->last_team_T;
+  *S = ctx->last_team_S;
+  return RFS_OK;
+}
 int rfs_count_evals(rfs_ctx *ctx, int enable) {
   if (!ctx) return RFS_E_ARG;
   CK(cudaSetDevice(ctx->device));

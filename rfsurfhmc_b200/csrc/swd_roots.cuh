@@ -46,46 +46,67 @@ struct SwdModel {
 };
 
 // ---- Love secular function: Haskell 2-vector from the half-space up (surfdisp96.f:727-787)
-RFS_DEVINL double dltar1_dev(double wvno, double omega, const SwdModel &M, long long b, int llw) {
+// love_layer builds the layer terms, love_apply propagates + normalises the 2-vector; the split
+// lets the team kernel (swd_roots_team.cuh) build layers in parallel with the same operations.
+struct LoveL {
+  double xmu, cosq, y, z;
+};
+template <class MT>
+RFS_DEVINL LoveL love_layer(const MT &M, long long b, int m, double wvno, double omega) {
+  LoveL L;
+  const double beta1 = M.ld(F_B, m, b);
+  const double rho1 = M.ld(F_RHO, m, b);
+  const double dm = M.ld(F_D, m, b);
+  L.xmu = rho1 * beta1 * beta1;
+  const double xkb = omega / beta1;
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  const double q = dm * rb;
+  if (wvno < xkb) {
+    double sinq;
+    sincos_cb(q, &sinq, &L.cosq);
+    L.y = sinq / rb;
+    L.z = -rb * sinq;
+  } else if (wvno == xkb) {
+    L.cosq = 1.0;
+    L.y = dm;
+    L.z = 0.0;
+  } else {
+    double fac = 0.0;
+    if (q < 16.0) fac = exp_neg(2.0 * q);
+    L.cosq = (1.0 + fac) * 0.5;
+    const double sinq = (1.0 - fac) * 0.5;
+    L.y = sinq / rb;
+    L.z = rb * sinq;
+  }
+  return L;
+}
+RFS_DEVINL void love_apply(const LoveL &L, double &e1, double &e2) {
+  const double e10 = e1 * L.cosq + e2 * L.xmu * L.z;
+  const double e20 = e1 * L.y / L.xmu + e2 * L.cosq;
+  double xnor = fmax(fabs(e10), fabs(e20));
+  if (xnor < 1.e-40) xnor = 1.0;
+  e1 = e10 / xnor;
+  e2 = e20 / xnor;
+}
+template <class MT>
+RFS_DEVINL void love_halfspace(const MT &M, long long b, double wvno, double omega, double &e1,
+                               double &e2) {
   const int mmax = M.n;
-  double beta1 = M.ld(F_B, mmax - 1, b);
-  double rho1 = M.ld(F_RHO, mmax - 1, b);
-  double xkb = omega / beta1;
-  double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-  double e1 = rho1 * rb;
-  double e2 = 1.0 / (beta1 * beta1);
+  const double beta1 = M.ld(F_B, mmax - 1, b);
+  const double rho1 = M.ld(F_RHO, mmax - 1, b);
+  const double xkb = omega / beta1;
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  e1 = rho1 * rb;
+  e2 = 1.0 / (beta1 * beta1);
+}
+template <class MT>
+RFS_DEVINL double dltar1_dev(double wvno, double omega, const MT &M, long long b, int llw) {
+  const int mmax = M.n;
+  double e1, e2;
+  love_halfspace(M, b, wvno, omega, e1, e2);
   for (int m = mmax - 2; m >= llw - 1; m--) {
-    beta1 = M.ld(F_B, m, b);
-    rho1 = M.ld(F_RHO, m, b);
-    const double dm = M.ld(F_D, m, b);
-    const double xmu = rho1 * beta1 * beta1;
-    xkb = omega / beta1;
-    rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const double q = dm * rb;
-    double y, z, cosq;
-    if (wvno < xkb) {
-      double sinq;
-      sincos_cb(q, &sinq, &cosq);
-      y = sinq / rb;
-      z = -rb * sinq;
-    } else if (wvno == xkb) {
-      cosq = 1.0;
-      y = dm;
-      z = 0.0;
-    } else {
-      double fac = 0.0;
-      if (q < 16.0) fac = exp_neg(2.0 * q);
-      cosq = (1.0 + fac) * 0.5;
-      const double sinq = (1.0 - fac) * 0.5;
-      y = sinq / rb;
-      z = rb * sinq;
-    }
-    const double e10 = e1 * cosq + e2 * xmu * z;
-    const double e20 = e1 * y / xmu + e2 * cosq;
-    double xnor = fmax(fabs(e10), fabs(e20));
-    if (xnor < 1.e-40) xnor = 1.0;
-    e1 = e10 / xnor;
-    e2 = e20 / xnor;
+    const LoveL L = love_layer(M, b, m, wvno, omega);
+    love_apply(L, e1, e2);
   }
   return e1;
 }
@@ -182,7 +203,8 @@ struct Dunkin {
   double c11, c12, c13, c14, c15, c21, c22, c23, c24, c31, c32, c33, c34, c35, c41, c42, c43, c51,
       c53;
 };
-RFS_DEVINL Dunkin dunkin_layer(const SwdModel &M, long long b, int m, double wvno, double wvno2,
+template <class MT>
+RFS_DEVINL Dunkin dunkin_layer(const MT &M, long long b, int m, double wvno, double wvno2,
                                double omega, double iom) {
   const double bm = M.ld(F_B, m, b);
   const double dpth = M.ld(F_D, m, b), rho = M.ld(F_RHO, m, b), irho = M.ld(F_IRHO, m, b);
@@ -247,8 +269,40 @@ RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2
   e3 = n3 * it1;
   e4 = n4 * it1;
 }
-RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const SwdModel &M,
-                             long long b, int llw) {
+// half-space start vector of dltar4 (surfdisp96.f:815-835)
+template <class MT>
+RFS_DEVINL void dunkin_halfspace(const MT &M, long long b, double wvno, double wvno2, double omega,
+                                 double iom, double &e0, double &e1, double &e2, double &e3,
+                                 double &e4) {
+  const int mmax = M.n;
+  const double bm = M.ld(F_B, mmax - 1, b);
+  const double rho1 = M.ld(F_RHO, mmax - 1, b);
+  const double xka = omega * M.ld(F_IA, mmax - 1, b), xkb = omega * M.ld(F_IB, mmax - 1, b);
+  const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
+  const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
+  const double t = bm * iom;
+  const double gammk = 2.0 * t * t;
+  const double gam = gammk * wvno2;
+  const double gamm1 = gam - 1.0;
+  e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
+  e1 = -rho1 * ra;
+  e2 = rho1 * (gamm1 - gammk * ra * rb);
+  e3 = rho1 * rb;
+  e4 = wvno2 - ra * rb;
+}
+// water layer on top (surfdisp96.f:870-886)
+template <class MT>
+RFS_DEVINL double dunkin_water_top(const MT &M, long long b, double wvno, double omega, double e0,
+                                   double e1) {
+  const double dpth = M.ld(F_D, 0, b), rho1 = M.ld(F_RHO, 0, b);
+  const double xka = omega * M.ld(F_IA, 0, b);
+  const VarHalf P = var_half(wvno, xka, (wvno + xka) * fabs(wvno - xka), dpth);
+  const double w0 = -rho1 * P.w;
+  return P.c * e0 + w0 * e1;
+}
+template <class MT>
+RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const MT &M, long long b,
+                             int llw) {
   const int mmax = M.n;
   double omega = omga, iom = iomga;
   if (omega < 1.0e-4) {
@@ -257,35 +311,13 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const SwdMo
   }
   const double wvno2 = wvno * wvno;
   double e0, e1, e2, e3, e4;
-  {
-    const double bm = M.ld(F_B, mmax - 1, b);
-    const double rho1 = M.ld(F_RHO, mmax - 1, b);
-    const double xka = omega * M.ld(F_IA, mmax - 1, b), xkb = omega * M.ld(F_IB, mmax - 1, b);
-    const double ra = sqrt((wvno + xka) * fabs(wvno - xka));
-    const double rb = sqrt((wvno + xkb) * fabs(wvno - xkb));
-    const double t = bm * iom;
-    const double gammk = 2.0 * t * t;
-    const double gam = gammk * wvno2;
-    const double gamm1 = gam - 1.0;
-    e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
-    e1 = -rho1 * ra;
-    e2 = rho1 * (gamm1 - gammk * ra * rb);
-    e3 = rho1 * rb;
-    e4 = wvno2 - ra * rb;
-  }
+  dunkin_halfspace(M, b, wvno, wvno2, omega, iom, e0, e1, e2, e3, e4);
   // (forming two layer matrices per trip for more ILP was measured SLOWER: 166 registers or spills)
   for (int m = mmax - 2; m >= llw - 1; m--) {
     const Dunkin C = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
     dunkin_apply(C, e0, e1, e2, e3, e4);
   }
-  if (llw != 1) {
-    // water layer on top (surfdisp96.f:870-886)
-    const double dpth = M.ld(F_D, 0, b), rho1 = M.ld(F_RHO, 0, b);
-    const double xka = omega * M.ld(F_IA, 0, b);
-    const VarHalf P = var_half(wvno, xka, (wvno + xka) * fabs(wvno - xka), dpth);
-    const double w0 = -rho1 * P.w;
-    return P.c * e0 + w0 * e1;
-  }
+  if (llw != 1) return dunkin_water_top(M, b, wvno, omega, e0, e1);
   return e0;
 }
 
