@@ -58,6 +58,16 @@ int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int nt
                    int mode, int sphere, int stale_group_kernel);
 int rfs_config_rf(rfs_ctx *ctx, int nlayer, double ray_p, int nt, double dt, double gauss,
                   double time_shift, double water, int rf_type, int method);
+/* Extensions of the two calls above for objectives with several modes / several ray parameters
+ * (BASELINE configs 2 and 3; the reference's classes hold one `mode` and one `ray_p`, so such data
+ * sets need one model object per mode / ray parameter there).  modes[] ascending; the SWD data
+ * vector becomes [mode][Rc,Rg,Lc,Lg], the RF data vector [ray parameter][nt].  All modes are solved
+ * in ONE chained root-search pass (surfdisp96.f:232-368 solves modes 1..mode+1 anyway). */
+int rfs_config_swd_modes(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int ntRg,
+                         const double *tRg, int ntLc, const double *tLc, int ntLg, const double *tLg,
+                         int nmodes, const int *modes, int sphere, int stale_group_kernel);
+int rfs_config_rf_rays(rfs_ctx *ctx, int nlayer, int nray, const double *ray_p, int nt, double dt,
+                       double gauss, double time_shift, double water, int rf_type, int method);
 /* dobs (host pointer): [nt_rf + n_swd] joint, or the matching sub-vector for which=1/2 */
 int rfs_config_obs(rfs_ctx *ctx, double sigma1, double sigma2, const double *dobs, int ndobs);
 
@@ -105,6 +115,8 @@ int rfs_rf_kernel_all(rfs_ctx *ctx, long long B, int n, const double *thk, const
 
 /* ---- device-resident HMC (replaces the Python loops of pyhmc/hmc.py:140-276 and
  *      pyhmc/hmcda.py:170-369; chain i uses NumPy-legacy MT19937 seeded with seed+chain_id[i]) ---
+ * which  : objective sampled, as in rfs_misfit_grad_dev (0 Joint_RF_SWD, 1 ReceiverFunc, 2 SurfWD:
+ *          the reference samplers take any object with misfit_and_grad, pyhmc/hmc.py:113-119).
  * sampler: 0 HamitonianMC (fixed dt, L ~ randint[Lmin,Lmax]), 1 HMCDualAveraging (L0, target;
  *          Lmax > 0 caps L = max(1,int(lambda/dt)) — an extension, 0 = unlimited as the reference).
  * bounds [2n][2] (low, high), shared by all chains (host pointer).
@@ -112,7 +124,7 @@ int rfs_rf_kernel_all(rfs_ctx *ctx, long long B, int n, const double *thk, const
  * syn [C][nsamples][ndata], initmodel [C][2n], n_iter [C] (trajectories run), n_acc [C],
  * dt_final [C], accept_seq [C][max_iter_log] (1/0 per trajectory, -1 padding; for RNG parity tests).
  * max_iters bounds the number of trajectories per chain (0 = unlimited). */
-int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_id,
+int rfs_hmc_run(rfs_ctx *ctx, int sampler, int which, long long C, const long long *chain_id,
                 const double *bounds, double dt, int Lmin, int Lmax, int L0, double target_ratio,
                 long long seed, int nsamples, int ndraws, long long max_iters, double *samples,
                 double *misfit, double *syn, double *initmodel, long long *n_iter,

@@ -186,8 +186,9 @@ def _find_initial_dt(f, dt0, x, bounds, rs):
     return dt
 
 
-def run_da(f, bounds, dt_cfg, L0, target, seed, nsamples, ndraws, max_iters=None):
-    """HMCDualAveraging.sample for one chain whose seed is already `seed + rank`."""
+def run_da(f, bounds, dt_cfg, L0, target, seed, nsamples, ndraws, max_iters=None, max_L=0):
+    """HMCDualAveraging.sample for one chain whose seed is already `seed + rank`.
+    max_L > 0: the cap on L that rfs_hmc_run offers as an extension (0 = the reference)."""
     rs = np.random.RandomState()
     rs.seed(seed)
     R = ChainResult()
@@ -207,6 +208,8 @@ def run_da(f, bounds, dt_cfg, L0, target, seed, nsamples, ndraws, max_iters=None
         if max_iters is not None and ncount >= max_iters:
             break
         L = max(1, int(lam / dt))
+        if max_L > 0:
+            L = min(L, max_L)
         t = _trajectory(f, x, dt, L, bounds, rs)
         alpha = 0.
         if t is not None:
@@ -247,10 +250,11 @@ def run_da(f, bounds, dt_cfg, L0, target, seed, nsamples, ndraws, max_iters=None
     return R
 
 
-def oracle_joint_f(O, dobs, cfg):
-    """misfit_and_grad callable backed by the C++ oracle (Joint_RF_SWD semantics)."""
+def oracle_joint_f(O, dobs, cfg, which=0):
+    """misfit_and_grad callable backed by the C++ oracle (which: 0 Joint_RF_SWD, 1 ReceiverFunc,
+    2 SurfWD semantics)."""
     def f(x):
-        U, g, d, fl = O.joint_batch(np.asarray(x)[None, :], dobs, cfg, which=0)
+        U, g, d, fl = O.joint_batch(np.asarray(x)[None, :], dobs, cfg, which=which)
         if not fl[0]:
             return 0.0, np.zeros(len(x)), dobs, False
         return float(U[0]), g[0], d[0], True

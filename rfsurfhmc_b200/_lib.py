@@ -53,6 +53,12 @@ def load_library():
         L.rfs_config_rf.restype = C.c_int
         L.rfs_config_rf.argtypes = [_vp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
                                     C.c_double, C.c_int, C.c_int]
+        L.rfs_config_swd_modes.restype = C.c_int
+        L.rfs_config_swd_modes.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp,
+                                           C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.rfs_config_rf_rays.restype = C.c_int
+        L.rfs_config_rf_rays.argtypes = [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, C.c_int, C.c_int]
         L.rfs_config_obs.restype = C.c_int
         L.rfs_config_obs.argtypes = [_vp, C.c_double, C.c_double, _dp, C.c_int]
         L.rfs_misfit_grad_dev.restype = C.c_int
@@ -75,7 +81,7 @@ def load_library():
         L.rfs_rf_kernel_all.restype = C.c_int
         L.rfs_rf_kernel_all.argtypes = rf_in + [_dp, _dp]
         L.rfs_hmc_run.restype = C.c_int
-        L.rfs_hmc_run.argtypes = [_vp, C.c_int, C.c_longlong, _llp, _dp, C.c_double, C.c_int, C.c_int, C.c_int,
+        L.rfs_hmc_run.argtypes = [_vp, C.c_int, C.c_int, C.c_longlong, _llp, _dp, C.c_double, C.c_int, C.c_int, C.c_int,
                                   C.c_double, C.c_longlong, C.c_int, C.c_int, C.c_longlong, _dp, _dp, _dp, _dp,
                                   _llp, _llp, _dp, _i8p, C.c_longlong]
         L.rfs_hmc_last_evals.restype = C.c_longlong
@@ -110,7 +116,8 @@ def exported_symbols():
             "rfs_surf_adjoint_kernel_modes", "rfs_rf_forward", "rfs_rf_kernel", "rfs_rf_kernel_all",
             "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
             "rfs_measure_fp64_peak", "rfs_read_eval_stats", "rfs_selftest_math",
-            "rfs_set_roots_team", "rfs_last_roots_team", "rfs_profile_eval", "rfs_profile_kernel_name"]
+            "rfs_set_roots_team", "rfs_last_roots_team", "rfs_profile_eval", "rfs_profile_kernel_name",
+            "rfs_config_swd_modes", "rfs_config_rf_rays"]
 
 
 def _f64(a):
@@ -194,19 +201,26 @@ class Context:
 
     # ---- configuration
     def config_swd(self, nlayer, tRc=None, tRg=None, tLc=None, tLg=None, mode=0, sphere=False, stale=True):
+        """mode: int (the reference's SurfWD.mode) or an ascending list of modes (one objective over
+        several modes; data vector [mode][Rc,Rg,Lc,Lg])."""
         per = [_f64(t if t is not None else []) for t in (tRc, tRg, tLc, tLg)]
-        self._ck(self.L.rfs_config_swd(self.h, int(nlayer), per[0].size, _p(per[0]), per[1].size, _p(per[1]),
-                                       per[2].size, _p(per[2]), per[3].size, _p(per[3]), int(mode),
-                                       int(bool(sphere)), int(bool(stale))))
+        modes = np.ascontiguousarray(np.atleast_1d(mode), dtype=np.int32)
+        self._ck(self.L.rfs_config_swd_modes(
+            self.h, int(nlayer), per[0].size, _p(per[0]), per[1].size, _p(per[1]), per[2].size, _p(per[2]),
+            per[3].size, _p(per[3]), modes.size, modes.ctypes.data_as(C.POINTER(C.c_int)),
+            int(bool(sphere)), int(bool(stale))))
         self.n = int(nlayer)
-        self.n_swd_data = sum(p.size for p in per)
+        self.n_swd_data = sum(p.size for p in per) * modes.size
 
     def config_rf(self, nlayer, ray_p, nt, dt, gauss, time_shift, water=0.001, rf_type="P", method="freq"):
-        self._ck(self.L.rfs_config_rf(self.h, int(nlayer), float(ray_p), int(nt), float(dt), float(gauss),
-                                      float(time_shift), float(water), rf_type_code(rf_type),
-                                      method_code(method)))
+        """ray_p: float (the reference's ReceiverFunc.ray_p) or a list (one objective over several ray
+        parameters; data vector [ray parameter][nt])."""
+        rays = _f64(np.atleast_1d(ray_p))
+        self._ck(self.L.rfs_config_rf_rays(self.h, int(nlayer), rays.size, _p(rays), int(nt), float(dt),
+                                           float(gauss), float(time_shift), float(water),
+                                           rf_type_code(rf_type), method_code(method)))
         self.n = int(nlayer)
-        self.nt_rf = int(nt)
+        self.nt_rf = int(nt) * rays.size
 
     def config_obs(self, dobs, sigma1=1.0, sigma2=1.0):
         d = _f64(dobs)
@@ -315,12 +329,12 @@ class Context:
     # ---- device-resident HMC
     def hmc_run(self, sampler, chain_ids, bounds, dt, Lrange=(5, 20), L0=10, target_ratio=0.65,
                 seed=0, nsamples=800, ndraws=200, max_iters=0, want_samples=True, want_syn=False,
-                log_accepts=0):
+                log_accepts=0, which=0):
         ids = np.ascontiguousarray(np.asarray(chain_ids, dtype=np.int64))
         Cn = ids.size
         b = _f64(bounds)
         n2 = b.shape[0]
-        nd = self.ndata(0)
+        nd = self.ndata(which)
         out = {
             "misfit": np.zeros((Cn, nsamples)),
             "samples": np.zeros((Cn, nsamples, n2)) if want_samples else None,
@@ -331,8 +345,11 @@ class Context:
             "dt": np.zeros(Cn),
             "accept_seq": np.zeros((Cn, log_accepts), dtype=np.int8) if log_accepts > 0 else None,
         }
+        if Cn == 0:   # a rank without chains (nchains < world size): empty results, nothing to run
+            out.update(evals=0, warning="")
+            return out
         rc = self.L.rfs_hmc_run(
-            self.h, int(sampler), Cn, ids.ctypes.data_as(_llp), _p(b), float(dt), int(Lrange[0]),
+            self.h, int(sampler), int(which), Cn, ids.ctypes.data_as(_llp), _p(b), float(dt), int(Lrange[0]),
             int(Lrange[1]), int(L0), float(target_ratio), int(seed), int(nsamples), int(ndraws),
             int(max_iters), _p(out["samples"]), _p(out["misfit"]), _p(out["syn"]), _p(out["initmodel"]),
             out["n_iter"].ctypes.data_as(_llp), out["n_acc"].ctypes.data_as(_llp), _p(out["dt"]),

@@ -41,6 +41,7 @@ struct rfs_ctx {
   // ---- SWD configuration
   bool has_swd = false;
   int n_swd = 0, mode = 0, stale = 1, sphere = 0;
+  std::vector<int> modes;  // modes of the fused SWD objective (reference: one mode)
   SwdPlan plan;
   std::vector<double> periods;
   Buf d_periods;
@@ -48,6 +49,7 @@ struct rfs_ctx {
   bool has_rf = false;
   int n_rf = 0, nt = 0, nft = 0, logn = 0, n2 = 0, rf_type = 1, method = 1;
   double ray_p = 0, dt = 0, gauss = 0, tshift = 0, water = 0.001;
+  std::vector<double> ray_ps;  // ray parameters of the fused RF objective (reference: one)
   // ---- observations
   bool has_obs = false;
   double sigma1 = 1.0, sigma2 = 1.0;
@@ -398,7 +400,7 @@ int decon_threads(int nft) { return std::max(64, std::min(512, nft / 2)); }
 
 int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, double *d_rf,
                  long long ldrf, double *d_U, double *d_grad, double sigma, double tshift,
-                 cudaStream_t st) {
+                 cudaStream_t st, int accumulate = 0) {
   const size_t sm = decon_smem(ctx->nft, ctx->n2);
   if (sm > 48 * 1024) {
     CK(cudaFuncSetAttribute(rf_decon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -408,7 +410,7 @@ int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, doub
   LAUNCH(rf_decon_kernel, (unsigned)B, decon_threads(ctx->nft), sm, st,
          (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt,
          ctx->nft, ctx->logn, ctx->dt, ctx->gauss, tshift, ctx->water, sigma, d_dobs, d_rf, ldrf,
-         d_U, d_grad, (const double2 *)ctx->d_tw.p);
+         d_U, d_grad, (const double2 *)ctx->d_tw.p, accumulate);
   return RFS_OK;
 }
 
@@ -481,8 +483,9 @@ size_t per_model_bytes(const rfs_ctx *ctx, int which) {
   size_t s = 0;
   if (which != 1 && ctx->has_swd) {
     const SwdPlan &P = ctx->plan;
-    s += sizeof(double) * ((size_t)SWD_NF * ctx->n_swd + 3 * (size_t)P.nsolve +
-                           (size_t)P.nsolve * 4 * ctx->n_swd) + sizeof(int) * P.nseq;
+    const size_t nmo = ctx->modes.size() > 1 ? (size_t)P.nmode : 1;
+    s += sizeof(double) * ((size_t)SWD_NF * ctx->n_swd + (1 + 2 * nmo) * (size_t)P.nsolve +
+                           nmo * (size_t)P.nsolve * 4 * ctx->n_swd) + sizeof(int) * P.nseq;
   }
   if (which != 2 && ctx->has_rf) {
     s += sizeof(double) * (6 * (size_t)ctx->n_rf) + sizeof(RfLayer) * (size_t)ctx->n_rf +
@@ -558,13 +561,19 @@ void rfs_destroy(rfs_ctx *ctx) {
 const char *rfs_last_error(rfs_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 long long rfs_launch_count(rfs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int ntRg,
-                   const double *tRg, int ntLc, const double *tLc, int ntLg, const double *tLg,
-                   int mode, int sphere, int stale) {
+int rfs_config_swd_modes(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int ntRg,
+                         const double *tRg, int ntLc, const double *tLc, int ntLg, const double *tLg,
+                         int nmodes, const int *modes, int sphere, int stale) {
   if (!ctx) return RFS_E_ARG;
   CK(cudaSetDevice(ctx->device));
   if (nlayer < 2 || nmax_for(nlayer) < 0) return fail(ctx, RFS_E_ARG, "bad layer count");
-  if (mode < 0 || mode > 16) return fail(ctx, RFS_E_ARG, "bad mode");
+  if (nmodes < 1 || nmodes > RFS_MAX_MODES || !modes) return fail(ctx, RFS_E_ARG, "bad mode list");
+  int mode = 0;
+  for (int i = 0; i < nmodes; i++) {
+    if (modes[i] < 0 || modes[i] > 16) return fail(ctx, RFS_E_ARG, "bad mode");
+    if (i > 0 && modes[i] <= modes[i - 1]) return fail(ctx, RFS_E_ARG, "modes must be ascending");
+    mode = std::max(mode, modes[i]);
+  }
   const int nts[4] = {ntRc, ntRg, ntLc, ntLg};
   const double *ts[4] = {tRc, tRg, tLc, tLg};
   int rc = build_plan(ctx, ctx->plan, ctx->periods, nts, ts, mode, true);
@@ -575,19 +584,35 @@ int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int nt
                 cudaMemcpyHostToDevice));
   ctx->n_swd = nlayer;
   ctx->mode = mode;
+  ctx->modes.assign(modes, modes + nmodes);
   ctx->stale = stale ? 1 : 0;
   ctx->sphere = sphere ? 1 : 0;
   ctx->has_swd = true;
   return RFS_OK;
 }
 
-int rfs_config_rf(rfs_ctx *ctx, int nlayer, double ray_p, int nt, double dt, double gauss,
-                  double time_shift, double water, int rf_type, int method) {
+int rfs_config_swd(rfs_ctx *ctx, int nlayer, int ntRc, const double *tRc, int ntRg,
+                   const double *tRg, int ntLc, const double *tLc, int ntLg, const double *tLg,
+                   int mode, int sphere, int stale) {
+  return rfs_config_swd_modes(ctx, nlayer, ntRc, tRc, ntRg, tRg, ntLc, tLc, ntLg, tLg, 1, &mode,
+                              sphere, stale);
+}
+
+int rfs_config_rf_rays(rfs_ctx *ctx, int nlayer, int nray, const double *ray_p, int nt, double dt,
+                       double gauss, double time_shift, double water, int rf_type, int method) {
   if (!ctx) return RFS_E_ARG;
-  int rc = set_rf_cfg(ctx, nlayer, ray_p, nt, dt, gauss, time_shift, water, rf_type, method);
+  if (nray < 1 || nray > 64 || !ray_p) return fail(ctx, RFS_E_ARG, "bad ray-parameter list");
+  int rc = set_rf_cfg(ctx, nlayer, ray_p[0], nt, dt, gauss, time_shift, water, rf_type, method);
   if (rc) return rc;
+  ctx->ray_ps.assign(ray_p, ray_p + nray);
   ctx->has_rf = true;
   return RFS_OK;
+}
+
+int rfs_config_rf(rfs_ctx *ctx, int nlayer, double ray_p, int nt, double dt, double gauss,
+                  double time_shift, double water, int rf_type, int method) {
+  return rfs_config_rf_rays(ctx, nlayer, 1, &ray_p, nt, dt, gauss, time_shift, water, rf_type,
+                            method);
 }
 
 int rfs_config_obs(rfs_ctx *ctx, double sigma1, double sigma2, const double *dobs, int ndobs) {
@@ -614,7 +639,9 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   if (use_swd && use_rf && ctx->n_swd != ctx->n_rf)
     return fail(ctx, RFS_E_CONFIG, "SWD and RF layer counts differ");
   const int n = use_swd ? ctx->n_swd : ctx->n_rf;
-  const int n1 = use_rf ? ctx->nt : 0, nsw = use_swd ? ctx->plan.ndata : 0;
+  const int nray = use_rf ? (int)ctx->ray_ps.size() : 0;
+  const int nmsel = use_swd ? (int)ctx->modes.size() : 0;
+  const int n1 = use_rf ? ctx->nt * nray : 0, nsw = use_swd ? ctx->plan.ndata * nmsel : 0;
   const int ndata = n1 + nsw;
   if ((int)ctx->dobs.size() != ndata) return fail(ctx, RFS_E_CONFIG, "dobs length != ndata");
   CK(cudaSetDevice(ctx->device));
@@ -629,6 +656,14 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   const double sigma = rf_time ? 0.0 : 1.0 / ctx->dt / ctx->nft * 4.;
   const double q = ctx->sigma1 / ctx->sigma2;
   const double wt = (which == 0) ? q * q * n1 / nsw : 1.0;
+  // several modes in one objective: solve all modes 0..max in one chained pass and pick the listed ones
+  const bool multi_mode = use_swd && nmsel > 1;
+  ModeSel msel;
+  msel.n = use_swd ? nmsel : 1;
+  for (int i = 0; i < RFS_MAX_MODES; i++) msel.m[i] = 0;
+  if (multi_mode)
+    for (int i = 0; i < nmsel; i++) msel.m[i] = ctx->modes[i];
+  const double ray_p_saved = ctx->ray_p;
   for (long long off = 0; off < B; off += Bmax) {
     const long long Bc = std::min(Bmax, B - off);
     int rc;
@@ -648,32 +683,48 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(sr, ctx->ev_fork, 0));
       }
-      if ((rc = run_rf_spectra(ctx, (const double *)ctx->w_rfm.p, (const double *)ctx->w_chain.p,
-                               nullptr, nullptr, Bc, n, rf_time ? 4 : 2, sigma, sr,
-                               rf_time ? RFS_PI64 : RFS_PI32)))
-        return rc;
       if ((rc = ensure(ctx, ctx->w_urf, sizeof(double) * Bc))) return rc;
       if ((rc = ensure(ctx, ctx->w_grf, sizeof(double) * 2 * nB))) return rc;
       double *Uo = (which == 1) ? U + off : (double *)ctx->w_urf.p;
       double *go = (which == 1) ? grad + off * 2 * n : (double *)ctx->w_grf.p;
-      if (!rf_time) {
-        if ((rc = run_rf_decon(ctx, Bc, 2 * n, d_dobs, dsyn + off * ndata, ndata, Uo, go, sigma,
-                               tshift, sr)))
+      // one pass per ray parameter; misfit and gradient accumulate over the passes (the reference's
+      // ReceiverFunc has one ray parameter, model/model_rf.py:5-18; the list is BASELINE config 3)
+      for (int ir = 0; ir < nray; ir++) {
+        ctx->ray_p = ctx->ray_ps[ir];
+        rc = run_rf_spectra(ctx, (const double *)ctx->w_rfm.p, (const double *)ctx->w_chain.p, nullptr,
+                            nullptr, Bc, n, rf_time ? 4 : 2, sigma, sr, rf_time ? RFS_PI64 : RFS_PI32);
+        double *dsyn_r = dsyn + off * ndata + (size_t)ir * ctx->nt;
+        const double *dobs_r = d_dobs + (size_t)ir * ctx->nt;
+        if (!rc) {
+          if (!rf_time) {
+            rc = run_rf_decon(ctx, Bc, 2 * n, dobs_r, dsyn_r, ndata, Uo, go, sigma, tshift, sr, ir > 0);
+          } else {
+            // deconit is nonlinear (argmax spike picking): no adjoint shortcut, materialise the traces
+            rc = run_rf_time(ctx, Bc, 4 * n, dsyn_r, ndata, tshift, sr);
+            if (!rc) {
+              prof_begin(ctx, "rf_trace_grad_kernel", sr);
+              rf_trace_grad_kernel<<<gridFor(Bc * n, 128), 128, 0, sr>>>(
+                  (const double *)ctx->w_rftr.p, (const double *)ctx->w_chain.p,
+                  (const double *)dsyn_r, (long long)ndata, dobs_r, Bc, n, ctx->nt, Uo, go, ir > 0);
+              ctx->launches++;
+              prof_end(ctx, sr);
+              if (cudaGetLastError() != cudaSuccess) rc = fail(ctx, RFS_E_CUDA, "rf_trace_grad_kernel launch");
+            }
+          }
+        }
+        if (rc) {
+          ctx->ray_p = ray_p_saved;
           return rc;
-      } else {
-        // deconit is nonlinear (argmax spike picking): no adjoint shortcut, materialise the traces
-        if ((rc = run_rf_time(ctx, Bc, 4 * n, dsyn + off * ndata, ndata, tshift, sr))) return rc;
-        LAUNCH(rf_trace_grad_kernel, gridFor(Bc * n, 128), 128, 0, sr, (const double *)ctx->w_rftr.p,
-               (const double *)ctx->w_chain.p, (const double *)(dsyn + off * ndata), (long long)ndata,
-               d_dobs, Bc, n, ctx->nt, Uo, go);
+        }
       }
+      ctx->ray_p = ray_p_saved;
       if (which == 1) CK(cudaMemsetAsync(flag + off, 1, Bc, sr));
       if (sr != st) CK(cudaEventRecord(ctx->ev_join, sr));
     }
     if (use_swd) {
       SwdBlocks blk;
       if ((rc = make_blocks(ctx, (const double *)ctx->w_swd.p, Bc, n, ctx->sphere, blk, st))) return rc;
-      if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p, blk, Bc, n, false, true, st)))
+      if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p, blk, Bc, n, multi_mode, true, st)))
         return rc;
       SwdView V;
       V.blk = blk;
@@ -688,7 +739,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       LAUNCH(joint_assemble_kernel, gridFor(Bc * n, 128), 128, 0, st, ctx->plan, V,
              (const int *)ctx->w_ierr.p, (const double *)ctx->w_chain.p, ctx->stale, which, n1,
              d_dobs, (const double *)ctx->w_urf.p, (const double *)ctx->w_grf.p, wt, U + off,
-             grad + off * 2 * n, dsyn + off * ndata, flag + off);
+             grad + off * 2 * n, dsyn + off * ndata, flag + off, msel);
     }
   }
   return RFS_OK;
@@ -703,7 +754,8 @@ int rfs_misfit_grad_host(rfs_ctx *ctx, long long B, const double *x, int which, 
   if ((use_swd && !ctx->has_swd) || (use_rf && !ctx->has_rf))
     return fail(ctx, RFS_E_CONFIG, "context not configured (rfs_config_swd/rf/obs)");
   const int n = use_swd ? ctx->n_swd : ctx->n_rf;
-  const int ndata = (use_rf ? ctx->nt : 0) + (use_swd ? ctx->plan.ndata : 0);
+  const int ndata = (use_rf ? ctx->nt * (int)ctx->ray_ps.size() : 0) +
+                    (use_swd ? ctx->plan.ndata * (int)ctx->modes.size() : 0);
   CK(cudaSetDevice(ctx->device));
   int rc;
   if ((rc = ensure(ctx, ctx->io_x, sizeof(double) * B * 2 * n))) return rc;

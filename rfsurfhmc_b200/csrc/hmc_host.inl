@@ -55,7 +55,7 @@ extern "C" {
 
 long long rfs_hmc_last_evals(rfs_ctx *ctx) { return ctx ? ctx->hmc_evals : 0; }
 
-int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_id,
+int rfs_hmc_run(rfs_ctx *ctx, int sampler, int which, long long C, const long long *chain_id,
                 const double *bounds, double dt, int Lmin, int Lmax, int L0, double target_ratio,
                 long long seed, int nsamples, int ndraws, long long max_iters, double *samples,
                 double *misfit, double *syn, double *initmodel, long long *n_iter,
@@ -65,12 +65,22 @@ int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_i
   if (sampler != 0 && sampler != 1) return fail(ctx, RFS_E_ARG, "sampler must be 0 or 1");
   if (C <= 0 || !chain_id || !bounds || nsamples <= 0 || ndraws < 0)
     return fail(ctx, RFS_E_ARG, "bad HMC arguments");
-  if (!ctx->has_swd || !ctx->has_rf || !ctx->has_obs)
-    return fail(ctx, RFS_E_CONFIG, "joint model not configured (rfs_config_swd/rf/obs)");
+  if (which < 0 || which > 2) return fail(ctx, RFS_E_ARG, "which must be 0,1,2");
+  const bool use_swd = which != 1, use_rf = which != 2;
+  if ((use_swd && !ctx->has_swd) || (use_rf && !ctx->has_rf) || !ctx->has_obs)
+    return fail(ctx, RFS_E_CONFIG, "objective not configured (rfs_config_swd/rf/obs)");
+  if (use_swd && use_rf && ctx->n_swd != ctx->n_rf)
+    return fail(ctx, RFS_E_CONFIG, "SWD and RF layer counts differ");
+  // NumPy's RandomState.seed raises for seeds outside [0, 2**32-1]; chain i is seeded seed + id_i
+  for (long long c = 0; c < C; c++)
+    if (chain_id[c] < 0 || seed < 0 || seed + chain_id[c] > 0xffffffffLL)
+      return fail(ctx, RFS_E_ARG, "Seed must be between 0 and 2**32 - 1");
   if (sampler == 0 && (Lmin < 1 || Lmax < Lmin)) return fail(ctx, RFS_E_ARG, "bad Lrange");
-  if (seed + 0 < 0) return fail(ctx, RFS_E_ARG, "Seed must be between 0 and 2**32 - 1");
   CK(cudaSetDevice(ctx->device));
-  const int n = ctx->n_swd, n2 = 2 * n, nd = ctx->nt + ctx->plan.ndata;
+  const int n = use_swd ? ctx->n_swd : ctx->n_rf, n2 = 2 * n;
+  const int nd = (use_rf ? ctx->nt * (int)ctx->ray_ps.size() : 0) +
+                 (use_swd ? ctx->plan.ndata * (int)ctx->modes.size() : 0);
+  if ((int)ctx->dobs.size() != nd) return fail(ctx, RFS_E_CONFIG, "dobs length != ndata");
   cudaStream_t st = ctx->stream;
   HmcCfg cfg;
   cfg.n2 = n2;
@@ -141,7 +151,7 @@ int rfs_hmc_run(rfs_ctx *ctx, int sampler, long long C, const long long *chain_i
   while (h_active > 0) {
     for (int s = 0; s < check_every; s++) {
       if (packed) LAUNCH(hmc_gather_kernel, gridFor(Ba * n2, 256), 256, 0, st, D, n2, Ba);
-      rc = rfs_misfit_grad_dev(ctx, Ba, packed ? D.xg : D.xeval, 0, (double *)ctx->io_U.p,
+      rc = rfs_misfit_grad_dev(ctx, Ba, packed ? D.xg : D.xeval, which, (double *)ctx->io_U.p,
                                (double *)ctx->io_grad.p, (double *)ctx->io_dsyn.p,
                                (unsigned char *)ctx->io_flag.p, st);
       if (rc) return rc;

@@ -12,6 +12,14 @@
 
 namespace rfs {
 
+// modes of one SWD objective (extension of the reference's single `mode`: BASELINE config 2 asks for
+// modes 0-2 in one objective).  n == 1 with the mode arrays already offset: the reference's case.
+#define RFS_MAX_MODES 8
+struct ModeSel {
+  int n;                 // modes in the data vector
+  int m[RFS_MAX_MODES];  // their indices into the [mode][...] result arrays
+};
+
 // which: 0 joint, 1 RF only, 2 SWD only
 // One thread per (model, layer).  Layout of outputs (row-major per model, as the Python API):
 //   U[B], grad[B][2n] (vs then thk), dsyn[B][ndata] with ndata = nt_rf + nsw (joint),
@@ -22,7 +30,8 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
                                       const double *__restrict__ U_rf,
                                       const double *__restrict__ g_rf, double wt,
                                       double *__restrict__ U, double *__restrict__ grad,
-                                      double *__restrict__ dsyn, unsigned char *__restrict__ flag) {
+                                      double *__restrict__ dsyn, unsigned char *__restrict__ flag,
+                                      ModeSel ms) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long B = V.B;
   const int n = V.n;
@@ -30,7 +39,7 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
   const long long b = i % B;
   const int m = (int)(i / B);
   const long long nB = (long long)n * B;
-  const int nsw = (which == 1) ? 0 : plan.ndata;
+  const int nsw = (which == 1) ? 0 : plan.ndata * ms.n;
   const int n1 = (which == 2) ? 0 : nt_rf;
   const int ndata = n1 + nsw;
   bool ok = true;
@@ -39,19 +48,28 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
   double gv = 0.0, gh = 0.0, us = 0.0;
   if (which != 1 && ok) {
     const double dadb = chain[0 * nB + m * B + b], drda = chain[1 * nB + m * B + b];
-    for (int r = 0; r < plan.nrow; r++) {
-      const SwdRow rw = plan.row[r];
-      for (int k = 0; k < rw.nper; k++) {
-        const double d = swd_row_value(plan, V, rw, k, b);
-        const double res = d - dobs[n1 + rw.d_off + k];
-        double K[4];
-        swd_row_kernels(plan, V, rw, k, m, b, stale, K);
-        const double kv = K[1] + K[0] * dadb + K[2] * drda * dadb;
-        gv += res * kv;
-        gh += res * K[3];
-        if (m == 0) {
-          us += res * res;
-          dsyn[b * ndata + n1 + rw.d_off + k] = d;
+    for (int im = 0; im < ms.n; im++) {
+      // view of mode ms.m[im]: results are laid out [mode][solve]...
+      SwdView Vm = V;
+      const long long mo = ms.m[im];
+      Vm.croot = V.croot + mo * plan.nsolve * B;
+      Vm.ugr = V.ugr + mo * plan.nsolve * B;
+      Vm.kern = V.kern + mo * plan.nsolve * 4 * nB;
+      const int doff = n1 + im * plan.ndata;
+      for (int r = 0; r < plan.nrow; r++) {
+        const SwdRow rw = plan.row[r];
+        for (int k = 0; k < rw.nper; k++) {
+          const double d = swd_row_value(plan, Vm, rw, k, b);
+          const double res = d - dobs[doff + rw.d_off + k];
+          double K[4];
+          swd_row_kernels(plan, Vm, rw, k, m, b, stale, K);
+          const double kv = K[1] + K[0] * dadb + K[2] * drda * dadb;
+          gv += res * kv;
+          gh += res * K[3];
+          if (m == 0) {
+            us += res * res;
+            dsyn[b * ndata + doff + rw.d_off + k] = d;
+          }
         }
       }
     }

@@ -501,7 +501,9 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
                                 double f0, double t0, double water, double sigma,
                                 const double *__restrict__ dobs, double *__restrict__ rf,
                                 long long ldrf, double *__restrict__ U,
-                                double *__restrict__ grad, const double2 *__restrict__ tw) {
+                                double *__restrict__ grad, const double2 *__restrict__ tw,
+                                int accumulate) {
+  // accumulate != 0: U and grad are added to (second and later ray parameters of one objective)
   extern __shared__ double smem[];
   const int n2 = nft / 2 + 1;
   cd *buf = reinterpret_cast<cd *>(smem);
@@ -555,7 +557,7 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
   }
   if (dobs == nullptr) return;
   const double ss = block_reduce(lsum, red, false);
-  if (tid == 0) U[b] = 0.5 * ss;
+  if (tid == 0) U[b] = accumulate ? U[b] + 0.5 * ss : 0.5 * ss;
   if (grad == nullptr) return;
   __syncthreads();
   block_fft(buf, nft, logn, -1, tw);
@@ -590,7 +592,7 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
       acc += wt[k].x * d.x - wt[k].y * d.y;
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) grad[b * nrow + rr] = acc;
+    if (lane == 0) grad[b * nrow + rr] = accumulate ? grad[b * nrow + rr] + acc : acc;
   }
 }
 

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
 __global__ void rf_trace_grad_kernel(const double *__restrict__ traces, const double *__restrict__ chain,
                                      const double *__restrict__ rf, long long ldrf,
                                      const double *__restrict__ dobs, long long B, int n, int nt,
-                                     double *__restrict__ U, double *__restrict__ grad) {
+                                     double *__restrict__ U, double *__restrict__ grad,
+                                     int accumulate) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= B * n) return;
   const long long b = i % B;
@@ -199,9 +200,13 @@ __global__ void rf_trace_grad_kernel(const double *__restrict__ traces, const do
     g1 += kh[t] * res;
     us += res * res;
   }
+  if (accumulate) {
+    g0 += grad[b * 2 * n + m];
+    g1 += grad[b * 2 * n + n + m];
+  }
   grad[b * 2 * n + m] = g0;
   grad[b * 2 * n + n + m] = g1;
-  if (m == 0) U[b] = 0.5 * us;
+  if (m == 0) U[b] = accumulate ? U[b] + 0.5 * us : 0.5 * us;
 }
 
 }  // namespace rfs

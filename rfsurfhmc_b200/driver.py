@@ -57,16 +57,26 @@ def run(param, sampler="base", nchains=4, save_chains=True, max_iters=0, max_L=0
     if sampler == "da":
         chain.max_L = int(max_L)      # 0 = the reference's uncapped L = int(lambda/dt)
     ids = D.shard_chains(nchains)
+    if nchains < ws:
+        raise ValueError("need at least one chain per rank (chains %d < world size %d)" % (nchains, ws))
     if save_chains:
-        # per-chain files need every accepted sample's synthetics on the host: [chains, nsamples, ndata]
-        need = len(ids) * float(param['hmc']['nsamples']) * model.ndata * 8
+        # per-chain files need every accepted sample's synthetics on the host: [chains, nsamples, ndata];
+        # the decision is collective (max over ranks) so that no rank leaves the others in a gather
+        need = D.max_over_ranks(len(ids) * float(param['hmc']['nsamples']) * model.ndata * 8)
         if need > 8e9:
             raise MemoryError("per-chain result files for %d chains need %.1f GB of synthetics per rank; "
                               "run with --no-chain-files (misfit.npy is still written)" % (len(ids), need / 1e9))
     out = chain.sample_chains(ids, want_syn=save_chains, save=save_chains)
+    # end-of-run gathers (replace comm.Gather at main_base.py:90): misfit history + per-chain counters
+    t0 = time.perf_counter()
     misfit = D.gather_chains(out["misfit"], nchains)
     n_iter = D.gather_chains(out["n_iter"], nchains)
+    n_acc = D.gather_chains(out["n_acc"], nchains)
+    complete = D.gather_chains(out["complete"].astype(np.int64), nchains).astype(bool)
+    out["gather_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["n_acc_all"], out["complete_all"] = n_acc, complete
     if rank == 0:
+        # rows an incomplete chain never filled are NaN (never 0.0: argsort would pick them as "best")
         np.save(f"{outdir}/misfit.npy", misfit)
     return misfit, n_iter, out
 
@@ -91,10 +101,16 @@ def main():
         if val is not None:
             param['hmc'][key] = val
     tic = time.time()
-    misfit, n_iter, _ = run(param, a.sampler, a.chains, not a.no_chain_files, a.max_iters, a.max_L)
+    misfit, n_iter, out = run(param, a.sampler, a.chains, not a.no_chain_files, a.max_iters, a.max_L)
     if int(os.environ.get("RANK", "0")) == 0:
-        print("chains %d, accepted samples %d, mean accept ratio %.3f" %
-              (misfit.shape[0], misfit.size, (misfit.shape[1] + param['hmc']['ndraws']) / n_iter.mean()))
+        comp = out["complete_all"]
+        print("chains %d (%d complete), kept samples %d, accept ratio %.3f" %
+              (misfit.shape[0], int(comp.sum()), int(np.isfinite(misfit).sum()),
+               out["n_acc_all"].sum() / max(1, n_iter.sum())))
+        if not comp.all():
+            print("WARNING: %d chain(s) stopped early (max-iters or a failing state): their unfilled rows "
+                  "in misfit.npy are NaN and their chain files are flagged complete=False"
+                  % int((~comp).sum()))
         print("time elapse: {}".format(time.time() - tic))
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():

@@ -16,8 +16,9 @@ class Joint_RF_SWD:
         self.rfmodel = rfmodel
         self.swdmodel = swdmodel
         self.ndata = rfmodel.nt + swdmodel.nt
+        self.which = 0
         self._ctx = None
-        self._ctx_n = None
+        self._ctx_key = None
         self._device = 0
 
     def set_obsdata(self, rfobs: np.ndarray, swdobs: np.ndarray):
@@ -28,26 +29,32 @@ class Joint_RF_SWD:
         self.swdmodel.set_obsdata(swdobs)
         self.dobs[:self.rfmodel.nt] = self.rfobs * 1.
         self.dobs[self.rfmodel.nt:] = self.swdobs * 1.
-        self._ctx_n = None
 
     def set_device(self, device):
+        """GPU of this model and of its two sub-models."""
+        self.rfmodel.set_device(device)
+        self.swdmodel.set_device(device)
         if device != self._device:
             self._device = device
             self._ctx = None
-            self._ctx_n = None
+            self._ctx_key = None
 
     def device_context(self, n):
-        """Configured rfs context (joint model + observations) for n layers."""
+        """Configured rfs context (joint model + observations) for n layers.  The configuration is
+        re-pushed whenever a field the reference reads per call has changed (sigma1/2, every field of
+        the two sub-models, the observations): model_rf_swd_vs_thk.py:66-86."""
         if self._ctx is None:
             self._ctx = Context(self._device)
-        if self._ctx_n != n:
-            r, s = self.rfmodel, self.swdmodel
+        r, s = self.rfmodel, self.swdmodel
+        key = (self.sigma1, self.sigma2, r._config_fields(n), s._config_fields(n),
+               np.asarray(self.dobs, dtype=np.float64).tobytes())
+        if self._ctx_key != key:
             tRc, tRg, tLc, tLg = s._grad_periods()
             self._ctx.config_swd(n, tRc, tRg, tLc, tLg, mode=s.mode, sphere=s.sphere)
-            self._ctx.config_rf(n, r.ray_p, r.nt, r.dt, r.gauss, r.time_shift, r.water_level, r.rf_type,
-                                r.method)
+            self._ctx.config_rf(n, r.ray_p, r.nt_trace, r.dt, r.gauss, r.time_shift, r.water_level,
+                                r.rf_type, r.method)
             self._ctx.config_obs(self.dobs, self.sigma1, self.sigma2)
-            self._ctx_n = n
+            self._ctx_key = key
         return self._ctx
 
     def forward(self, x: np.ndarray):

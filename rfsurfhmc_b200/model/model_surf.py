@@ -5,7 +5,10 @@ Same constructor, `init(**kargs)`, `set_obsdata`, `set_thk`, `empirical_relation
 (rfs_misfit_grad_host, which=2) instead of per-wave-type pybind calls + NumPy glue; `forward`
 goes through the libsurf drop-in.  Reference quirks kept: Lc/Lg are evaluated on `tRc`
 (model_surf.py:200-201,211-212) and `forward` evaluates Rg/Lc/Lg on `tRc` (:114-130); on a failed
-root search the gradient has length n, not 2n (:179-180)."""
+root search the gradient has length n, not 2n (:179-180).
+
+Extension: `mode` may be an ascending list of modes; the data vector is then [mode][Rc,Rg,Lc,Lg]
+(`nt` counts all of them) and all modes come out of ONE chained root-search pass."""
 import numpy as np
 from .lib import libsurf
 from .._lib import Context
@@ -14,7 +17,10 @@ from .._lib import Context
 class SurfWD:
     def __init__(self, mode=0, sphere=False, tRc=None, tRg=None, tLc=None, tLg=None):
         self.mode = mode
+        self.nmode = int(np.size(mode))
         self.sphere = sphere
+        self.which = 2
+        self._device = 0
         self.tRc, self.tRg, self.tLc, self.tLg = None, None, None, None
         self.nt = 0
         self.ntRc, self.ntRg, self.ntLc, self.ntLg = 0, 0, 0, 0
@@ -34,8 +40,9 @@ class SurfWD:
             self.tLg = np.asarray(tLg)
             self.ntLg = len(tLg)
             self.nt += self.ntLg
+        self.nt *= self.nmode
         self._ctx = None
-        self._ctx_n = None
+        self._ctx_key = None
 
     @classmethod
     def init(self, **kargs):
@@ -43,7 +50,12 @@ class SurfWD:
 
     def set_obsdata(self, dobs):
         self.dobs = dobs
-        self._ctx_n = None
+
+    def set_device(self, device):
+        if device != self._device:
+            self._device = device
+            self._ctx = None
+            self._ctx_key = None
 
     def set_thk(self, thk):
         self.thk = thk * 1.0
@@ -69,15 +81,28 @@ class SurfWD:
                              "equal len(tRc) (model/model_surf.py:200-201,211-212)")
         return self.tRc, self.tRg, lc, lg
 
-    def _context(self, n):
+    def _config_fields(self, n):
+        # every field the reference reads on each misfit_and_grad call (model_surf.py:155-228)
+        per = tuple(None if t is None else np.asarray(t, dtype=np.float64).tobytes()
+                    for t in self._grad_periods())
+        return (n, tuple(np.atleast_1d(self.mode).tolist()), bool(self.sphere), per)
+
+    def _config_key(self, n):
+        return self._config_fields(n) + (np.asarray(self.dobs, dtype=np.float64).tobytes(),)
+
+    def device_context(self, n):
+        """Configured rfs context (SWD objective + observations) for n layers."""
         if self._ctx is None:
-            self._ctx = Context(0)
-        if self._ctx_n != n:
+            self._ctx = Context(self._device)
+        key = self._config_key(n)
+        if self._ctx_key != key:
             tRc, tRg, tLc, tLg = self._grad_periods()
             self._ctx.config_swd(n, tRc, tRg, tLc, tLg, mode=self.mode, sphere=self.sphere)
             self._ctx.config_obs(self.dobs)
-            self._ctx_n = n
+            self._ctx_key = key
         return self._ctx
+
+    _context = device_context
 
     def forward(self, x: np.ndarray):
         d = np.zeros((self.nt))
@@ -86,13 +111,14 @@ class SurfWD:
         thk = x[layers:]
         vp, rho = self.empirical_relation(vs)
         k1 = 0
-        for nt_w, wt in ((self.ntRc, "Rc"), (self.ntRg, "Rg"), (self.ntLc, "Lc"), (self.ntLg, "Lg")):
-            if nt_w > 0:
-                k2 = k1 + nt_w
-                d[k1:k2], flag = libsurf.forward(thk, vp, vs, rho, self.tRc, wt, self.mode, self.sphere)
-                if flag is False:
-                    return d, flag
-                k1 = k2
+        for mode in np.atleast_1d(self.mode):
+            for nt_w, wt in ((self.ntRc, "Rc"), (self.ntRg, "Rg"), (self.ntLc, "Lc"), (self.ntLg, "Lg")):
+                if nt_w > 0:
+                    k2 = k1 + nt_w
+                    d[k1:k2], flag = libsurf.forward(thk, vp, vs, rho, self.tRc, wt, int(mode), self.sphere)
+                    if flag is False:
+                        return d, flag
+                    k1 = k2
         return d, True
 
     def misfit(self, x):
@@ -104,7 +130,12 @@ class SurfWD:
     def misfit_and_grad(self, x):
         x = np.asarray(x, dtype=np.float64)
         n = int(x.shape[0] / 2)
-        U, g, d, f = self._context(n).misfit_grad_host(x[None, :], which=2)
+        U, g, d, f = self.device_context(n).misfit_grad_host(x[None, :], which=2)
         if not f[0]:
             return 0.0, np.zeros((n)), d[0], False
         return float(U[0]), g[0], d[0], True
+
+    def misfit_and_grad_batch(self, X):
+        """X [B, 2n] -> (U[B], grad[B,2n], dsyn[B,nt], flag[B]) in one fused GPU evaluation."""
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        return self.device_context(X.shape[1] // 2).misfit_grad_host(X, which=2)

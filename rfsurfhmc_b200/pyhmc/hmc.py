@@ -7,7 +7,7 @@ hmc_kernels.cuh; chain `myrank` is seeded with `seed + myrank` exactly like one 
 reference (hmc.py:43,61), so `sample()` reproduces that rank's accept/reject sequence, and
 `sample_chains(ids)` runs any number of ranks at once on one GPU."""
 import numpy as np
-from ._common import write_chain_file, best_mean_model, require_device_model
+from ._common import require_device_model, finish_run, save_chain
 
 
 class HamitonianMC:
@@ -41,19 +41,15 @@ class HamitonianMC:
         ctx = self.model.device_context(n)
         out = ctx.hmc_run(0, chain_ids, self.boundaries, self.dt, Lrange=self.Lrange, seed=self._base_seed,
                           nsamples=self.nsamples, ndraws=self.ndraws, max_iters=self.max_iters,
-                          want_samples=True, want_syn=want_syn, log_accepts=log_accepts)
+                          want_samples=True, want_syn=want_syn, log_accepts=log_accepts,
+                          which=self.model.which)
+        finish_run(out, self.nsamples, self.ndraws)
         if save:
             for i, cid in enumerate(np.atleast_1d(chain_ids)):
-                self._save(out, i, int(cid))
+                save_chain(f"{self.outdir}/{self.name}.{int(cid)}.npz", self.model, out, i, self.nbest_model,
+                           self.nsamples)
         self.last = out
         return out
-
-    def _save(self, out, i, cid):
-        xmean = best_mean_model(out["misfit"][i], out["samples"][i], self.nbest_model)
-        _, _, dsyn, _ = self.model.misfit_and_grad(xmean)
-        syn = out["syn"][i] if out["syn"] is not None else np.zeros((self.nsamples, 0))
-        write_chain_file(f"{self.outdir}/{self.name}.{cid}.npz", out["initmodel"][i], self.model.dobs,
-                         xmean, dsyn, out["samples"][i], syn)
 
     def sample(self):
         """One chain (this rank), as the reference: returns misfit[nsamples] and writes

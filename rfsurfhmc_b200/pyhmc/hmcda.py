@@ -3,7 +3,7 @@
 sampler (rfs_hmc_run, sampler=1): `_find_initial_dt`, L = max(1, int(lambda/dt)), always-drawn u and
 the Hoffman-Gelman dual-averaging recursion run per chain on the GPU (hmc_kernels.cuh)."""
 import numpy as np
-from ._common import write_chain_file, best_mean_model, require_device_model
+from ._common import require_device_model, finish_run, save_chain
 
 
 class HMCDualAveraging:
@@ -43,14 +43,12 @@ class HMCDualAveraging:
                           target_ratio=self.delta,
                           seed=self._base_seed, nsamples=self.nsamples, ndraws=self.ndraws,
                           max_iters=self.max_iters, want_samples=True, want_syn=want_syn,
-                          log_accepts=log_accepts)
+                          log_accepts=log_accepts, which=self.model.which)
+        finish_run(out, self.nsamples, self.ndraws)
         if save:
             for i, cid in enumerate(np.atleast_1d(chain_ids)):
-                xmean = best_mean_model(out["misfit"][i], out["samples"][i], 10)  # nbests hard-coded, hmcda.py:359
-                _, _, dsyn, _ = self.model.misfit_and_grad(xmean)
-                syn = out["syn"][i] if out["syn"] is not None else np.zeros((self.nsamples, 0))
-                write_chain_file(f"{self.outdir}/{self.name}.{int(cid)}.npz", out["initmodel"][i],
-                                 self.model.dobs, xmean, dsyn, out["samples"][i], syn)
+                # nbests hard-coded to 10 in the reference (hmcda.py:359)
+                save_chain(f"{self.outdir}/{self.name}.{int(cid)}.npz", self.model, out, i, 10, self.nsamples)
         self.last = out
         return out
 

@@ -174,10 +174,40 @@ def test_chain_result_file_and_best_mean_model(tmp_path):
     path = tmp_path / "sub" / "chain_x.0.npz"
     write_chain_file(str(path), samples[0], syn[0], xm, syn.mean(0), samples, syn)
     z = np.load(path)
-    assert sorted(z.files) == sorted(["initmodel", "obs", "mean/model", "mean/syn", "models", "syn"])
-    assert np.array_equal(z["models"], samples) and np.array_equal(z["mean/model"], xm)
+    assert sorted(z.files) == sorted(["initmodel", "obs", "mean/model", "mean/syn", "models", "syn", "complete"])
+    assert np.array_equal(z["models"], samples) and np.array_equal(z["mean/model"], xm) and bool(z["complete"])
     with pytest.raises(TypeError):
         require_device_model(object())
+
+
+def test_incomplete_chains_are_masked_and_flagged(tmp_path):
+    """A chain stopped by max_iters (or stuck at a failing state) leaves rows unfilled: they must not
+    look like zero-misfit samples (the 'best' ones for argsort), the accept ratio must count what was
+    run, and the chain file must say it is incomplete (driver.py)."""
+    import warnings
+    from rfsurfhmc_b200.pyhmc._common import finish_run, save_chain, best_mean_model
+    ns, nd, n2 = 5, 2, 4
+    out = {"misfit": np.array([[3., 2., 0., 0., 0.], [5., 4., 3., 2., 1.]]),
+           "samples": np.arange(2 * ns * n2, dtype=float).reshape(2, ns, n2), "syn": None,
+           "initmodel": np.zeros((2, n2)), "n_acc": np.array([4, 7]), "n_iter": np.array([9, 8]),
+           "warning": "1 chain(s) stuck"}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        finish_run(out, ns, nd)
+    assert len(w) == 2 and "stuck" in str(w[0].message)
+    assert out["n_valid"].tolist() == [2, 5] and out["complete"].tolist() == [False, True]
+    assert np.isnan(out["misfit"][0, 2:]).all() and np.isfinite(out["misfit"][1]).all()
+    xm = best_mean_model(out["misfit"][0], out["samples"][0], 3, out["n_valid"][0])
+    assert np.allclose(xm, out["samples"][0][:2].mean(axis=0))      # the zero rows are not 'best'
+
+    class M:
+        dobs = np.zeros(3)
+
+        def misfit_and_grad(self, x):
+            return 0.0, x, np.ones(3)
+    save_chain(str(tmp_path / "c.0.npz"), M(), out, 0, 3, ns)
+    z = np.load(tmp_path / "c.0.npz")
+    assert not bool(z["complete"]) and z["models"].shape == (2, n2)
 
 
 def _ref_python_golden():

@@ -1,0 +1,314 @@
+"""GPU parity at the sizes BASELINE.json names (VERDICT r1 "parity holes"): C2 (n=40, 60 periods,
+four wave types, modes 0-2), C3 (nt=2048, a=2.5, three ray parameters, freq + time), C5 (n=200,
+128 periods, nt=4096), finite Q, the dual-averaging sampler with the L cap the bench uses, and the
+objectives / samplers added in round 2 (mode lists, ray-parameter lists, RF-only and SWD-only
+samplers).  Tolerances: c, U <= 1e-6 relative; RF <= 1e-5 of the trace peak; gradients <= 1e-4
+relative to the largest component."""
+import os
+import numpy as np
+import pytest
+from oracle import hmc_ref
+from oracle.oracle import brocher
+from rfsurfhmc_b200.fixtures import f1_config, f1_true_model, driver_bounds, sorted_uniform_models
+
+pytestmark = pytest.mark.gpu
+TOL_C, TOL_RF, TOL_G = 1e-6, 1e-5, 1e-4
+NTH = os.cpu_count() or 8
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def layered(B, n, seed, thk0=None, jitter=0.04):
+    rng = np.random.default_rng(seed)
+    if thk0 is None:
+        thk0 = np.hstack((0.5 + 0.1 * np.arange(n - 1), [0.0]))
+    thk = thk0[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (B, n)))
+    thk[:, -1] = 0.0
+    vs0 = 2.0 + 2.7 * (np.arange(n) / (n - 1.0))**0.7
+    vs = np.clip(vs0[None, :] * (1 + jitter * rng.standard_normal((B, n))), 1.5, 5.0)
+    return np.hstack((vs, thk))
+
+
+def grad_err(g1, g0):
+    return np.max(np.abs(g1 - g0), axis=1) / np.max(np.abs(g0), axis=1)
+
+
+def test_c2_swd_sizes_modes_0_to_2(ctx, oracle):
+    """C2: n=40, 60 periods geomspace(2,100), Rc+Rg+Lc+Lg, modes 0,1,2, B=2048 against the oracle
+    (surfdisp96.f:317,356-362 decide where a higher mode is cut off: same zero pattern required)."""
+    n, B = 40, 2048
+    X = layered(B, n, 21)
+    T = np.geomspace(2, 100, 60)
+    base = dict(f1_config(), tRc=T, tRg=T, tLc=T, tLg=T)
+    dobs = np.full(240, 3.2)
+    per_mode = []
+    for mode in (0, 1, 2):
+        ctx.config_swd(n, T, T, T, T, mode=mode)
+        ctx.config_obs(dobs)
+        Ub, gb, db, fb = ctx.misfit_grad_host(X, which=2)
+        Ua, ga, da, fa = oracle.joint_batch(X, dobs, dict(base, mode=mode), which=2, nthreads=NTH)
+        per_mode.append((Ua, ga, da, fa))
+        assert np.array_equal(fa, fb), mode
+        ok = np.isfinite(da) & (da != 0)
+        assert np.array_equal(np.isfinite(db) & (db != 0), ok), mode   # same cut-off / missing-mode pattern
+        e = np.abs(db - da)[ok] / np.abs(da[ok])
+        assert np.mean(e <= TOL_C) >= 0.999 and e.max() <= 1e-3, (mode, e.max(), np.mean(e <= TOL_C))
+        fin = np.isfinite(ga).all(axis=1) & fa
+        assert np.array_equal(fin, np.isfinite(gb).all(axis=1) & fb), mode
+        if fin.any():
+            eg = grad_err(gb[fin], ga[fin])
+            assert np.mean(eg <= TOL_G) >= 0.99 and eg.max() <= 1e-2, (mode, eg.max())
+    # ---- the same three modes as ONE objective (mode list): data [mode][Rc,Rg,Lc,Lg], one root pass
+    ctx.config_swd(n, T, T, T, T, mode=[0, 1, 2])
+    dobs3 = np.full(720, 3.2)
+    ctx.config_obs(dobs3)
+    U3, g3, d3, f3 = ctx.misfit_grad_host(X, which=2)
+    assert d3.shape == (B, 720)
+    f_all = per_mode[0][3] & per_mode[1][3] & per_mode[2][3]
+    assert np.array_equal(f3, per_mode[0][3])      # the flag is the fundamental mode's (surfdisp.cpp:93-100)
+    for im in range(3):
+        da = per_mode[im][2]
+        ok = np.isfinite(da) & (da != 0) & f3[:, None] & per_mode[im][3][:, None]
+        blk = d3[:, 240 * im:240 * (im + 1)]
+        e = np.abs(blk - da)[ok] / np.abs(da[ok])
+        assert np.mean(e <= TOL_C) >= 0.999 and e.max() <= 1e-3, im
+    gsum = per_mode[0][1] + per_mode[1][1] + per_mode[2][1]
+    fin = np.isfinite(gsum).all(axis=1) & f_all
+    assert fin.sum() > 0
+    eg = grad_err(g3[fin], gsum[fin])
+    assert np.mean(eg <= TOL_G) >= 0.99 and eg.max() <= 1e-2
+    # ---- all_modes drop-in (libsurf.adjoint_kernel semantics per mode)
+    vs, thk = X[:64, :n], X[:64, n:]
+    vp, rho = brocher(vs)
+    c, da_, db_, dr_, dh_, ok = ctx.surf_adjoint_kernel(thk, vp, vs, rho, T, "Rc", mode=2, all_modes=True)
+    for b in range(0, 64, 16):
+        for mode in (0, 1, 2):
+            r0 = oracle.surf_adjoint_kernel(thk[b], vp[b], vs[b], rho[b], T, "Rc", mode=mode)
+            m = r0[0] > 0
+            assert np.array_equal(c[b, mode] > 0, m)
+            if m.any():
+                assert rel(c[b, mode][m], r0[0][m]) <= TOL_C
+                s = np.max(np.abs(r0[2][m]))
+                assert np.max(np.abs(db_[b, mode][m] - r0[2][m])) / s <= TOL_G
+
+
+def test_c3_rf_sizes_three_ray_parameters(ctx, oracle):
+    """C3: nt=2048 (-> 2048-point FFT), dt=0.05, Gaussian a=2.5, p in {0.04,0.06,0.08}: freq-domain
+    forward + Frechet (fused objective, per ray parameter and as one three-ray objective) and the
+    time-domain forward (RFModule.f90:368-381 spectral division, deconit.f90)."""
+    n, B, nt = 40, 16, 2048
+    X = layered(B, n, 22)
+    rays = (0.04, 0.06, 0.08)
+    base = dict(f1_config(), nt=nt, dt=0.05, gauss=2.5, time_shift=5.0, water=1e-3)
+    rngo = np.random.default_rng(1)
+    dobs = 0.02 * rngo.standard_normal(3 * nt)
+    Us, gs, ds = [], [], []
+    for i, p in enumerate(rays):
+        ctx.config_rf(n, p, nt, 0.05, 2.5, 5.0, 1e-3, "P", "freq")
+        ctx.config_obs(dobs[i * nt:(i + 1) * nt])
+        Ub, gb, db, fb = ctx.misfit_grad_host(X, which=1)
+        Ua, ga, da, fa = oracle.joint_batch(X, dobs[i * nt:(i + 1) * nt], dict(base, ray_p=p), which=1,
+                                            nthreads=NTH)
+        assert np.max(np.abs(db - da)) <= TOL_RF * np.max(np.abs(da)), p
+        assert rel(Ub, Ua) <= 1e-8 and grad_err(gb, ga).max() <= TOL_G, p
+        Us.append(Ua), gs.append(ga), ds.append(da)
+    # one objective over the three ray parameters
+    ctx.config_rf(n, list(rays), nt, 0.05, 2.5, 5.0, 1e-3, "P", "freq")
+    ctx.config_obs(dobs)
+    U3, g3, d3, f3 = ctx.misfit_grad_host(X, which=1)
+    assert d3.shape == (B, 3 * nt) and f3.all()
+    assert np.max(np.abs(d3 - np.hstack(ds))) <= TOL_RF * np.max(np.abs(np.hstack(ds)))
+    assert rel(U3, sum(Us)) <= 1e-8 and grad_err(g3, sum(gs)).max() <= TOL_G
+    # Frechet traces themselves (librf.kernel_all) and the time-domain forward at this size
+    vs, thk = X[:2, :n], X[:2, n:]
+    vp, rho = brocher(vs)
+    q = np.full_like(vs, 9999.)
+    kw = dict(ray_p=0.06, nt=nt, dt=0.05, gauss=2.5, time_shift=5.0, water=1e-3, rf_type="P")
+    rf1, k1 = ctx.rf_kernel_all(thk, rho, vp, vs, q, q, method="freq", **kw)
+    for b in range(2):
+        rf0, k0 = oracle.rf_kernel_all(thk[b], rho[b], vp[b], vs[b], q[b], q[b], method="freq", **kw)
+        assert np.max(np.abs(rf1[b] - rf0)) <= TOL_RF * np.max(np.abs(rf0))
+        for i in range(4):
+            assert np.max(np.abs(k1[b, i] - k0[i])) <= TOL_G * np.max(np.abs(k0[i])), i
+    vs, thk = X[:8, :n], X[:8, n:]
+    vp, rho = brocher(vs)
+    q = np.full_like(vs, 9999.)
+    for p in rays:
+        rft = ctx.rf_forward(thk, rho, vp, vs, q, q, p, nt, 0.05, 2.5, 5.0, method="time", rf_type="P")
+        for b in range(8):
+            r0 = oracle.rf_forward(thk[b], rho[b], vp[b], vs[b], q[b], q[b], p, nt, 0.05, 2.5, 5.0,
+                                   method="time", rf_type="P")
+            assert np.max(np.abs(rft[b] - r0)) <= TOL_RF * np.max(np.abs(r0)), (p, b)
+
+
+def test_c5_sizes_two_hundred_layers(ctx, oracle):
+    """C5: n=200, 128 Rc + 128 Rg periods, RF nt=4096 (-> 4096-point FFT), B=32.  The SWD objective
+    and the RF forward are compared with the oracle at full size; the RF gradient at nt=4096 is compared
+    with the oracle at n=40 (the reference's O(n^2) Frechet algorithm needs minutes per model at
+    n=200) and, at n=200, checked against central differences of the device misfit."""
+    n, B = 200, 32
+    X = layered(B, n, 23, thk0=np.hstack((np.full(n - 1, 0.4), [0.0])), jitter=0.02)
+    T = np.geomspace(1, 150, 128)
+    cfg = dict(f1_config(), tRc=T, tRg=T, nt=4096, dt=0.025, gauss=2.5, ray_p=0.06)
+    dsw = np.full(256, 3.3)
+    ctx.config_swd(n, T, T)
+    ctx.config_obs(dsw)
+    Ub, gb, db, fb = ctx.misfit_grad_host(X, which=2)
+    Ua, ga, da, fa = oracle.joint_batch(X, dsw, cfg, which=2, nthreads=NTH)
+    assert np.array_equal(fa, fb) and fa.all()
+    assert rel(db, da) <= TOL_C
+    fin = np.isfinite(ga).all(axis=1)          # nu_b = 0 after the float32 rounding: NaN in the oracle
+    assert fin.sum() >= B - 3 and np.isfinite(gb).all()
+    assert grad_err(gb[fin], ga[fin]).max() <= TOL_G
+    # RF forward at nt = 4096, n = 200
+    vs, thk = X[:, :n], X[:, n:]
+    vp, rho = brocher(vs)
+    q = np.full_like(vs, 9999.)
+    rf1 = ctx.rf_forward(thk, rho, vp, vs, q, q, 0.06, 4096, 0.025, 2.5, 5.0, method="freq", rf_type="P")
+    for b in range(0, B, 4):
+        r0 = oracle.rf_forward(thk[b], rho[b], vp[b], vs[b], q[b], q[b], 0.06, 4096, 0.025, 2.5, 5.0,
+                               method="freq", rf_type="P")
+        assert np.max(np.abs(rf1[b] - r0)) <= TOL_RF * np.max(np.abs(r0)), b
+    # RF objective at nt = 4096 against the oracle (n = 40)
+    X40 = layered(8, 40, 24)
+    dr = 0.02 * np.random.default_rng(2).standard_normal(4096)
+    ctx.config_rf(40, 0.06, 4096, 0.025, 2.5, 5.0, 1e-3, "P", "freq")
+    ctx.config_obs(dr)
+    U1, g1, d1, _ = ctx.misfit_grad_host(X40, which=1)
+    U0, g0, d0, _ = oracle.joint_batch(X40, dr, cfg, which=1, nthreads=NTH)
+    assert np.max(np.abs(d1 - d0)) <= TOL_RF * np.max(np.abs(d0))
+    assert rel(U1, U0) <= 1e-8 and grad_err(g1, g0).max() <= TOL_G
+    # joint objective at the full C5 size: gradient against central differences of the misfit
+    ctx.config_swd(n, T, T)
+    ctx.config_rf(n, 0.06, 4096, 0.025, 2.5, 5.0, 1e-3, "P", "freq")
+    dobs = np.hstack((dr, dsw))
+    ctx.config_obs(dobs)
+    x = X[:1]
+    U, g, d, f = ctx.misfit_grad_host(x)
+    assert f.all() and d.shape == (1, 4096 + 256) and np.isfinite(g).all()
+    idx = [3, 57, 120, 199, 200 + 10, 200 + 150]
+    P = np.repeat(x, 2 * len(idx), axis=0)
+    for j, i in enumerate(idx):
+        h = 1e-4 * max(abs(x[0, i]), 0.1)
+        P[2 * j, i] += h
+        P[2 * j + 1, i] -= h
+    Up = ctx.misfit_grad_host(P)[0]
+    for j, i in enumerate(idx):
+        h = 1e-4 * max(abs(x[0, i]), 0.1)
+        fd = (Up[2 * j] - Up[2 * j + 1]) / (2 * h)
+        # the SWD part of the misfit is a float32-rounded forward: finite differences carry ~1e-3 noise
+        assert abs(fd - g[0, i]) <= 2e-2 * np.max(np.abs(g[0])) + 1e-3 * abs(g[0, i]), (i, fd, g[0, i])
+
+
+def test_finite_q_attenuation(ctx, oracle):
+    """RFModule.f90:377-378: complex velocities from Qa, Qb.  Every other test runs Q = 9999."""
+    for n, nt, dt in ((7, 125, 0.4), (40, 512, 0.1)):
+        if n == 7:
+            x = f1_true_model()
+            vs, thk = x[:7][None, :], x[7:][None, :]
+        else:
+            X = layered(3, n, 25)
+            vs, thk = X[:, :n], X[:, n:]
+        vp, rho = brocher(vs)
+        qa, qb = np.full_like(vs, 200.), np.full_like(vs, 80.)
+        qb[:, ::3] = 40.
+        for rft in ("P", "S"):
+            kw = dict(ray_p=0.06, nt=nt, dt=dt, gauss=2.0, time_shift=5.0, water=1e-3, rf_type=rft)
+            rf1, k1 = ctx.rf_kernel_all(thk, rho, vp, vs, qa, qb, method="freq", **kw)
+            rfq, _ = ctx.rf_kernel_all(thk, rho, vp, vs, qa * 0 + 9999., qb * 0 + 9999., method="freq", **kw)
+            assert np.max(np.abs(rf1 - rfq)) > 1e-3 * np.max(np.abs(rfq))     # attenuation is really applied
+            for b in range(vs.shape[0]):
+                rf0, k0 = oracle.rf_kernel_all(thk[b], rho[b], vp[b], vs[b], qa[b], qb[b], method="freq", **kw)
+                assert np.max(np.abs(rf1[b] - rf0)) <= TOL_RF * np.max(np.abs(rf0)), (n, rft)
+                for i in range(4):
+                    assert np.max(np.abs(k1[b, i] - k0[i])) <= TOL_G * np.max(np.abs(k0[i])), (n, rft, i)
+            rt1 = ctx.rf_forward(thk, rho, vp, vs, qa, qb, method="time", **kw)
+            for b in range(vs.shape[0]):
+                rt0 = oracle.rf_forward(thk[b], rho[b], vp[b], vs[b], qa[b], qb[b], method="time", **kw)
+                assert np.max(np.abs(rt1[b] - rt0)) <= TOL_RF * np.max(np.abs(rt0)), (n, rft, "time")
+
+
+def _f1(ctx, dobs=None, which=0):
+    cfg = f1_config()
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if dobs is None:
+        dobs = np.load(os.path.join(ROOT, "tests", "golden", "f1_joint.npz"))["dobs"]
+    ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"])
+    ctx.config_rf(7, cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"],
+                  cfg["rf_type"], cfg["method"])
+    d = dobs if which == 0 else (dobs[:125] if which == 1 else dobs[125:])
+    ctx.config_obs(d)
+    return cfg, d, driver_bounds(f1_true_model())
+
+
+def test_dual_averaging_with_the_L_cap_of_the_bench(ctx, oracle):
+    """bench.py runs HMCDualAveraging with max_L = 40 (extension); accept sequences, step sizes and L
+    must match the restated reference sampler with the same cap."""
+    cfg, dobs, bounds = _f1(ctx)
+    ids = [1, 4, 9]
+    niter = 14
+    out = ctx.hmc_run(1, ids, bounds, 0.02, Lrange=(1, 40), L0=20, target_ratio=0.65, seed=991206,
+                      nsamples=20, ndraws=6, max_iters=niter, want_samples=True, log_accepts=niter)
+    f = hmc_ref.oracle_joint_f(oracle, dobs, cfg)
+    for i, cid in enumerate(ids):
+        R = hmc_ref.run_da(f, bounds, 0.02, 20, 0.65, 991206 + cid, nsamples=20, ndraws=6, max_iters=niter,
+                           max_L=40)
+        assert max(R.trace_L) <= 40
+        seq = out["accept_seq"][i][:out["n_iter"][i]]
+        assert list(seq) == R.accepts, (cid, list(seq), R.accepts)
+        assert np.isclose(out["dt"][i], R.dt, rtol=1e-6)
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_rf_only_and_swd_only_samplers(ctx, oracle, which):
+    """The reference samplers take any model with misfit_and_grad (pyhmc/hmc.py:113-119): SurfWD and
+    ReceiverFunc objectives sampled on the device, accept sequences against the restated sampler."""
+    cfg, dobs, bounds = _f1(ctx, which=which)
+    ids = [0, 2]
+    niter = 16
+    out = ctx.hmc_run(0, ids, bounds, 0.05, Lrange=(5, 12), seed=991206, nsamples=20, ndraws=3,
+                      max_iters=niter, want_samples=True, want_syn=True, log_accepts=niter, which=which)
+    assert out["syn"].shape[2] == dobs.size
+    f = hmc_ref.oracle_joint_f(oracle, dobs, cfg, which=which)
+    for i, cid in enumerate(ids):
+        R = hmc_ref.run_base(f, bounds, 0.05, (5, 12), 991206 + cid, nsamples=20, ndraws=3, max_iters=niter)
+        seq = out["accept_seq"][i][:out["n_iter"][i]]
+        assert list(seq) == R.accepts, (which, cid)
+        ns = max(0, R.n_acc - 3)
+        if ns > 0:
+            assert np.allclose(out["samples"][i][:ns], R.samples[:ns], rtol=1e-6, atol=1e-9)
+            assert np.allclose(out["misfit"][i][:ns], R.misfit[:ns], rtol=1e-4)
+
+
+def test_sampler_front_ends_accept_the_three_model_classes(ctx, tmp_path):
+    """HamitonianMC(model=SurfWD / ReceiverFunc / Joint_RF_SWD) as in the reference; a changed model
+    field re-configures the device context (stale configuration)."""
+    from rfsurfhmc_b200.model.model_rf import ReceiverFunc
+    from rfsurfhmc_b200.model.model_surf import SurfWD
+    from rfsurfhmc_b200.pyhmc.hmc import HamitonianMC
+    cfg = f1_config()
+    x0 = f1_true_model()
+    bounds = driver_bounds(x0)
+    swd = SurfWD(tRc=cfg["tRc"], tRg=cfg["tRg"])
+    d, ok = swd.forward(x0)
+    swd.set_obsdata(d * 1.01)
+    ch = HamitonianMC(swd, bounds, 0.05, (5, 8), 3, 991206, nsamples=4, ndraws=1, myrank=2, name="s",
+                      outdir=str(tmp_path))
+    ch.max_iters = 12
+    m = ch.sample()
+    assert m.shape == (4,) and os.path.exists(tmp_path / "s.2.npz")
+    U1 = swd.misfit_and_grad(x0 * 1.02)[0]
+    swd.mode = 1                                     # the reference reads self.mode on every call
+    U2 = swd.misfit_and_grad(x0 * 1.02)[0]
+    assert U1 != U2
+    rf = ReceiverFunc(cfg["ray_p"], cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], "P", "freq")
+    rf.set_obsdata(rf.forward(x0) * 1.01)
+    ch = HamitonianMC(rf, bounds, 0.05, (5, 8), 3, 991206, nsamples=4, ndraws=1, myrank=0, name="r",
+                      outdir=str(tmp_path))
+    ch.max_iters = 12
+    assert ch.sample().shape == (4,)
+    U1 = rf.misfit_and_grad(x0 * 1.02)[0]
+    rf.gauss = 2.5
+    assert rf.misfit_and_grad(x0 * 1.02)[0] != U1
