@@ -130,8 +130,15 @@ int rfs_hmc_run(rfs_ctx *ctx, int sampler, int which, long long C, const long lo
                 double *misfit, double *syn, double *initmodel, long long *n_iter,
                 long long *n_acc, double *dt_final, signed char *accept_seq,
                 long long max_iter_log);
-/* number of misfit_and_grad evaluations performed by the last rfs_hmc_run */
+/* number of misfit_and_grad evaluations / of global steps (one batched evaluation each) performed by
+ * the last rfs_hmc_run */
 long long rfs_hmc_last_evals(rfs_ctx *ctx);
+long long rfs_hmc_last_steps(rfs_ctx *ctx);
+/* Options of rfs_hmc_run (no reference counterpart).  resident_slots > 0: at most that many chains are
+ * resident on the device at a time; a finished chain hands its slot to the next queued chain on the
+ * device, so the evaluated batch stays full (results do not depend on it).  max_seconds > 0: stop the
+ * run after that wall-clock time; unfinished chains keep what they have (rfs_hmc_run returns 1). */
+int rfs_set_hmc_options(rfs_ctx *ctx, long long resident_slots, double max_seconds);
 
 /* ---- measurement helpers (no reference counterpart; used by bench.py) --------------------------
  * rfs_count_evals(ctx,1) zeroes and enables a device counter of secular-function evaluations

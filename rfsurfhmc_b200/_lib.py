@@ -86,6 +86,10 @@ def load_library():
                                   _llp, _llp, _dp, _i8p, C.c_longlong]
         L.rfs_hmc_last_evals.restype = C.c_longlong
         L.rfs_hmc_last_evals.argtypes = [_vp]
+        L.rfs_hmc_last_steps.restype = C.c_longlong
+        L.rfs_hmc_last_steps.argtypes = [_vp]
+        L.rfs_set_hmc_options.restype = C.c_int
+        L.rfs_set_hmc_options.argtypes = [_vp, C.c_longlong, C.c_double]
         L.rfs_count_evals.restype = C.c_int
         L.rfs_count_evals.argtypes = [_vp, C.c_int]
         L.rfs_read_evals.restype = C.c_longlong
@@ -117,7 +121,7 @@ def exported_symbols():
             "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
             "rfs_measure_fp64_peak", "rfs_read_eval_stats", "rfs_selftest_math",
             "rfs_set_roots_team", "rfs_last_roots_team", "rfs_profile_eval", "rfs_profile_kernel_name",
-            "rfs_config_swd_modes", "rfs_config_rf_rays"]
+            "rfs_config_swd_modes", "rfs_config_rf_rays", "rfs_hmc_last_steps", "rfs_set_hmc_options"]
 
 
 def _f64(a):
@@ -327,6 +331,11 @@ class Context:
         return rf, drf
 
     # ---- device-resident HMC
+    def set_hmc_options(self, resident=0, max_seconds=0.0):
+        """resident > 0: chains share that many device slots (finished chains hand their slot to queued
+        ones); max_seconds > 0: wall-clock budget of a run."""
+        self._ck(self.L.rfs_set_hmc_options(self.h, int(resident), float(max_seconds)))
+
     def hmc_run(self, sampler, chain_ids, bounds, dt, Lrange=(5, 20), L0=10, target_ratio=0.65,
                 seed=0, nsamples=800, ndraws=200, max_iters=0, want_samples=True, want_syn=False,
                 log_accepts=0, which=0):
@@ -356,6 +365,7 @@ class Context:
             out["accept_seq"].ctypes.data_as(_i8p) if log_accepts > 0 else None, int(log_accepts))
         self._ck(rc)
         out["evals"] = int(self.L.rfs_hmc_last_evals(self.h))
+        out["global_steps"] = int(self.L.rfs_hmc_last_steps(self.h))
         out["warning"] = self.last_error() if rc > 0 else ""
         return out
 

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -65,7 +66,9 @@ struct rfs_ctx {
       w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
   // ---- HMC
-  long long hmc_evals = 0;
+  long long hmc_evals = 0, hmc_steps = 0;
+  long long hmc_resident = 0;    // resident chain slots of rfs_hmc_run (0 = all chains at once)
+  double hmc_max_seconds = 0.0;  // wall-clock budget of rfs_hmc_run (0 = none)
   Buf h_state, h_misc, h_out;
   size_t ws_budget = (size_t)24 << 30;  // workspace budget per chunk (bytes)
   Buf d_counter;                 // [0] secular-function evaluations (algorithmic-work counter)

@@ -21,7 +21,8 @@ namespace rfs {
 
 enum { HP_INIT = 0, HP_FD = 1, HP_LEAP = 2, HP_DONE = 3 };
 // status: 0 running/finished normally, 2 max_iters reached, 3 current state cannot be evaluated
-// (the reference would loop forever), 4 failure inside _find_initial_dt (reference: exit(1))
+// (the reference would loop forever), 4 failure inside _find_initial_dt (reference: exit(1)),
+// 5 stopped by the wall-clock budget of rfs_set_hmc_options
 
 struct HmcCfg {
   int n2, ndata, sampler, Lmin, Lmax, L0, nsamples, ndraws;
@@ -29,12 +30,25 @@ struct HmcCfg {
   long long max_iters, max_log;
 };
 
+// Chains live in SLOTS: R <= C slots are resident on the device; when the chain of a slot finishes, the
+// slot is refilled with the next queued chain (device-side queue head), so the evaluated batch stays
+// full until the queue is empty.  Trajectory state is per slot, results are per chain.
 struct HmcDev {
-  // chain state
-  double *xcur, *xnew, *pnew, *gcur, *dcur;  // [C][n2] x4, [C][ndata]
+  // trajectory state, per slot
+  double *xcur, *xnew, *pnew, *gcur, *dcur;  // [R][n2] x4, [R][ndata]
   double *Ucur, *Hcur, *dt, *dtbar, *h0, *fdH;
-  int *phase, *istep, *L, *okcur, *fd_it, *fd_a, *status;
-  long long *iacc, *ncount, *nevals;
+  int *phase, *istep, *L, *okcur, *fd_it, *fd_a;
+  long long *iacc, *ncount;
+  // per chain results [C]
+  int *status;
+  long long *nevals, *o_iter, *o_acc;
+  double *o_dt;
+  // slot -> chain, queue of chains not started yet
+  int *chain;        // [R] chain index of the slot
+  int *queue_head;   // next chain index to start (device counter)
+  long long C_total; // number of chains
+  const long long *chain_id;  // [C] the reference's MPI rank of each chain (seed offset)
+  long long seed;
   // RNG (NumPy legacy MT19937), mt laid out [624][C]
   unsigned int *mt;
   int *mti, *has_gauss;
@@ -47,9 +61,9 @@ struct HmcDev {
   double *samples, *misfit, *syn, *initmodel;
   signed char *alog;
   const double *bounds;  // [n2][2]
-  int *n_active;         // [0] chains still running after the last advance, [1] compaction counter
-  // compaction of the evaluation batch once chains have finished: slot[c] = row of chain c in the
-  // evaluated batch (-1: finished), idx[j] = chain of row j, xg = gathered positions [Ba][n2]
+  int *n_active;         // [0] slots still running after the last advance, [1] compaction counter
+  // compaction of the evaluation batch once slots have run dry: slot[s] = row of slot s in the
+  // evaluated batch (-1: finished), idx[j] = slot of row j, xg = gathered positions [Ba][n2]
   int *slot, *idx;
   double *xg;
 };
@@ -203,16 +217,15 @@ RFS_DEVINL bool hmc_mirror(const HmcDev &D, const HmcCfg &cfg, long long c) {
   return fin;
 }
 
-// chain initialisation: seed, set_initial_model until in bounds (hmc.py:74-99,231-235)
-__global__ void hmc_init_kernel(HmcDev D, HmcCfg cfg, long long C, const long long *chain_id,
-                                long long seed) {
-  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// chain initialisation: seed, set_initial_model until in bounds (hmc.py:74-99,231-235).
+// Starts chain `ch` in slot `c` (R = number of slots: the stride of the MT19937 state).
+RFS_DEVINL void hmc_chain_start(const HmcDev &D, const HmcCfg &cfg, long long R, long long c,
+                                long long ch) {
   Rng r;
   r.mt = D.mt;
-  r.C = C;
+  r.C = R;
   r.c = c;
-  r.seed((unsigned int)((seed + chain_id[c]) & 0xffffffffLL));
+  r.seed((unsigned int)((D.seed + D.chain_id[ch]) & 0xffffffffLL));
   const int n2 = cfg.n2, n = n2 / 2;
   double *x = D.xcur + c * n2;
   for (;;) {
@@ -239,19 +252,19 @@ __global__ void hmc_init_kernel(HmcDev D, HmcCfg cfg, long long C, const long lo
   }
   for (int i = 0; i < n2; i++) {
     D.xeval[c * n2 + i] = x[i];
-    if (D.initmodel) D.initmodel[c * n2 + i] = x[i];
+    if (D.initmodel) D.initmodel[ch * n2 + i] = x[i];
   }
+  D.chain[c] = (int)ch;
   D.phase[c] = HP_INIT;
-  D.slot[c] = (int)c;
   D.istep[c] = 0;
   D.L[c] = 0;
   D.okcur[c] = 0;
   D.fd_it[c] = 0;
   D.fd_a[c] = 0;
-  D.status[c] = 0;
+  D.status[ch] = 0;
   D.iacc[c] = 0;
   D.ncount[c] = 0;
-  D.nevals[c] = 0;
+  D.nevals[ch] = 0;
   D.dt[c] = cfg.dt0;
   D.dtbar[c] = cfg.dt0;
   D.h0[c] = 0.0;
@@ -259,6 +272,12 @@ __global__ void hmc_init_kernel(HmcDev D, HmcCfg cfg, long long C, const long lo
   D.Hcur[c] = 0.0;
   D.fdH[c] = 0.0;
   rng_store(D, r);
+}
+__global__ void hmc_init_kernel(HmcDev D, HmcCfg cfg, long long R) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c >= R) return;
+  D.slot[c] = (int)c;
+  hmc_chain_start(D, cfg, R, c, c);  // slots 0..R-1 start chains 0..R-1; the queue head starts at R
 }
 
 // Chains finish at different times (random L, rejections, stuck chains): re-pack the running ones so
@@ -283,18 +302,41 @@ __global__ void hmc_gather_kernel(HmcDev D, int n2, long long Ba) {
   D.xg[t] = D.xeval[(long long)D.idx[j] * n2 + i];
 }
 
+// Wall-clock budget exhausted (rfs_set_hmc_options): stop every running slot where it stands and mark
+// its chain, and every chain still queued, with status 5.
+__global__ void hmc_abort_kernel(HmcDev D, long long R) {
+  const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (c < R && D.phase[c] != HP_DONE) {
+    const long long ch = D.chain[c];
+    D.status[ch] = 5;
+    D.o_iter[ch] = D.ncount[c];
+    D.o_acc[ch] = D.iacc[c];
+    D.o_dt[ch] = D.dt[c];
+    D.phase[c] = HP_DONE;
+  }
+  // chains that never started
+  const long long first = min((long long)*D.queue_head, D.C_total);
+  for (long long ch = first + c; ch < D.C_total; ch += R) {
+    D.status[ch] = 5;
+    D.o_iter[ch] = 0;
+    D.o_acc[ch] = 0;
+    D.o_dt[ch] = 0.0;
+  }
+}
+
 RFS_DEVINL bool any_nan(const double *v, int n) {
   bool f = false;
   for (int i = 0; i < n; i++) f = f || isnan(v[i]);
   return f;
 }
 
-// One global step of every chain.
+// One global step of every slot (c = slot, ch = the chain it currently runs; C = number of slots).
 __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
   const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (c >= C) return;
   int phase = D.phase[c];
   if (phase == HP_DONE) return;
+  const long long ch = D.chain[c];
   const int n2 = cfg.n2, nd = cfg.ndata;
   Rng r = rng_load(D, C, c);
   double *xcur = D.xcur + c * n2, *xnew = D.xnew + c * n2, *pnew = D.pnew + c * n2,
@@ -303,7 +345,7 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
   const double *ge = D.ge + e * n2, *de = D.de + e * nd;
   const double Ue = D.Ue[e];
   const bool fe = D.fe[e] != 0;
-  D.nevals[c] += 1;
+  D.nevals[ch] += 1;
   double dt = D.dt[c];
   const double log_half = log(0.5);
 
@@ -320,7 +362,7 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
     if (cfg.sampler == 1) {
       // ---- _find_initial_dt prologue (hmcda.py:170-184)
       if (!D.okcur[c]) {
-        D.status[c] = 3;
+        D.status[ch] = 3;
         phase = HP_DONE;
       } else {
         double K = 0.0;
@@ -348,7 +390,7 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
   } else if (phase == HP_FD) {
     // ---- _find_initial_dt loop body (hmcda.py:186-215)
     if (!fe) {
-      D.status[c] = 4;
+      D.status[ch] = 4;
       phase = HP_DONE;
     } else {
       double K = 0.0;
@@ -446,11 +488,11 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
         D.okcur[c] = 1;
         if (iacc >= cfg.ndraws) {
           const long long s = iacc - cfg.ndraws;
-          if (D.misfit) D.misfit[c * cfg.nsamples + s] = Ue;
+          if (D.misfit) D.misfit[ch * cfg.nsamples + s] = Ue;
           if (D.samples)
-            for (int j = 0; j < n2; j++) D.samples[(c * cfg.nsamples + s) * n2 + j] = xnew[j];
+            for (int j = 0; j < n2; j++) D.samples[(ch * cfg.nsamples + s) * n2 + j] = xnew[j];
           if (D.syn)
-            for (int j = 0; j < nd; j++) D.syn[(c * cfg.nsamples + s) * nd + j] = de[j];
+            for (int j = 0; j < nd; j++) D.syn[(ch * cfg.nsamples + s) * nd + j] = de[j];
         }
         iacc++;
         D.iacc[c] = iacc;
@@ -471,7 +513,7 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
           dt = D.dtbar[c] * 1.;
         }
       }
-      if (D.alog && nc < cfg.max_log) D.alog[c * cfg.max_log + nc] = accept ? 1 : 0;
+      if (D.alog && nc < cfg.max_log) D.alog[ch * cfg.max_log + nc] = accept ? 1 : 0;
       D.ncount[c] = nc + 1;
       failed = false;
       begin = true;
@@ -484,12 +526,12 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
         break;
       }
       if (cfg.max_iters > 0 && D.ncount[c] >= cfg.max_iters) {
-        D.status[c] = 2;
+        D.status[ch] = 2;
         phase = HP_DONE;
         break;
       }
       if (!D.okcur[c]) {
-        D.status[c] = 3;
+        D.status[ch] = 3;
         phase = HP_DONE;
         break;
       }
@@ -532,6 +574,17 @@ __global__ void hmc_advance_kernel(HmcDev D, HmcCfg cfg, long long C) {
   D.dt[c] = dt;
   D.phase[c] = phase;
   rng_store(D, r);
+  if (phase == HP_DONE) {
+    // chain finished: publish its counters and hand the slot to the next queued chain, if any
+    D.o_iter[ch] = D.ncount[c];
+    D.o_acc[ch] = D.iacc[c];
+    D.o_dt[ch] = dt;
+    const int next = atomicAdd(D.queue_head, 1);
+    if ((long long)next < D.C_total) {
+      hmc_chain_start(D, cfg, C, c, next);
+      phase = HP_INIT;
+    }
+  }
   if (phase != HP_DONE) atomicAdd(D.n_active, 1);
 }
 

@@ -71,6 +71,37 @@ def test_batch_compaction_leaves_every_chain_unchanged(ctx):
                 assert np.array_equal(np.asarray(full[k])[part], np.asarray(sub[k]), equal_nan=True), k
 
 
+def test_slot_refill_and_budget_leave_every_chain_unchanged(ctx):
+    """Chain-level refill: with fewer resident slots than chains, a finished chain hands its slot to the
+    next queued chain on the device.  Every chain's result must be the one it has when all chains are
+    resident; a wall-clock budget stops the run with the unfinished chains flagged."""
+    cfg, dobs, bounds = _setup(ctx)
+    ids = np.arange(40)
+    kw = dict(seed=991206, nsamples=5, ndraws=1, max_iters=12, want_samples=True, log_accepts=12)
+    full = ctx.hmc_run(0, ids, bounds, 0.1, Lrange=(5, 20), **kw)
+    try:
+        for resident in (7, 16):
+            ctx.set_hmc_options(resident=resident)
+            part = ctx.hmc_run(0, ids, bounds, 0.1, Lrange=(5, 20), **kw)
+            assert part["global_steps"] > full["global_steps"]        # the same work through fewer slots
+            for k in ("samples", "misfit", "n_iter", "n_acc", "accept_seq", "initmodel", "dt"):
+                assert np.array_equal(np.asarray(full[k]), np.asarray(part[k]), equal_nan=True), (resident, k)
+            assert part["evals"] == full["evals"]
+        da_full = ctx.hmc_run(1, ids[:12], bounds, 0.02, L0=10, target_ratio=0.65, seed=991206, nsamples=6,
+                              ndraws=3, max_iters=10, want_samples=True, log_accepts=10)
+        ctx.set_hmc_options(resident=5)
+        da_part = ctx.hmc_run(1, ids[:12], bounds, 0.02, L0=10, target_ratio=0.65, seed=991206, nsamples=6,
+                              ndraws=3, max_iters=10, want_samples=True, log_accepts=10)
+        for k in ("samples", "misfit", "n_iter", "n_acc", "accept_seq", "dt"):
+            assert np.array_equal(np.asarray(da_full[k]), np.asarray(da_part[k]), equal_nan=True), k
+        # wall-clock budget: a run that cannot finish in time returns what it has
+        ctx.set_hmc_options(resident=4, max_seconds=1e-3)
+        cut = ctx.hmc_run(0, ids, bounds, 0.1, Lrange=(5, 20), seed=991206, nsamples=400, ndraws=100)
+        assert "wall-clock budget" in cut["warning"] and (cut["n_acc"] < 500).all()
+    finally:
+        ctx.set_hmc_options(0, 0.0)
+
+
 def test_sampler_front_ends_and_result_files(ctx, tmp_path):
     import yaml
     from rfsurfhmc_b200 import driver
