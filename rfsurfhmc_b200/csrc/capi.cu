@@ -532,7 +532,14 @@ int rfs_create(rfs_ctx **out, int device) {
       ctx->team_S = s2;
     }
   }
-  // workspace budget per chunk of the fused path (MiB); batches larger than what fits are chunked
+  // workspace budget per chunk of the fused path; batches larger than what fits are chunked.  Default:
+  // 60 % of the memory free on this GPU now (a B200 has 180 GB: the Jacobians of 8 192 models of 200
+  // layers fit in two chunks), overridden in MiB by RFS_WS_BUDGET_MB
+  {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr > ((size_t)8 << 30))
+      ctx->ws_budget = std::max<size_t>((size_t)4 << 30, (size_t)(0.6 * (double)fr));
+  }
   if (const char *e = getenv("RFS_WS_BUDGET_MB")) {
     const long long mb = atoll(e);
     if (mb > 0) ctx->ws_budget = (size_t)mb << 20;

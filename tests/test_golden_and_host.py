@@ -339,3 +339,18 @@ def test_references_own_test_script_curves(oracle):
     T = z["tf_tRc"]
     assert np.array_equal(oracle.surf_forward(thk, vp, vs, rho, T, "Rc")[0], z["tf_Rc"])
     assert np.array_equal(oracle.surf_forward(thk, vp, vs, rho, T, "Rg")[0], z["tf_Rg"])
+
+
+def test_real_data_resampling_matches_the_references_own_utils():
+    """rfsurfhmc_b200/utils.py against outputs of the reference's unmodified src/utils.py
+    (tests/golden/make_utils_golden.py generated utils_resample.npz in the build container)."""
+    from rfsurfhmc_b200.utils import get_rf_inv_para, next_power_of_2
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "utils_resample.npz"))
+    assert [next_power_of_2(int(v)) for v in z["pow2_in"]] == z["pow2_out"].tolist()
+    for i in range(3):
+        ts, te = z[f"in_{i}_win"]
+        y, nt, dt, shift = get_rf_inv_para(z[f"in_{i}_d"], z[f"in_{i}_t"], ts, te)
+        assert np.array_equal(y, z[f"out_{i}_y"])
+        assert [nt, dt, shift] == z[f"out_{i}_meta"].tolist()
+    with pytest.raises(Exception):
+        get_rf_inv_para(z["in_0_d"], z["in_0_t"], -100.0, 10.0)
