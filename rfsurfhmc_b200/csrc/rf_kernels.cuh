@@ -429,10 +429,13 @@ __global__ void __launch_bounds__(128, RFS_RF_MINBLOCKS)
 }
 
 // ------------------------------------------------------------------ shared-memory FFT
-// In-place radix-2 DIT on `buf[N]` (N power of two), executed by the whole block.
-// sign = -1: forward (e^{-i..}), +1: backward; unnormalised (FFTW convention).
-// tw[j] = exp(-i pi j / (N/2)), j < N/2 (fft_twiddle_kernel): the butterflies look their factors
-// up instead of evaluating sincospi per butterfly and stage (the same values, bit for bit).
+// Real <-> Hermitian transforms of length N (power of two) as ONE complex transform of length N/2
+// (even/odd packing) with a Stockham autosort radix-4 schedule: log4(N/2) passes (plus one radix-2
+// pass when log2(N/2) is odd), no bit-reversal pass, every pass reads a[j + r M/4] with unit stride
+// over the threads.  Replaces FFTW's r2c / c2r plans of /root/reference/src/RF/fftpack.f90 (and the
+// radix-2 + bit-reversal transform of round 1: half the butterflies, half the passes, a third of the
+// barriers).  Unnormalised (FFTW convention).
+// tw[j] = exp(-2 pi i j / N), j < N/2 (fft_twiddle_kernel): twiddles are looked up, never evaluated.
 __global__ void fft_twiddle_kernel(int N, double2 *__restrict__ tw) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N / 2) return;
@@ -440,33 +443,105 @@ __global__ void fft_twiddle_kernel(int N, double2 *__restrict__ tw) {
   sincospi(-(double)j / (double)(N / 2), &sn, &cs);
   tw[j] = make_double2(cs, sn);
 }
-// TW_SMEM: the table has been copied to shared memory by the caller (kernels that run many FFTs)
-template <bool TW_SMEM = false>
-RFS_DEVINL void block_fft(cd *buf, int N, int logN, int sign, const double2 *__restrict__ tw) {
+// exp(sign 2 pi i q / NT), 0 <= q < NT, from the half-circle table
+template <bool TW_SMEM>
+RFS_DEVINL cd tw_lookup(const double2 *__restrict__ tw, int q, int NT, int sign) {
+  const int h = NT >> 1;
+  const bool neg = q >= h;
+  const int qq = neg ? q - h : q;
+  const double2 t = TW_SMEM ? tw[qq] : __ldg(tw + qq);
+  const cd w(t.x, sign < 0 ? t.y : -t.y);
+  return neg ? cd(-w.x, -w.y) : w;
+}
+// Complex transform of length M = 2^logM, ping-pong between a and b (M entries each), executed by the
+// whole block; `tw` is the table of length NT/2 for NT = 2M.  Returns the buffer holding the result
+// (natural order).  sign = -1 forward (e^{-i..}), +1 backward.
+template <bool TW_SMEM>
+RFS_DEVINL cd *stockham_fft(cd *a, cd *b, int M, int logM, int sign, const double2 *__restrict__ tw,
+                            int NT) {
   const int tid = threadIdx.x, nth = blockDim.x;
-  // bit reversal
-  for (int i = tid; i < N; i += nth) {
-    const int j = (int)(__brev((unsigned)i) >> (32 - logN));
-    if (i < j) {
-      const cd t = buf[i];
-      buf[i] = buf[j];
-      buf[j] = t;
-    }
-  }
-  __syncthreads();
-  for (int s = 1; s <= logN; s++) {
-    const int half = 1 << (s - 1);
-    for (int t = tid; t < N / 2; t += nth) {
-      const int grp = t >> (s - 1), pos = t & (half - 1);
-      const int i0 = (grp << s) + pos, i1 = i0 + half;
-      const double2 w = TW_SMEM ? tw[pos << (logN - s)] : __ldg(tw + (pos << (logN - s)));
-      const cd wv(w.x, sign < 0 ? w.y : -w.y);
-      const cd u = buf[i0], v = buf[i1] * wv;
-      buf[i0] = u + v;
-      buf[i1] = u - v;
+  int Ns = 1, lg = logM;
+  while (lg >= 2) {
+    const int q4 = M >> 2;
+    const int tstep = NT / (4 * Ns);  // exp(sign 2 pi i r k / (4 Ns)) = table[r k tstep]
+    for (int j = tid; j < q4; j += nth) {
+      const int k = j & (Ns - 1);
+      cd v0 = a[j], v1 = a[j + q4], v2 = a[j + 2 * q4], v3 = a[j + 3 * q4];
+      if (k) {
+        v1 = v1 * tw_lookup<TW_SMEM>(tw, k * tstep, NT, sign);
+        v2 = v2 * tw_lookup<TW_SMEM>(tw, 2 * k * tstep, NT, sign);
+        v3 = v3 * tw_lookup<TW_SMEM>(tw, 3 * k * tstep, NT, sign);
+      }
+      const cd s02 = v0 + v2, d02 = v0 - v2, s13 = v1 + v3, d13 = v1 - v3;
+      const cd jd = (sign < 0) ? cd(d13.y, -d13.x) : cd(-d13.y, d13.x);  // -+ i (v1 - v3)
+      const int j0 = ((j - k) << 2) + k;
+      b[j0] = s02 + s13;
+      b[j0 + Ns] = d02 + jd;
+      b[j0 + 2 * Ns] = s02 - s13;
+      b[j0 + 3 * Ns] = d02 - jd;
     }
     __syncthreads();
+    cd *t = a;
+    a = b;
+    b = t;
+    Ns <<= 2;
+    lg -= 2;
   }
+  if (lg == 1) {
+    const int q2 = M >> 1;
+    const int tstep = NT / (2 * Ns);
+    for (int j = tid; j < q2; j += nth) {
+      const int k = j & (Ns - 1);
+      const cd v0 = a[j];
+      cd v1 = a[j + q2];
+      if (k) v1 = v1 * tw_lookup<TW_SMEM>(tw, k * tstep, NT, sign);
+      const int j0 = ((j - k) << 1) + k;
+      b[j0] = v0 + v1;
+      b[j0 + Ns] = v0 - v1;
+    }
+    __syncthreads();
+    cd *t = a;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+// c2r: Hermitian half spectrum X(k), k = 0..N/2 (imaginary parts of X(0), X(N/2) ignored, as FFTW's
+// c2r does) -> real x[0..N): returns z with x[2m] = z[m].x, x[2m+1] = z[m].y.  work: N complex.
+template <bool TW_SMEM, class F>
+RFS_DEVINL cd *block_irfft(F X, cd *work, int N, int logN, const double2 *__restrict__ tw) {
+  const int M = N >> 1;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    cd xk = X(k), xm = conj(X(M - k));
+    if (k == 0) {
+      xk.y = 0.0;
+      xm.y = 0.0;
+    }
+    const cd xe = xk + xm;
+    const cd xo = (xk - xm) * tw_lookup<TW_SMEM>(tw, k, N, +1);
+    work[k] = cd(xe.x - xo.y, xe.y + xo.x);  // xe + i xo
+  }
+  __syncthreads();
+  return stockham_fft<TW_SMEM>(work, work + M, M, logN - 1, +1, tw, N);
+}
+RFS_DEVINL double irfft_at(const cd *z, int t) { return (t & 1) ? z[t >> 1].y : z[t >> 1].x; }
+// r2c: real x(t), t = 0..N-1 -> z = FFT_{N/2}(x[2m] + i x[2m+1]); the half spectrum is then
+// rfft_at(z, k, ..), k = 0..N/2.  work: N complex.
+template <bool TW_SMEM, class F>
+RFS_DEVINL cd *block_rfft(F x, cd *work, int N, int logN, const double2 *__restrict__ tw) {
+  const int M = N >> 1;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) work[m] = cd(x(2 * m), x(2 * m + 1));
+  __syncthreads();
+  return stockham_fft<TW_SMEM>(work, work + M, M, logN - 1, -1, tw, N);
+}
+template <bool TW_SMEM>
+RFS_DEVINL cd rfft_at(const cd *z, int k, int N, const double2 *__restrict__ tw) {
+  const int M = N >> 1;
+  const cd zk = z[k & (M - 1)], zm = conj(z[(M - k) & (M - 1)]);
+  const cd xe = 0.5 * (zk + zm), d = zk - zm;
+  const cd xo(0.5 * d.y, -0.5 * d.x);  // (zk - zm) / (2 i)
+  if (k == M) return cd(xe.x - xo.x, 0.0);  // e^{-i pi} = -1
+  return xe + xo * tw_lookup<TW_SMEM>(tw, k, N, -1);
 }
 
 RFS_DEVINL double block_reduce(double v, double *red, bool is_max) {
@@ -522,30 +597,26 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
     lmax = fmax(lmax, a.x * a.x + a.y * a.y);
   }
   const double wmax = block_reduce(lmax, red, true);
-  // spectral division (:393-401) and Hermitian extension for the c2r transform
+  // spectral division (:393-401) into wt (free until the adjoint pass), then the c2r transform
   for (int k = tid; k < n2; k += nth) {
     const double w = 1.0 / nft / dt * k * 2.0 * RFS_PI32;
     const double gx = w / 2 / f0;
     const double g = exp(-(gx * gx));
     const double wa = norm2(s21[k]);
     const double fai = fmax(wa, water * wmax);
-    cd s = conj(s21[k]) * s22[k] * g * cis(-w * t0) / fai;
-    if (k == 0 || k == nft / 2) {
-      buf[k] = cd(s.x, 0.0);
-    } else {
-      buf[k] = s;
-      buf[nft - k] = conj(s);
-    }
+    wt[k] = conj(s21[k]) * s22[k] * g * cis(-w * t0) / fai;
   }
   __syncthreads();
-  block_fft(buf, nft, logn, +1, tw);
-  // trace, residual, weighted residual (:404-407 and the adjoint source)
+  const cd *z = block_irfft<false>([&](int k) { return wt[k]; }, buf, nft, logn, tw);
+  // trace, residual, weighted residual (:404-407 and the adjoint source; the real sequence is kept in
+  // the .x of wt[0..nt), the rest of the padded sequence is zero)
   double lsum = 0.0;
+  double *rsd = reinterpret_cast<double *>(wt);  // nt <= nft doubles fit in n2 complex entries
   for (int it = tid; it < nft; it += nth) {
     double rt = 0.0;
     if (it < nt) {
       const double e = exp(sigma * (-t0 + it * dt));
-      const double v = buf[it].x / nft / dt * e;
+      const double v = irfft_at(z, it) / nft / dt * e;
       rf[b * ldrf + it] = v;
       if (dobs) {
         const double r = v - dobs[it];
@@ -553,14 +624,14 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
         rt = r * e / dt;
       }
     }
-    buf[it] = cd(rt, 0.0);
+    rsd[it] = rt;
   }
   if (dobs == nullptr) return;
   const double ss = block_reduce(lsum, red, false);
   if (tid == 0) U[b] = accumulate ? U[b] + 0.5 * ss : 0.5 * ss;
   if (grad == nullptr) return;
   __syncthreads();
-  block_fft(buf, nft, logn, -1, tw);
+  const cd *zr = block_rfft<false>([&](int t) { return rsd[t]; }, buf, nft, logn, tw);
   // second water level on |R21^2|^2 (:410-413) and adjoint weights
   double lmax2 = 0.0;
   for (int k = tid; k < n2; k += nth) {
@@ -577,9 +648,9 @@ __global__ void rf_decon_kernel(const double2 *__restrict__ spec, const double2 
     const double fai = fmax(wa, water * wmax2);
     const cd Mk = conj(sq) * g * cis(-w * t0) / fai;
     const double ck = (k == 0 || k == nft / 2) ? 1.0 : 2.0;
-    cd rk = buf[k];
+    cd rk = rfft_at<false>(zr, k, nft, tw);
     if (k == 0 || k == nft / 2) rk.y = 0.0;
-    wt[k] = Mk * conj(rk) * (ck / nft);
+    wt[k] = Mk * conj(rk) * (ck / nft);  // the residual sequence kept in wt has been consumed by block_rfft
   }
   __syncthreads();
   // grad_row = sum_k Re(wt_k D_row,k): one warp per row
@@ -626,18 +697,12 @@ __global__ void rf_trace_kernel(const double2 *__restrict__ spec, const double2 
     const cd sq = s21[k] * s21[k];
     const double fai = fmax(norm2(sq), water * wmax2);
     const double2 d = dp[k];
-    const cd s = conj(sq) * cd(d.x, d.y) * g * cis(-w * t0) / fai;
-    if (k == 0 || k == nft / 2) {
-      buf[k] = cd(s.x, 0.0);
-    } else {
-      buf[k] = s;
-      buf[nft - k] = conj(s);
-    }
+    s21[k] = conj(sq) * cd(d.x, d.y) * g * cis(-w * t0) / fai;  // in place: s21[k] is read by this thread only
   }
   __syncthreads();
-  block_fft(buf, nft, logn, +1, tw);
+  const cd *z = block_irfft<false>([&](int k) { return s21[k]; }, buf, nft, logn, tw);
   for (int it = tid; it < nt; it += nth)
-    out[(b * nrow + rr) * (long long)nt + it] = buf[it].x / nft / dt * exp(sigma * (-t0 + it * dt));
+    out[(b * nrow + rr) * (long long)nt + it] = irfft_at(z, it) / nft / dt * exp(sigma * (-t0 + it * dt));
 }
 
 }  // namespace rfs

@@ -81,23 +81,17 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
   for (int it = 1; it <= 200; it++) {
     if (fabs(d_error) <= minderr) break;
     // cuw = irfft( rfft(rflt) conj(rfft(wflt)) ) dt ,  rfft(rflt) = Uf - dt P Wc
-    for (int k = tid; k < n2; k += nth) {
-      const cd R = Uf[k] - dt * (P[k] * Wf[k]);
-      const cd c = R * conj(Wf[k]);
-      if (k == 0 || k == nft / 2) {
-        buf[k] = cd(c.x, 0.0);
-      } else {
-        buf[k] = c;
-        buf[nft - k] = conj(c);
-      }
-    }
-    __syncthreads();
-    block_fft<true>(buf, nft, logn, +1, tws);
+    const cd *z = block_irfft<true>(
+        [&](int k) {
+          const cd R = Uf[k] - dt * (P[k] * Wf[k]);
+          return R * conj(Wf[k]);
+        },
+        buf, nft, logn, tws);
     // first maximum of |cuw| over the first nft/2 lags (maxloc, deconit.f90:178)
     double best = -1.0;
     int bi = 0x7fffffff;
     for (int t = tid; t < nft / 2; t += nth) {
-      const double v = fabs(buf[t].x);
+      const double v = fabs(irfft_at(z, t));
       if (v > best) {
         best = v;
         bi = t;
@@ -130,7 +124,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
         }
       }
       red[0] = (double)ii;
-      red[1] = buf[ii].x / nft * dt;  // cuw(idx) = irfft(..)*dt
+      red[1] = irfft_at(z, ii) / nft * dt;  // cuw(idx) = irfft(..)*dt
     }
     __syncthreads();
     const int idx = (int)red[0];
@@ -161,18 +155,12 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     const double g = exp(-0.25 * (gx * gx));
     cd pk = P[k] * g;
     if (k == 0 || k == nft / 2) pk.y = 0.0;  // irfft/rfft round trip inside apply_gaussian
-    const cd s = pk * cis(-((double)k / (nft * dt) * RFS_PI32 * 2 * tshift));
-    if (k == 0 || k == nft / 2) {
-      buf[k] = cd(s.x, 0.0);
-    } else {
-      buf[k] = s;
-      buf[nft - k] = conj(s);
-    }
+    P[k] = pk * cis(-((double)k / (nft * dt) * RFS_PI32 * 2 * tshift));
   }
   __syncthreads();
-  block_fft<true>(buf, nft, logn, +1, tws);
+  const cd *z = block_irfft<true>([&](int k) { return P[k]; }, buf, nft, logn, tws);
   double *dst = (r == 0) ? rf + b * ldrf : traces + (b * (long long)nrow + (r - 1)) * nt;
-  for (int t = tid; t < nt; t += nth) dst[t] = buf[t].x / nft;
+  for (int t = tid; t < nt; t += nth) dst[t] = irfft_at(z, t) / nft;
 }
 
 // misfit and gradient from materialised Frechet traces (time-domain method, where the adjoint
