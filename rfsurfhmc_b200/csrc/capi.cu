@@ -18,7 +18,7 @@
 #include "rf_kernels.cuh"
 #include "rf_time_kernels.cuh"
 #include "swd_kernels.cuh"
-#include "swd_roots_team.cuh"
+#include "swd_roots_launch.h"
 
 using namespace rfs;
 
@@ -259,32 +259,35 @@ void pick_team(const rfs_ctx *ctx, long long jobs, int n, int &T, int &S) {
   }
   T = 0;
   S = 1;
-  if (n <= 8) {
-    if (jobs >= 24576) return;
-    if (jobs >= 8192) { T = 4; S = 1; return; }
-    if (jobs >= 2048) { T = 8; S = 1; return; }
+  // jobs = (model, sequence) pairs in flight; thresholds: fastest mapping in the measured sweep
+  if (n <= 16) {
+    if (jobs >= 18432) return;                      // thread-mapped
+    if (jobs >= 9216) { T = 4; S = 4; return; }     // one lane per scan point, no layer split
+    if (jobs >= 4608) { T = 8; S = 2; return; }
+    if (jobs >= 1536) { T = 16; S = 2; return; }
     T = 32; S = 4;
     return;
   }
-  if (n <= 16) {
-    if (jobs >= 24576) return;
-    if (jobs >= 4096) { T = 8; S = 1; return; }
-    if (jobs >= 1024) { T = 16; S = 1; return; }
-    T = 32; S = 2;
-    return;
-  }
-  // many layers: one warp per sequence as soon as the thread mapping cannot fill the machine
-  if (jobs >= 32768) return;
-  if (jobs >= 8192) { T = 8; S = 1; return; }
-  T = 32; S = 1;
+  // many layers (n = 40 ... 200): the sequential 5-vector chain dominates; wide teams pay off longer
+  if (jobs >= 12288) return;
+  if (jobs >= 1536) { T = 16; S = 2; return; }
+  T = 32; S = 4;
 }
 
-bool team_supported(int T, int S) {
-  static const int ok[][2] = {{4, 1}, {4, 4}, {8, 1}, {8, 2}, {16, 1}, {16, 2}, {32, 1}, {32, 2}, {32, 4}};
-  for (auto &p : ok)
-    if (p[0] == T && p[1] == S) return true;
-  return false;
-}
+bool team_supported(int T, int S) { return team_shape_supported(T, S); }
+
+// launch through the root-search translation unit (swd_roots_tu.cu), with the bookkeeping of LAUNCH
+#define LAUNCH_TU(name, call)                                   \
+  do {                                                          \
+    prof_begin(ctx, name, st);                                  \
+    cudaError_t e_ = (call);                                    \
+    ctx->launches++;                                            \
+    prof_end(ctx, st);                                          \
+    if (e_ != cudaSuccess) {                                    \
+      ctx->err = std::string(name) + ": " + cudaGetErrorString(e_); \
+      return RFS_E_CUDA;                                        \
+    }                                                           \
+  } while (0)
 
 int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
                  long long B, int n, int all_modes, cudaStream_t st) {
@@ -295,30 +298,16 @@ int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const 
   ctx->last_team_T = T;
   ctx->last_team_S = S;
   if (T == 0) {
-    LAUNCH(swd_roots_kernel, gridFor(jobs, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd, B, n,
-           d_periods, all_modes, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
-           (int *)ctx->w_ierr.p, cnt);
+    LAUNCH_TU("swd_roots_kernel",
+              launch_roots_thread(P, d_swd, B, n, d_periods, all_modes, (double *)ctx->w_croot.p,
+                                  (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p, cnt, st));
     return RFS_OK;
   }
-  // threads per block: as many teams as fit ~64 KB of staged layer parameters
-  int threads = 128;
-  const size_t per_team = sizeof(double) * RFS_TEAM_NF * (size_t)n;
-  while (threads > 32 && threads > T && (threads / T) * per_team > 64 * 1024) threads /= 2;
-  const size_t sm = (threads / T) * per_team;
-  const unsigned grid = gridFor(jobs, threads / T);
-#define TEAM(TT, SS)                                                                              \
-  if (T == TT && S == SS) {                                                                       \
-    if (sm > 48 * 1024)                                                                           \
-      CK(cudaFuncSetAttribute(swd_roots_team_kernel<TT, SS>,                                      \
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));             \
-    LAUNCH((swd_roots_team_kernel<TT, SS>), grid, threads, sm, st, P, d_swd, B, n, d_periods,     \
-           all_modes, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p,   \
-           cnt);                                                                                  \
-    return RFS_OK;                                                                                \
-  }
-  TEAM(4, 1) TEAM(4, 4) TEAM(8, 1) TEAM(8, 2) TEAM(16, 1) TEAM(16, 2) TEAM(32, 1) TEAM(32, 2) TEAM(32, 4)
-#undef TEAM
-  return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
+  if (!team_shape_supported(T, S)) return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
+  LAUNCH_TU("swd_roots_team_kernel",
+            launch_roots_team(T, S, P, d_swd, B, n, d_periods, all_modes, (double *)ctx->w_croot.p,
+                              (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p, cnt, st));
+  return RFS_OK;
 }
 
 // ---- SWD pipeline on a prepared model block: roots + eigen solves
@@ -335,10 +324,11 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
   if ((rc = launch_roots(ctx, P, d_periods, d_swd, B, n, all_modes ? 1 : 0, st))) return rc;
   // per-period retries of failed fundamental-mode searches (rare; idle warps exit at once)
   if ((rc = ensure(ctx, ctx->w_rstat, sizeof(int) * (size_t)P.nsolve * B))) return rc;
-  LAUNCH(swd_retry_kernel, gridFor(B * P.nsolve, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st, P, d_swd,
-         B, n, d_periods, all_modes ? 1 : 0, (double *)ctx->w_croot.p, (double *)ctx->w_cwork.p,
-         (const int *)ctx->w_ierr.p, (int *)ctx->w_rstat.p,
-         ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr);
+  LAUNCH_TU("swd_retry_kernel",
+            launch_roots_retry(P, d_swd, B, n, d_periods, all_modes ? 1 : 0, (double *)ctx->w_croot.p,
+                               (double *)ctx->w_cwork.p, (const int *)ctx->w_ierr.p,
+                               (int *)ctx->w_rstat.p,
+                               ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr, st));
   LAUNCH(swd_retry_finish_kernel, gridFor(B * P.nseq, 128), 128, 0, st, P, B, all_modes ? 1 : 0,
          (double *)ctx->w_croot.p, (int *)ctx->w_ierr.p, (const int *)ctx->w_rstat.p);
   if (!want_eigen) return RFS_OK;

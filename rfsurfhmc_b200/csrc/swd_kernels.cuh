@@ -5,29 +5,9 @@
 #include "swd_love.cuh"
 #include "swd_rayleigh.cuh"
 #include "swd_roots.cuh"
+#include "swd_plan.cuh"
 
 namespace rfs {
-
-#define RFS_MAX_SEQ 12
-#define RFS_MAX_ROWS 4
-
-// one requested data block ("row"): a wave type on a period list
-struct SwdRow {
-  int type;      // 0 Rc, 1 Rg, 2 Lc, 3 Lg
-  int nper;      // periods
-  int per_off;   // offset of its period list in the period table
-  int s0, s1, s2;  // sequences: T, 1.05 T, 0.95 T (s1,s2 = -1 for phase velocity)
-  int d_off;     // offset of this row in the concatenated data vector
-};
-
-struct SwdPlan {
-  int nseq, nrow;
-  int nsolve;  // total (sequence, period) pairs == total periods over sequences
-  int ndata;   // total data count over rows
-  int nmode;   // modes solved (mode+1); the last one is reported
-  SwdSeq seq[RFS_MAX_SEQ];
-  SwdRow row[RFS_MAX_ROWS];
-};
 
 // ---- model preparation: x=[vs(n),thk(n)] -> Brocher vp/rho (+derivatives) and the two model
 // blocks.  Follows model/model_surf.py:47-79 and model/model_rf.py:52-77 (same polynomials) and
@@ -161,88 +141,6 @@ __global__ void prep_sphere_kernel(const double *__restrict__ flat, long long B,
     }
   }
   (void)nb;
-}
-
-// ---- K1: one thread per (model, sequence)
-// croot : [nmode_out][nsolve][B]   cwork : [nsolve][B] (only touched when nmode > 1)
-// ierr  : [nseq][B] int
-#ifndef RFS_ROOTS_MINBLOCKS
-#define RFS_ROOTS_MINBLOCKS 4
-#endif
-#ifndef RFS_ROOTS_BLOCK
-#define RFS_ROOTS_BLOCK 128
-#endif
-__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
-    swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
-                     const double *__restrict__ periods, int all_modes,
-                     double *__restrict__ croot, double *__restrict__ cwork,
-                     int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
-  __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const bool valid = i < B * plan.nseq;
-  const long long b = valid ? i % B : 0;
-  const int s = valid ? (int)(i / B) : 0;
-  SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
-  unsigned int nev = 0;
-  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
-                                   wsm_all[threadIdx.x >> 5], -1);
-  if (valid) ierr[(long long)s * B + b] = e;
-  if (neval_total) {
-    // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
-    unsigned int w = nev;
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
-    atomicMax(neval_total + 1, (unsigned long long)nev);          // slowest thread
-    if (nev > 2000u) atomicAdd(neval_total + 2, 1ull);            // heavy threads (> 2000 evals)
-  }
-}
-
-// ---- per-period retries of _surfdisp (surfdisp.cpp:93-100): when the fundamental mode failed in
-// the main pass, every period whose reported value is zero / NaN is searched again as a fresh
-// single-period problem (start value cc, scan upward in dc steps: hundreds of evaluations).
-// The reference does these one after the other and stops at the first one that fails again; the
-// jobs are independent, so they run here as one thread per (model, sequence, period) — in a warp
-// that is otherwise idle, whose 31 spare lanes take over the look-ahead scan — and
-// swd_retry_finish_kernel re-imposes the sequential stop rule.
-//   rstat [nsolve][B] int: -1 not retried, 0 retried ok, 1 retried and failed again
-__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
-    swd_retry_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
-                     const double *__restrict__ periods, int all_modes,
-                     double *__restrict__ croot, double *__restrict__ cwork,
-                     const int *__restrict__ ierr, int *__restrict__ rstat,
-                     unsigned long long *__restrict__ neval_total) {
-  __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const bool inrange = i < B * plan.nsolve;
-  const long long b = inrange ? i % B : 0;
-  const int solve = inrange ? (int)(i / B) : 0;
-  int s = 0;
-  for (int q = 0; q < plan.nseq; q++)
-    if (solve >= plan.seq[q].out_off && solve < plan.seq[q].out_off + plan.seq[q].nper) s = q;
-  const int k = solve - plan.seq[s].out_off;
-  bool valid = false;
-  if (inrange && ierr[(long long)s * B + b] != 0) {
-    const double *clast = croot + (all_modes ? (long long)(plan.nmode - 1) * plan.nsolve * B : 0);
-    const double v = clast[(long long)solve * B + b];
-    valid = (v == 0.0 || isnan(v));
-  }
-  // whole warps without work leave (the warp-cooperative loop needs all 32 lanes of a live warp)
-  if (__ballot_sync(0xffffffffu, valid) == 0u) {
-    if (inrange) rstat[(long long)solve * B + b] = -1;
-    return;
-  }
-  SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
-  unsigned int nev = 0;
-  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
-                                   wsm_all[threadIdx.x >> 5], k);
-  if (inrange) rstat[(long long)solve * B + b] = valid ? e : -1;
-  if (neval_total) {
-    unsigned int w = nev;
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
-  }
 }
 
 // sequential stop rule of the retry loop: `if(ierr !=0) return ierr;` leaves the later periods

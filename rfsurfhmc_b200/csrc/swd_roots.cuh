@@ -81,8 +81,9 @@ RFS_DEVINL LoveL love_layer(const MT &M, long long b, int m, double wvno, double
   return L;
 }
 RFS_DEVINL void love_apply(const LoveL &L, double &e1, double &e2) {
-  const double e10 = e1 * L.cosq + e2 * L.xmu * L.z;
-  const double e20 = e1 * L.y / L.xmu + e2 * L.cosq;
+  // explicit rounding (see RFS_FMA in common.cuh): the same bits from every kernel
+  const double e10 = RFS_FMA(e1, L.cosq, RFS_MUL(RFS_MUL(e2, L.xmu), L.z));
+  const double e20 = RFS_FMA(e2, L.cosq, RFS_MUL(e1, L.y) / L.xmu);
   double xnor = fmax(fabs(e10), fabs(e20));
   if (xnor < 1.e-40) xnor = 1.0;
   e1 = e10 / xnor;
@@ -218,24 +219,37 @@ RFS_DEVINL Dunkin dunkin_layer(const MT &M, long long b, int m, double wvno, dou
   const double a0 = (exa < 60.0) ? P.e * S.e : 0.0;
   const double cpcq = P.c * S.c, cpy = P.c * S.w, cpz = P.c * S.x, cqw = S.c * P.w,
                cqx = S.c * P.x, xy = P.x * S.w, xz = P.x * S.x, wy = P.w * S.w, wz = P.w * S.x;
-  // Dunkin matrix (dnka :1044-1088), unique entries only
+  // Dunkin matrix (dnka :1044-1088), unique entries only.  Every a*b+c below is an explicit FMA
+  // (RFS_FMA: fixed rounding in every kernel that inlines this function).
   const double gamm1 = gam - 1.0, twgm1 = gam + gamm1, gmgmk = gam * gammk, gmgm1 = gam * gamm1,
                gm1sq = gamm1 * gamm1, rho2 = rho * rho, irho2 = irho * irho, a0pq = a0 - cpcq;
   Dunkin C;
-  C.c11 = cpcq - 2.0 * gmgm1 * a0pq - gmgmk * xz - wvno2 * gm1sq * wy;
-  C.c12 = (wvno2 * cpy - cqx) * irho;
-  C.c13 = -(twgm1 * a0pq + gammk * xz + wvno2 * gamm1 * wy) * irho;
-  C.c14 = (cpz - wvno2 * cqw) * irho;
-  C.c15 = -(2.0 * wvno2 * a0pq + xz + wvno2 * wvno2 * wy) * irho2;
-  C.c21 = (gmgmk * cpz - gm1sq * cqw) * rho;
+  // c11 = cpcq - 2 gmgm1 a0pq - gmgmk xz - wvno2 gm1sq wy
+  C.c11 = RFS_FMA(-RFS_MUL(wvno2, gm1sq), wy,
+                  RFS_FMA(-gmgmk, xz, RFS_FMA(-RFS_MUL(2.0, gmgm1), a0pq, cpcq)));
+  C.c12 = RFS_MUL(RFS_FMA(wvno2, cpy, -cqx), irho);
+  // c13 = -(twgm1 a0pq + gammk xz + wvno2 gamm1 wy) / rho
+  C.c13 = -RFS_MUL(RFS_FMA(RFS_MUL(wvno2, gamm1), wy, RFS_FMA(gammk, xz, RFS_MUL(twgm1, a0pq))), irho);
+  C.c14 = RFS_MUL(RFS_FMA(-wvno2, cqw, cpz), irho);
+  // c15 = -(2 wvno2 a0pq + xz + wvno2^2 wy) / rho^2
+  C.c15 = -RFS_MUL(RFS_FMA(RFS_MUL(wvno2, wvno2), wy, RFS_FMA(RFS_MUL(2.0, wvno2), a0pq, xz)), irho2);
+  C.c21 = RFS_MUL(RFS_FMA(gmgmk, cpz, -RFS_MUL(gm1sq, cqw)), rho);
   C.c22 = cpcq;
-  C.c23 = gammk * cpz - gamm1 * cqw;
+  C.c23 = RFS_FMA(gammk, cpz, -RFS_MUL(gamm1, cqw));
   C.c24 = -wz;
-  C.c41 = (gm1sq * cpy - gmgmk * cqx) * rho;
+  C.c41 = RFS_MUL(RFS_FMA(gm1sq, cpy, -RFS_MUL(gmgmk, cqx)), rho);
   C.c42 = -xy;
-  C.c43 = gamm1 * cpy - gammk * cqx;
-  C.c51 = -(2.0 * gmgmk * gm1sq * a0pq + gmgmk * gmgmk * xz + gm1sq * gm1sq * wy) * rho2;
-  C.c53 = -(gammk * gamm1 * twgm1 * a0pq + gam * gammk * gammk * xz + gamm1 * gm1sq * wy) * rho;
+  C.c43 = RFS_FMA(gamm1, cpy, -RFS_MUL(gammk, cqx));
+  // c51 = -(2 gmgmk gm1sq a0pq + gmgmk^2 xz + gm1sq^2 wy) rho^2
+  C.c51 = -RFS_MUL(RFS_FMA(RFS_MUL(gm1sq, gm1sq), wy,
+                           RFS_FMA(RFS_MUL(gmgmk, gmgmk), xz,
+                                   RFS_MUL(RFS_MUL(RFS_MUL(2.0, gmgmk), gm1sq), a0pq))),
+                   rho2);
+  // c53 = -(gammk gamm1 twgm1 a0pq + gam gammk^2 xz + gamm1 gm1sq wy) rho
+  C.c53 = -RFS_MUL(RFS_FMA(RFS_MUL(gamm1, gm1sq), wy,
+                           RFS_FMA(RFS_MUL(gmgmk, gammk), xz,
+                                   RFS_MUL(RFS_MUL(RFS_MUL(gammk, gamm1), twgm1), a0pq))),
+                   rho);
   const double tt = -2.0 * wvno2;
   C.c31 = tt * C.c53;
   C.c32 = tt * C.c43;
@@ -248,11 +262,14 @@ RFS_DEVINL Dunkin dunkin_layer(const MT &M, long long b, int m, double wvno, dou
 // ca(5,2)=c41 ca(5,4)=c21 ca(5,5)=c11; two partial sums per component shorten the chain
 RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2, double &e3,
                              double &e4) {
-  const double n0 = (e0 * C.c11 + e1 * C.c21) + (e2 * C.c31 + e3 * C.c41) + e4 * C.c51;
-  const double n1 = (e0 * C.c12 + e1 * C.c22) + (e2 * C.c32 + e3 * C.c42) + e4 * C.c41;
-  const double n2 = (e0 * C.c13 + e1 * C.c23) + (e2 * C.c33 + e3 * C.c43) + e4 * C.c53;
-  const double n3 = (e0 * C.c14 + e1 * C.c24) + (e2 * C.c34 + e3 * C.c22) + e4 * C.c21;
-  const double n4 = (e0 * C.c15 + e1 * C.c14) + (e2 * C.c35 + e3 * C.c12) + e4 * C.c11;
+#define RFS_ROW(a0_, a1_, a2_, a3_, a4_)                                                      \
+  RFS_FMA(e4, a4_, RFS_ADD(RFS_FMA(e0, a0_, RFS_MUL(e1, a1_)), RFS_FMA(e2, a2_, RFS_MUL(e3, a3_))))
+  const double n0 = RFS_ROW(C.c11, C.c21, C.c31, C.c41, C.c51);
+  const double n1 = RFS_ROW(C.c12, C.c22, C.c32, C.c42, C.c41);
+  const double n2 = RFS_ROW(C.c13, C.c23, C.c33, C.c43, C.c53);
+  const double n3 = RFS_ROW(C.c14, C.c24, C.c34, C.c22, C.c21);
+  const double n4 = RFS_ROW(C.c15, C.c14, C.c35, C.c12, C.c11);
+#undef RFS_ROW
   // max |n_i| on the integer pipe: the bit patterns of non-negative doubles order like unsigned
   // integers (a NaN wins and poisons the vector one layer earlier than fmax would)
 #define RFS_ABSBITS(v) \
@@ -284,11 +301,12 @@ RFS_DEVINL void dunkin_halfspace(const MT &M, long long b, double wvno, double w
   const double gammk = 2.0 * t * t;
   const double gam = gammk * wvno2;
   const double gamm1 = gam - 1.0;
-  e0 = rho1 * rho1 * (gamm1 * gamm1 - gam * gammk * ra * rb);
+  const double rarb = RFS_MUL(ra, rb);
+  e0 = RFS_MUL(RFS_MUL(rho1, rho1), RFS_FMA(-RFS_MUL(gam, gammk), rarb, RFS_MUL(gamm1, gamm1)));
   e1 = -rho1 * ra;
-  e2 = rho1 * (gamm1 - gammk * ra * rb);
+  e2 = RFS_MUL(rho1, RFS_FMA(-gammk, rarb, gamm1));
   e3 = rho1 * rb;
-  e4 = wvno2 - ra * rb;
+  e4 = RFS_SUB(wvno2, rarb);
 }
 // water layer on top (surfdisp96.f:870-886)
 template <class MT>
@@ -298,7 +316,7 @@ RFS_DEVINL double dunkin_water_top(const MT &M, long long b, double wvno, double
   const double xka = omega * M.ld(F_IA, 0, b);
   const VarHalf P = var_half(wvno, xka, (wvno + xka) * fabs(wvno - xka), dpth);
   const double w0 = -rho1 * P.w;
-  return P.c * e0 + w0 * e1;
+  return RFS_FMA(P.c, e0, RFS_MUL(w0, e1));
 }
 template <class MT>
 RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const MT &M, long long b,
@@ -458,17 +476,17 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
           clow = cc;
           ifirst = 1;
         } else if (k == 0 && iq > 1) {
-          c1 = cwork[(long long)(sq.out_off + kb + 0) * stride + b] + one * dc;
+          c1 = RFS_ADD(cwork[(long long)(sq.out_off + kb + 0) * stride + b], RFS_MUL(one, dc));
           clow = c1;
           ifirst = 1;
         } else if (k > 0 && iq > 1) {
           ifirst = 0;
-          clow = cwork[(long long)(sq.out_off + kb + k) * stride + b] + one * dc;
+          clow = RFS_ADD(cwork[(long long)(sq.out_off + kb + k) * stride + b], RFS_MUL(one, dc));
           c1 = cprev;
           if (c1 < clow) c1 = clow;
         } else {
           ifirst = 0;
-          c1 = cprev - onea * dc;
+          c1 = RFS_SUB(cprev, RFS_MUL(onea, dc));
           clow = cm;
         }
         ceval = c1;
@@ -634,7 +652,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
               bad = true;
               break;
             }
-            xs[j] = (-ys[j] * xs[j + 1] + ys[mm] * xs[j]) / denom;
+            xs[j] = RFS_FMA(ys[mm], xs[j], RFS_MUL(-ys[j], xs[j + 1])) / denom;
           }
           if (!bad) {
             c3 = xs[0];

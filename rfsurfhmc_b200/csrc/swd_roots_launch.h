@@ -1,0 +1,30 @@
+// Host-side launchers of the root-search kernels.  The kernels live in their own translation unit
+// (swd_roots_tu.cu), compiled with -fmad=false: there ptxas never contracts a*b+c on its own, so the
+// thread-mapped, team-mapped and retry kernels -- three different inlining contexts of the same
+// secular-function source -- round identically; FMAs appear exactly where the source writes RFS_FMA.
+#pragma once
+#include <cuda_runtime.h>
+#include "swd_plan.cuh"
+
+namespace rfs {
+
+#ifndef RFS_ROOTS_BLOCK
+#define RFS_ROOTS_BLOCK 128
+#endif
+
+// one thread per (model, sequence)
+cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                                const double *periods, int all_modes, double *croot, double *cwork,
+                                int *ierr, unsigned long long *counter, cudaStream_t st);
+// T lanes per (model, sequence), S speculative scan points; false if (T,S) is not instantiated
+bool team_shape_supported(int T, int S);
+cudaError_t launch_roots_team(int T, int S, const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                              const double *periods, int all_modes, double *croot, double *cwork,
+                              int *ierr, unsigned long long *counter, cudaStream_t st);
+// per-period retries of failed fundamental-mode searches (surfdisp.cpp:93-100)
+cudaError_t launch_roots_retry(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                               const double *periods, int all_modes, double *croot, double *cwork,
+                               const int *ierr, int *rstat, unsigned long long *counter,
+                               cudaStream_t st);
+
+}  // namespace rfs

@@ -25,7 +25,8 @@
 // All lanes of a team carry the same state-machine state (uniform control flow inside a team);
 // teams of one warp run their state machines independently (sub-warp masks on every shuffle).
 #pragma once
-#include "swd_kernels.cuh"
+#include "swd_plan.cuh"
+#include "swd_roots_launch.h"
 
 namespace rfs {
 
@@ -255,7 +256,7 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
               bad = true;
               break;
             }
-            xs[j] = (-ys[j] * xs[j + 1] + ys[mm] * xs[j]) / denom;
+            xs[j] = RFS_FMA(ys[mm], xs[j], RFS_MUL(-ys[j], xs[j + 1])) / denom;
           }
           if (!bad) {
             c3 = xs[0];
@@ -329,17 +330,17 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
           clow = cc;
           ifirst = 1;
         } else if (k == 0 && iq > 1) {
-          c1 = cwork[(long long)(sq.out_off + kb + 0) * stride + b] + one * dc;
+          c1 = RFS_ADD(cwork[(long long)(sq.out_off + kb + 0) * stride + b], RFS_MUL(one, dc));
           clow = c1;
           ifirst = 1;
         } else if (k > 0 && iq > 1) {
           ifirst = 0;
-          clow = cwork[(long long)(sq.out_off + kb + k) * stride + b] + one * dc;
+          clow = RFS_ADD(cwork[(long long)(sq.out_off + kb + k) * stride + b], RFS_MUL(one, dc));
           c1 = cprev;
           if (c1 < clow) c1 = clow;
         } else {
           ifirst = 0;
-          c1 = cprev - onea * dc;
+          c1 = RFS_SUB(cprev, RFS_MUL(onea, dc));
           clow = cm;
         }
         ceval = c1;

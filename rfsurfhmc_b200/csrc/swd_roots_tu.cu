@@ -1,0 +1,149 @@
+// Translation unit of the phase-velocity root search (K1 thread-mapped, K1t team-mapped, retry).
+// Compiled with -fmad=false (see swd_roots_launch.h): every kernel in here evaluates the secular
+// function with the same roundings, so all mappings return the same bits.
+#include "swd_roots_team.cuh"
+
+namespace rfs {
+
+// ---- K1: one thread per (model, sequence)
+// croot : [nmode_out][nsolve][B]   cwork : [nsolve][B] (only touched when nmode > 1)
+// ierr  : [nseq][B] int
+#ifndef RFS_ROOTS_MINBLOCKS
+#define RFS_ROOTS_MINBLOCKS 4
+#endif
+#ifndef RFS_ROOTS_BLOCK
+#define RFS_ROOTS_BLOCK 128
+#endif
+__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
+    swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
+                     const double *__restrict__ periods, int all_modes,
+                     double *__restrict__ croot, double *__restrict__ cwork,
+                     int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
+  __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool valid = i < B * plan.nseq;
+  const long long b = valid ? i % B : 0;
+  const int s = valid ? (int)(i / B) : 0;
+  SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
+  unsigned int nev = 0;
+  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
+                                   wsm_all[threadIdx.x >> 5], -1);
+  if (valid) ierr[(long long)s * B + b] = e;
+  if (neval_total) {
+    // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
+    unsigned int w = nev;
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
+    atomicMax(neval_total + 1, (unsigned long long)nev);          // slowest thread
+    if (nev > 2000u) atomicAdd(neval_total + 2, 1ull);            // heavy threads (> 2000 evals)
+  }
+}
+
+// ---- per-period retries of _surfdisp (surfdisp.cpp:93-100): when the fundamental mode failed in
+// the main pass, every period whose reported value is zero / NaN is searched again as a fresh
+// single-period problem (start value cc, scan upward in dc steps: hundreds of evaluations).
+// The reference does these one after the other and stops at the first one that fails again; the
+// jobs are independent, so they run here as one thread per (model, sequence, period) — in a warp
+// that is otherwise idle, whose 31 spare lanes take over the look-ahead scan — and
+// swd_retry_finish_kernel re-imposes the sequential stop rule.
+//   rstat [nsolve][B] int: -1 not retried, 0 retried ok, 1 retried and failed again
+__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
+    swd_retry_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
+                     const double *__restrict__ periods, int all_modes,
+                     double *__restrict__ croot, double *__restrict__ cwork,
+                     const int *__restrict__ ierr, int *__restrict__ rstat,
+                     unsigned long long *__restrict__ neval_total) {
+  __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool inrange = i < B * plan.nsolve;
+  const long long b = inrange ? i % B : 0;
+  const int solve = inrange ? (int)(i / B) : 0;
+  int s = 0;
+  for (int q = 0; q < plan.nseq; q++)
+    if (solve >= plan.seq[q].out_off && solve < plan.seq[q].out_off + plan.seq[q].nper) s = q;
+  const int k = solve - plan.seq[s].out_off;
+  bool valid = false;
+  if (inrange && ierr[(long long)s * B + b] != 0) {
+    const double *clast = croot + (all_modes ? (long long)(plan.nmode - 1) * plan.nsolve * B : 0);
+    const double v = clast[(long long)solve * B + b];
+    valid = (v == 0.0 || isnan(v));
+  }
+  // whole warps without work leave (the warp-cooperative loop needs all 32 lanes of a live warp)
+  if (__ballot_sync(0xffffffffu, valid) == 0u) {
+    if (inrange) rstat[(long long)solve * B + b] = -1;
+    return;
+  }
+  SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
+  unsigned int nev = 0;
+  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
+                                   wsm_all[threadIdx.x >> 5], k);
+  if (inrange) rstat[(long long)solve * B + b] = valid ? e : -1;
+  if (neval_total) {
+    unsigned int w = nev;
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(neval_total, (unsigned long long)w);
+  }
+}
+
+
+static inline unsigned grid_for(long long total, int block) {
+  return (unsigned)((total + block - 1) / block);
+}
+
+cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                                const double *periods, int all_modes, double *croot, double *cwork,
+                                int *ierr, unsigned long long *counter, cudaStream_t st) {
+  swd_roots_kernel<<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
+      P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_roots_retry(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                               const double *periods, int all_modes, double *croot, double *cwork,
+                               const int *ierr, int *rstat, unsigned long long *counter,
+                               cudaStream_t st) {
+  swd_retry_kernel<<<grid_for(B * P.nsolve, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
+      P, blk, B, n, periods, all_modes, croot, cwork, ierr, rstat, counter);
+  return cudaGetLastError();
+}
+
+bool team_shape_supported(int T, int S) {
+  static const int ok[][2] = {{4, 1}, {4, 4}, {8, 1}, {8, 2}, {16, 1}, {16, 2}, {32, 1}, {32, 2}, {32, 4}};
+  for (auto &p : ok)
+    if (p[0] == T && p[1] == S) return true;
+  return false;
+}
+
+template <int T, int S>
+static cudaError_t launch_team(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                               const double *periods, int all_modes, double *croot, double *cwork,
+                               int *ierr, unsigned long long *counter, cudaStream_t st) {
+  // threads per block: as many teams as fit ~64 KB of staged layer parameters
+  int threads = 128;
+  const size_t per_team = sizeof(double) * RFS_TEAM_NF * (size_t)n;
+  while (threads > 32 && threads > T && (threads / T) * per_team > 64 * 1024) threads /= 2;
+  const size_t sm = (threads / T) * per_team;
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(swd_roots_team_kernel<T, S>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+  }
+  swd_roots_team_kernel<T, S><<<grid_for(B * P.nseq, threads / T), threads, sm, st>>>(
+      P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_roots_team(int T, int S, const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                              const double *periods, int all_modes, double *croot, double *cwork,
+                              int *ierr, unsigned long long *counter, cudaStream_t st) {
+#define RFS_TEAM(TT, SS) \
+  if (T == TT && S == SS) return launch_team<TT, SS>(P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter, st);
+  RFS_TEAM(4, 1) RFS_TEAM(4, 4) RFS_TEAM(8, 1) RFS_TEAM(8, 2) RFS_TEAM(16, 1) RFS_TEAM(16, 2)
+  RFS_TEAM(32, 1) RFS_TEAM(32, 2) RFS_TEAM(32, 4)
+#undef RFS_TEAM
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace rfs
