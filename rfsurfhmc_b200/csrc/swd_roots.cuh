@@ -80,14 +80,34 @@ RFS_DEVINL LoveL love_layer(const MT &M, long long b, int m, double wvno, double
   }
   return L;
 }
+// 2^-k for the vector whose largest |component| has the (31-bit, sign stripped) high word h:
+// 2^k <= max < 2^(k+1); 1 when the maximum is zero / denormal / infinite / NaN.  Multiplying by it is
+// exact, so the renormalisation below never rounds.
+RFS_DEVINL double pow2_unscale(int h) {
+  const int be = h >> 20;  // biased exponent of the maximum
+  int sb = 2046 - be;      // biased exponent of 2^-(be-1023)
+  if (be == 0 || be == 2047) sb = 1023;
+  if (sb < 1) sb = 1;
+  return __hiloint2double(sb << 20, 0);
+}
+#define RFS_HIABS(v) (__double2hiint(v) & 0x7fffffff)
+// One layer of the Love recursion.  The reference divides the 2-vector by its max-norm after every
+// layer (surfdisp96.f:778-784); those factors cancel in the final ratio e1/max(|e1|,|e2|), so the vector
+// is only kept in range here by an exact power of two and normalised ONCE at the top (love_finish):
+// same value in exact arithmetic, fewer roundings, and no division on the layer-to-layer critical path.
 RFS_DEVINL void love_apply(const LoveL &L, double &e1, double &e2) {
   // explicit rounding (see RFS_FMA in common.cuh): the same bits from every kernel
   const double e10 = RFS_FMA(e1, L.cosq, RFS_MUL(RFS_MUL(e2, L.xmu), L.z));
   const double e20 = RFS_FMA(e2, L.cosq, RFS_MUL(e1, L.y) / L.xmu);
-  double xnor = fmax(fabs(e10), fabs(e20));
+  const double sc = pow2_unscale(max(RFS_HIABS(e10), RFS_HIABS(e20)));
+  e1 = e10 * sc;
+  e2 = e20 * sc;
+}
+// the normalisation of the last layer step (normc): e1 / max(|e1|, |e2|)
+RFS_DEVINL double love_finish(double e1, double e2) {
+  double xnor = fmax(fabs(e1), fabs(e2));
   if (xnor < 1.e-40) xnor = 1.0;
-  e1 = e10 / xnor;
-  e2 = e20 / xnor;
+  return e1 / xnor;
 }
 template <class MT>
 RFS_DEVINL void love_halfspace(const MT &M, long long b, double wvno, double omega, double &e1,
@@ -109,6 +129,7 @@ RFS_DEVINL double dltar1_dev(double wvno, double omega, const MT &M, long long b
     const LoveL L = love_layer(M, b, m, wvno, omega);
     love_apply(L, e1, e2);
   }
+  if (mmax - 2 >= llw - 1) return love_finish(e1, e2);
   return e1;
 }
 
@@ -258,8 +279,14 @@ RFS_DEVINL Dunkin dunkin_layer(const MT &M, long long b, int m, double wvno, dou
   C.c35 = tt * C.c13;
   return C;
 }
-// e <- normc(e * ca): ee(i) = sum_j e(j) ca(j,i), with ca(2,5)=c14 ca(4,4)=c22 ca(4,5)=c12
-// ca(5,2)=c41 ca(5,4)=c21 ca(5,5)=c11; two partial sums per component shorten the chain
+// e <- e * ca: ee(i) = sum_j e(j) ca(j,i), with ca(2,5)=c14 ca(4,4)=c22 ca(4,5)=c12
+// ca(5,2)=c41 ca(5,4)=c21 ca(5,5)=c11; two partial sums per component shorten the chain.
+// The reference divides the 5-vector by its max-norm after every layer (normc, surfdisp96.f:1013-1040).
+// Those factors cancel: after the last layer the normalised vector is u / max|u| whatever positive
+// scalings were applied on the way.  So the vector is kept in range by an EXACT power of two per layer
+// (integer pipe, no rounding) and normalised once at the top (dunkin_finish): the same value in exact
+// arithmetic, one division per evaluation instead of one per layer, and a layer-to-layer critical path
+// of 4 dependent FP64 operations instead of ~25.
 RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2, double &e3,
                              double &e4) {
 #define RFS_ROW(a0_, a1_, a2_, a3_, a4_)                                                      \
@@ -270,21 +297,27 @@ RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2
   const double n3 = RFS_ROW(C.c14, C.c24, C.c34, C.c22, C.c21);
   const double n4 = RFS_ROW(C.c15, C.c14, C.c35, C.c12, C.c11);
 #undef RFS_ROW
-  // max |n_i| on the integer pipe: the bit patterns of non-negative doubles order like unsigned
-  // integers (a NaN wins and poisons the vector one layer earlier than fmax would)
+  const double sc = pow2_unscale(
+      max(max(max(RFS_HIABS(n0), RFS_HIABS(n1)), max(RFS_HIABS(n2), RFS_HIABS(n3))), RFS_HIABS(n4)));
+  e0 = n0 * sc;
+  e1 = n1 * sc;
+  e2 = n2 * sc;
+  e3 = n3 * sc;
+  e4 = n4 * sc;
+}
+// normc of the last layer step: e0, e1 <- e0 / max|e|, e1 / max|e| (only these two are used afterwards).
+// max |e_i| on the integer pipe: the bit patterns of non-negative doubles order like unsigned integers
+// (a NaN wins and poisons the result).
+RFS_DEVINL void dunkin_finish(double &e0, double &e1, double e2, double e3, double e4) {
 #define RFS_ABSBITS(v) \
   (((unsigned long long)((unsigned)__double2hiint(v) & 0x7fffffffu) << 32) | (unsigned)__double2loint(v))
-  const unsigned long long u0 = RFS_ABSBITS(n0), u1 = RFS_ABSBITS(n1), u2 = RFS_ABSBITS(n2),
-                           u3 = RFS_ABSBITS(n3), u4 = RFS_ABSBITS(n4);
+  const unsigned long long u0 = RFS_ABSBITS(e0), u1 = RFS_ABSBITS(e1), u2 = RFS_ABSBITS(e2),
+                           u3 = RFS_ABSBITS(e3), u4 = RFS_ABSBITS(e4);
 #undef RFS_ABSBITS
   double t1 = __longlong_as_double((long long)max(max(max(u0, u1), max(u2, u3)), u4));
   if (t1 < 1.e-40) t1 = 1.0;
-  const double it1 = 1.0 / t1;
-  e0 = n0 * it1;
-  e1 = n1 * it1;
-  e2 = n2 * it1;
-  e3 = n3 * it1;
-  e4 = n4 * it1;
+  e0 = e0 / t1;
+  e1 = e1 / t1;
 }
 // half-space start vector of dltar4 (surfdisp96.f:815-835)
 template <class MT>
@@ -335,6 +368,7 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const MT &M
     const Dunkin C = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
     dunkin_apply(C, e0, e1, e2, e3, e4);
   }
+  if (mmax - 2 >= llw - 1) dunkin_finish(e0, e1, e2, e3, e4);
   if (llw != 1) return dunkin_water_top(M, b, wvno, omega, e0, e1);
   return e0;
 }

@@ -38,18 +38,42 @@ struct SmemModel {
 };
 #define RFS_TEAM_NF 7  // F_D .. F_IRHO
 
+// layer terms of one warp in shared memory: entry-major [RFS_TEAM_NE][32 lanes], so that the lanes'
+// stores are conflict-free and every lane of a slot reads the same word (broadcast) in the chain
+#define RFS_TEAM_NE 19
+RFS_DEVINL void dunkin_st(double *cm, int col, const Dunkin &C) {
+  const double *v = reinterpret_cast<const double *>(&C);
+#pragma unroll
+  for (int e = 0; e < RFS_TEAM_NE; e++) cm[e * 32 + col] = v[e];
+}
+RFS_DEVINL Dunkin dunkin_ld(const double *cm, int col) {
+  Dunkin C;
+  double *v = reinterpret_cast<double *>(&C);
+#pragma unroll
+  for (int e = 0; e < RFS_TEAM_NE; e++) v[e] = cm[e * 32 + col];
+  return C;
+}
+static_assert(sizeof(Dunkin) == RFS_TEAM_NE * sizeof(double), "Dunkin is stored as 19 doubles");
+
 // Secular function at phase velocity c for this lane's candidate slot; the value is valid in every
 // lane of the slot (lanes slot*GL .. slot*GL+GL-1 of the team).
+//   build : lane g of the slot forms the layer terms of layer base+g and parks them in shared memory;
+//   chain : every lane of the slot then walks the layers in order, reading the parked terms (the next
+//           layer's terms are fetched while the current one is applied) — no data moves between lanes,
+//           and the 5-vector stays in registers with 4 dependent FP64 operations per layer.
+// cm: the warp's [RFS_TEAM_NE][32] parking area; lane: 0..31.
 template <int T, int S>
 RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double omega_in,
-                               double iomega_in, double c, unsigned tmask, int tl) {
+                               double iomega_in, double c, unsigned tmask, int tl, double *cm,
+                               int lane) {
   constexpr int GL = T / S;
   const double wvno = omega_in / c;
   if (GL == 1) {
     return (ifunc == 1) ? dltar1_dev(wvno, omega_in, M, 0, llw)
                         : dltar4_dev(wvno, omega_in, iomega_in, M, 0, llw);
   }
-  const int slot = tl / GL, g = tl % GL;
+  const int g = tl % GL;
+  const int col0 = lane - g;  // column of my slot's first layer lane
   const int mmax = M.n;
   const int nl = mmax - llw;  // finite layers to propagate through: m = mmax-2 ... llw-1
   if (ifunc == 1) {
@@ -57,18 +81,25 @@ RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double om
     love_halfspace(M, 0, wvno, omega_in, e1, e2);
     for (int base = 0; base < nl; base += GL) {
       int li = base + g;
-      if (li > nl - 1) li = nl - 1;  // spare lanes rebuild the last layer (never selected below)
+      if (li > nl - 1) li = nl - 1;  // spare lanes rebuild the last layer (never read below)
       const LoveL L = love_layer(M, 0, mmax - 2 - li, wvno, omega_in);
+      __syncwarp(tmask);  // the previous round has been read
+      cm[0 * 32 + lane] = L.xmu;
+      cm[1 * 32 + lane] = L.cosq;
+      cm[2 * 32 + lane] = L.y;
+      cm[3 * 32 + lane] = L.z;
+      __syncwarp(tmask);
       const int cnt = min(GL, nl - base);
       for (int s = 0; s < cnt; s++) {
-        double n1 = e1, n2 = e2;
-        love_apply(L, n1, n2);
-        const int src = slot * GL + s;
-        e1 = __shfl_sync(tmask, n1, src, T);
-        e2 = __shfl_sync(tmask, n2, src, T);
+        LoveL Ls;
+        Ls.xmu = cm[0 * 32 + col0 + s];
+        Ls.cosq = cm[1 * 32 + col0 + s];
+        Ls.y = cm[2 * 32 + col0 + s];
+        Ls.z = cm[3 * 32 + col0 + s];
+        love_apply(Ls, e1, e2);
       }
     }
-    return e1;
+    return (nl > 0) ? love_finish(e1, e2) : e1;
   }
   double omega = omega_in, iom = iomega_in;
   if (omega < 1.0e-4) {
@@ -82,18 +113,24 @@ RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double om
     int li = base + g;
     if (li > nl - 1) li = nl - 1;
     const Dunkin C = dunkin_layer(M, 0, mmax - 2 - li, wvno, wvno2, omega, iom);
+    __syncwarp(tmask);  // the previous round has been read
+    dunkin_st(cm, lane, C);
+    __syncwarp(tmask);
     const int cnt = min(GL, nl - base);
-    for (int s = 0; s < cnt; s++) {
-      double n0 = e0, n1 = e1, n2 = e2, n3 = e3, n4 = e4;
-      dunkin_apply(C, n0, n1, n2, n3, n4);
-      const int src = slot * GL + s;
-      e0 = __shfl_sync(tmask, n0, src, T);
-      e1 = __shfl_sync(tmask, n1, src, T);
-      e2 = __shfl_sync(tmask, n2, src, T);
-      e3 = __shfl_sync(tmask, n3, src, T);
-      e4 = __shfl_sync(tmask, n4, src, T);
+    // two layers per trip, the second one's terms in flight while the first is applied
+    int s = 0;
+    Dunkin A = dunkin_ld(cm, col0);
+    for (;;) {
+      Dunkin B2 = A;
+      if (s + 1 < cnt) B2 = dunkin_ld(cm, col0 + s + 1);
+      dunkin_apply(A, e0, e1, e2, e3, e4);
+      if (++s >= cnt) break;
+      if (s + 1 < cnt) A = dunkin_ld(cm, col0 + s + 1);
+      dunkin_apply(B2, e0, e1, e2, e3, e4);
+      if (++s >= cnt) break;
     }
   }
+  if (nl > 0) dunkin_finish(e0, e1, e2, e3, e4);
   if (llw != 1) return dunkin_water_top(M, 0, wvno, omega, e0, e1);
   return e0;
 }
@@ -107,7 +144,7 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
                               const double *__restrict__ periods, int nmode, int all_modes,
                               double *__restrict__ cout, long long cout_mode_stride,
                               double *__restrict__ cwork, long long stride, unsigned int &n_evals,
-                              unsigned tmask, int tl, int only_k) {
+                              unsigned tmask, int tl, int only_k, double *park, int lane) {
   constexpr int GL = T / S;
   const int mmax = M.n;
   const int ifunc = sq.ifunc;
@@ -365,7 +402,7 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
         if (spec && slot == j) myc = cand[j];
       }
     }
-    const double myval = team_secular<T, S>(M, ifunc, llw, omega, iomega, myc, tmask, tl);
+    const double myval = team_secular<T, S>(M, ifunc, llw, omega, iomega, myc, tmask, tl, park, lane);
     double vals[S];
     vals[0] = myval;
     if (S > 1) {
@@ -386,7 +423,8 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
 }
 
 // ---- K1t: T lanes per (model, sequence); blockDim.x / T teams per block
-// dynamic shared memory: (blockDim.x / T) * RFS_TEAM_NF * n doubles
+// dynamic shared memory: (blockDim.x / T) * RFS_TEAM_NF * n doubles (staged models)
+//                        + (blockDim.x / 32) * RFS_TEAM_NE * 32 doubles (parked layer terms)
 template <int T, int S>
 __global__ void __launch_bounds__(128)
     swd_roots_team_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
@@ -414,10 +452,11 @@ __global__ void __launch_bounds__(128)
   if (!valid) return;
   const int lane = threadIdx.x & 31;
   const unsigned tmask = (T >= 32) ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
+  double *cm = team_sm + (size_t)tpb * RFS_TEAM_NF * n + (size_t)(threadIdx.x >> 5) * RFS_TEAM_NE * 32;
   SmemModel M{lp, n};
   unsigned int nev = 0;
   const int e = swd_solve_team<T, S>(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                     (long long)plan.nsolve * B, cwork, B, nev, tmask, tl, -1);
+                                     (long long)plan.nsolve * B, cwork, B, nev, tmask, tl, -1, cm, lane);
   if (tl == 0) {
     ierr[(long long)s * B + b] = e;
     if (neval_total) {
