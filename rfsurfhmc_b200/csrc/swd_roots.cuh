@@ -81,13 +81,11 @@ RFS_DEVINL LoveL love_layer(const MT &M, long long b, int m, double wvno, double
   return L;
 }
 // 2^-k for the vector whose largest |component| has the (31-bit, sign stripped) high word h:
-// 2^k <= max < 2^(k+1); 1 when the maximum is zero / denormal / infinite / NaN.  Multiplying by it is
-// exact, so the renormalisation below never rounds.
+// 2^k <= max < 2^(k+1).  Multiplying by it is exact, so the renormalisation below never rounds.
 RFS_DEVINL double pow2_unscale(int h) {
-  const int be = h >> 20;  // biased exponent of the maximum
-  int sb = 2046 - be;      // biased exponent of 2^-(be-1023)
-  if (be == 0 || be == 2047) sb = 1023;
-  if (sb < 1) sb = 1;
+  // biased exponent of 2^-(be-1023) for the maximum's biased exponent be = h >> 20, kept >= 1: a zero
+  // or denormal maximum is scaled by 2^1023 (exact, still below 2), inf / NaN stay what they are
+  const int sb = max(2046 - (h >> 20), 1);
   return __hiloint2double(sb << 20, 0);
 }
 #define RFS_HIABS(v) (__double2hiint(v) & 0x7fffffff)
@@ -316,8 +314,9 @@ RFS_DEVINL void dunkin_finish(double &e0, double &e1, double e2, double e3, doub
 #undef RFS_ABSBITS
   double t1 = __longlong_as_double((long long)max(max(max(u0, u1), max(u2, u3)), u4));
   if (t1 < 1.e-40) t1 = 1.0;
-  e0 = e0 / t1;
-  e1 = e1 / t1;
+  const double it1 = 1.0 / t1;
+  e0 = e0 * it1;
+  e1 = e1 * it1;
 }
 // half-space start vector of dltar4 (surfdisp96.f:815-835)
 template <class MT>

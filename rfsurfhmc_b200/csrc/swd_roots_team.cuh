@@ -38,19 +38,26 @@ struct SmemModel {
 };
 #define RFS_TEAM_NF 7  // F_D .. F_IRHO
 
-// layer terms of one warp in shared memory: entry-major [RFS_TEAM_NE][32 lanes], so that the lanes'
-// stores are conflict-free and every lane of a slot reads the same word (broadcast) in the chain
+// layer terms of one warp in shared memory: pairs of entries, pair-major [RFS_TEAM_NP][32 lanes] double2,
+// so that the lanes' 128-bit stores are conflict-free and every lane of a slot reads the same 16 bytes
+// (broadcast) in the chain
 #define RFS_TEAM_NE 19
-RFS_DEVINL void dunkin_st(double *cm, int col, const Dunkin &C) {
+#define RFS_TEAM_NP 10
+RFS_DEVINL void dunkin_st(double2 *cm, int col, const Dunkin &C) {
   const double *v = reinterpret_cast<const double *>(&C);
 #pragma unroll
-  for (int e = 0; e < RFS_TEAM_NE; e++) cm[e * 32 + col] = v[e];
+  for (int p = 0; p < RFS_TEAM_NP; p++)
+    cm[p * 32 + col] = make_double2(v[2 * p], (2 * p + 1 < RFS_TEAM_NE) ? v[2 * p + 1] : 0.0);
 }
-RFS_DEVINL Dunkin dunkin_ld(const double *cm, int col) {
+RFS_DEVINL Dunkin dunkin_ld(const double2 *cm, int col) {
   Dunkin C;
   double *v = reinterpret_cast<double *>(&C);
 #pragma unroll
-  for (int e = 0; e < RFS_TEAM_NE; e++) v[e] = cm[e * 32 + col];
+  for (int p = 0; p < RFS_TEAM_NP; p++) {
+    const double2 t = cm[p * 32 + col];
+    v[2 * p] = t.x;
+    if (2 * p + 1 < RFS_TEAM_NE) v[2 * p + 1] = t.y;
+  }
   return C;
 }
 static_assert(sizeof(Dunkin) == RFS_TEAM_NE * sizeof(double), "Dunkin is stored as 19 doubles");
@@ -61,10 +68,10 @@ static_assert(sizeof(Dunkin) == RFS_TEAM_NE * sizeof(double), "Dunkin is stored 
 //   chain : every lane of the slot then walks the layers in order, reading the parked terms (the next
 //           layer's terms are fetched while the current one is applied) — no data moves between lanes,
 //           and the 5-vector stays in registers with 4 dependent FP64 operations per layer.
-// cm: the warp's [RFS_TEAM_NE][32] parking area; lane: 0..31.
+// cm: the warp's [RFS_TEAM_NP][32] double2 parking area; lane: 0..31.
 template <int T, int S>
 RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double omega_in,
-                               double iomega_in, double c, unsigned tmask, int tl, double *cm,
+                               double iomega_in, double c, unsigned tmask, int tl, double2 *cm,
                                int lane) {
   constexpr int GL = T / S;
   const double wvno = omega_in / c;
@@ -84,18 +91,17 @@ RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double om
       if (li > nl - 1) li = nl - 1;  // spare lanes rebuild the last layer (never read below)
       const LoveL L = love_layer(M, 0, mmax - 2 - li, wvno, omega_in);
       __syncwarp(tmask);  // the previous round has been read
-      cm[0 * 32 + lane] = L.xmu;
-      cm[1 * 32 + lane] = L.cosq;
-      cm[2 * 32 + lane] = L.y;
-      cm[3 * 32 + lane] = L.z;
+      cm[0 * 32 + lane] = make_double2(L.xmu, L.cosq);
+      cm[1 * 32 + lane] = make_double2(L.y, L.z);
       __syncwarp(tmask);
       const int cnt = min(GL, nl - base);
       for (int s = 0; s < cnt; s++) {
+        const double2 a = cm[0 * 32 + col0 + s], bq = cm[1 * 32 + col0 + s];
         LoveL Ls;
-        Ls.xmu = cm[0 * 32 + col0 + s];
-        Ls.cosq = cm[1 * 32 + col0 + s];
-        Ls.y = cm[2 * 32 + col0 + s];
-        Ls.z = cm[3 * 32 + col0 + s];
+        Ls.xmu = a.x;
+        Ls.cosq = a.y;
+        Ls.y = bq.x;
+        Ls.z = bq.y;
         love_apply(Ls, e1, e2);
       }
     }
@@ -117,17 +123,19 @@ RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double om
     dunkin_st(cm, lane, C);
     __syncwarp(tmask);
     const int cnt = min(GL, nl - base);
-    // two layers per trip, the second one's terms in flight while the first is applied
+    // two layers per trip: both layers' terms are fetched first, so the second fetch is in flight while
+    // the first layer is applied (no register copies: an odd count peels its first layer)
     int s = 0;
-    Dunkin A = dunkin_ld(cm, col0);
-    for (;;) {
-      Dunkin B2 = A;
-      if (s + 1 < cnt) B2 = dunkin_ld(cm, col0 + s + 1);
+    if (cnt & 1) {
+      const Dunkin A = dunkin_ld(cm, col0);
       dunkin_apply(A, e0, e1, e2, e3, e4);
-      if (++s >= cnt) break;
-      if (s + 1 < cnt) A = dunkin_ld(cm, col0 + s + 1);
+      s = 1;
+    }
+    for (; s < cnt; s += 2) {
+      const Dunkin A = dunkin_ld(cm, col0 + s);
+      const Dunkin B2 = dunkin_ld(cm, col0 + s + 1);
+      dunkin_apply(A, e0, e1, e2, e3, e4);
       dunkin_apply(B2, e0, e1, e2, e3, e4);
-      if (++s >= cnt) break;
     }
   }
   if (nl > 0) dunkin_finish(e0, e1, e2, e3, e4);
@@ -144,7 +152,7 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
                               const double *__restrict__ periods, int nmode, int all_modes,
                               double *__restrict__ cout, long long cout_mode_stride,
                               double *__restrict__ cwork, long long stride, unsigned int &n_evals,
-                              unsigned tmask, int tl, int only_k, double *park, int lane) {
+                              unsigned tmask, int tl, int only_k, double2 *park, int lane) {
   constexpr int GL = T / S;
   const int mmax = M.n;
   const int ifunc = sq.ifunc;
@@ -424,7 +432,7 @@ RFS_DEVINL int swd_solve_team(const SmemModel &M, long long b, const SwdSeq &sq,
 
 // ---- K1t: T lanes per (model, sequence); blockDim.x / T teams per block
 // dynamic shared memory: (blockDim.x / T) * RFS_TEAM_NF * n doubles (staged models)
-//                        + (blockDim.x / 32) * RFS_TEAM_NE * 32 doubles (parked layer terms)
+//                        + (blockDim.x / 32) * RFS_TEAM_NP * 32 double2 (parked layer terms)
 template <int T, int S>
 __global__ void __launch_bounds__(128)
     swd_roots_team_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
@@ -452,7 +460,10 @@ __global__ void __launch_bounds__(128)
   if (!valid) return;
   const int lane = threadIdx.x & 31;
   const unsigned tmask = (T >= 32) ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
-  double *cm = team_sm + (size_t)tpb * RFS_TEAM_NF * n + (size_t)(threadIdx.x >> 5) * RFS_TEAM_NE * 32;
+  // parked layer terms behind the staged models, 16-byte aligned
+  const size_t model_doubles = ((size_t)tpb * RFS_TEAM_NF * n + 1) & ~(size_t)1;
+  double2 *cm = reinterpret_cast<double2 *>(team_sm + model_doubles) +
+                (size_t)(threadIdx.x >> 5) * RFS_TEAM_NP * 32;
   SmemModel M{lp, n};
   unsigned int nev = 0;
   const int e = swd_solve_team<T, S>(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,

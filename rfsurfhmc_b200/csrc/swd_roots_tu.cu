@@ -124,7 +124,8 @@ static cudaError_t launch_team(const SwdPlan &P, const SwdBlocks &blk, long long
   int threads = 128;
   const size_t per_team = sizeof(double) * RFS_TEAM_NF * (size_t)n;
   while (threads > 32 && threads > T && (threads / T) * per_team > 64 * 1024) threads /= 2;
-  const size_t sm = (threads / T) * per_team + (size_t)(threads / 32) * RFS_TEAM_NE * 32 * sizeof(double);
+  const size_t sm = (((threads / T) * per_team + 15) & ~(size_t)15) +
+                    (size_t)(threads / 32) * RFS_TEAM_NP * 32 * sizeof(double2);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(swd_roots_team_kernel<T, S>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

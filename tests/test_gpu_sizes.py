@@ -84,11 +84,27 @@ def test_c2_swd_sizes_modes_0_to_2(ctx, oracle):
         ok = np.isfinite(da) & (da != 0) & f3[:, None] & per_mode[im][3][:, None] & np.isfinite(blk) & (blk != 0)
         e = np.abs(blk - da)[ok] / np.abs(da[ok])
         assert np.mean(e <= TOL_C) >= 0.999 and e.max() <= 1e-3, im
+    # gradient of the three-mode objective: at these periods (up to 100 s) modes 1 and 2 are cut off for
+    # every model, so the reference semantics make the gradient NaN everywhere -- on both sides
     gsum = per_mode[0][1] + per_mode[1][1] + per_mode[2][1]
-    fin = np.isfinite(gsum).all(axis=1) & f_all & np.isfinite(g3).all(axis=1)
-    assert fin.sum() > 0
-    eg = grad_err(g3[fin], gsum[fin])
-    assert np.mean(eg <= TOL_G) >= 0.99 and eg.max() <= 1e-2
+    assert np.array_equal(np.isfinite(gsum).all(axis=1) & f_all, np.isfinite(g3).all(axis=1) & f_all)
+    # ... and on short periods, where all three modes exist, it is the sum of the per-mode gradients
+    Ts = np.geomspace(2, 5, 16)
+    Xs = X[:256]
+    dob = np.full(3 * 64, 3.2)
+    ctx.config_swd(n, Ts, Ts, Ts, Ts, mode=[0, 1, 2])
+    ctx.config_obs(dob)
+    Us, gs_, ds_, fs_ = ctx.misfit_grad_host(Xs, which=2)
+    Uo, go = 0.0, 0.0
+    for mode in (0, 1, 2):
+        r = oracle.joint_batch(Xs, dob[:64], dict(base, tRc=Ts, tRg=Ts, tLc=Ts, tLg=Ts, mode=mode), which=2,
+                               nthreads=NTH)
+        Uo, go = Uo + r[0], go + r[1]
+    fin = np.isfinite(go).all(axis=1) & np.isfinite(gs_).all(axis=1) & fs_
+    assert fin.mean() > 0.5, fin.mean()
+    eg = grad_err(gs_[fin], go[fin])
+    assert np.mean(eg <= TOL_G) >= 0.99 and eg.max() <= 1e-2, eg.max()
+    assert rel(Us[fin], Uo[fin]) <= 1e-5
     # ---- all_modes drop-in (libsurf.adjoint_kernel semantics per mode)
     vs, thk = X[:64, :n], X[:64, n:]
     vp, rho = brocher(vs)
