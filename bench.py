@@ -189,7 +189,7 @@ def config_legs(torch, dev_index, ncores, hbm_peak, fp64_peak, with_cpu=True):
            "value": B / sec, "unit": "models/s", "seconds": sec, "failed_models": nfail, "gpu_launches": nl,
            "kernels": _kernel_table(prof), "root_search_mapping": list(ctx.last_roots_team())}
     if with_cpu:
-        Xc = X[:32 * ncores]
+        Xc = X[:96 * ncores]
         base = dict(tRc=T, tRg=T, tLc=T, tLg=T, ray_p=0.06, nt=64, dt=0.1, gauss=2.5, time_shift=5.0)
         t0 = time.perf_counter()
         for mode in (0, 1, 2):
@@ -224,7 +224,7 @@ def config_legs(torch, dev_index, ncores, hbm_peak, fp64_peak, with_cpu=True):
                        "ray parameters 0.04/0.06/0.08 as one objective (6144 data), batch %d" % B,
            "value": B / sec, "unit": "models/s", "seconds": sec, "gpu_launches": nl, "kernels": kt}
     if with_cpu:
-        Xc = X[:4 * ncores]
+        Xc = X[:20 * ncores]
         base = dict(nt=nt, dt=0.05, gauss=2.5, time_shift=5.0, water=1e-3, rf_type="P", method="freq")
         t0 = time.perf_counter()
         for p in rays[:1]:
@@ -284,7 +284,7 @@ def config_legs(torch, dev_index, ncores, hbm_peak, fp64_peak, with_cpu=True):
            "finite_grad_fraction": float(torch.isfinite(res[1]).all(dim=1).float().mean().item()),
            "kernels": _kernel_table(prof), "root_search_mapping": list(ctx.last_roots_team())}
     if with_cpu:
-        Xc = X[:8 * ncores]
+        Xc = X[:40 * ncores]
         cfg5 = dict(tRc=T, tRg=T, ray_p=0.06, nt=256, dt=0.025 * 16, gauss=2.5, time_shift=5.0, water=1e-3,
                     rf_type="P", method="freq")
         t0 = time.perf_counter()
