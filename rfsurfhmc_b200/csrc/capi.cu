@@ -407,7 +407,10 @@ int run_rf_decon(rfs_ctx *ctx, long long B, int nrow, const double *d_dobs, doub
   return RFS_OK;
 }
 
-size_t time_smem(int nft, int n2) { return sizeof(double) * (2 * (size_t)nft + 8 * (size_t)n2 + 64); }
+size_t time_smem(int nft, int n2) { return sizeof(double) * (2 * (size_t)nft + 5 * (size_t)n2 + 64); }
+// one radix-4 butterfly per thread in the half-length transform (two at nft = 4096); 256-thread blocks
+// of 74 KB: three per SM at nft = 2048
+int time_threads(int nft) { return std::max(64, std::min(256, nft / 8)); }
 
 // time-domain method: iterative deconvolution of the spectra in w_spec / w_dspec (sigma = 0)
 // nrow = 0 (receiver function only) or 4n (plus all Frechet traces -> w_rftr [B][4n][nt])
@@ -423,7 +426,7 @@ int run_rf_time(rfs_ctx *ctx, long long B, int nrow, double *d_rf, long long ldr
     CK(cudaFuncSetAttribute(rf_time_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                             cudaSharedmemCarveoutMaxShared));
   }
-  LAUNCH(rf_time_kernel, (unsigned)(B * (nrow + 1)), decon_threads(ctx->nft), sm, st,
+  LAUNCH(rf_time_kernel, (unsigned)(B * (nrow + 1)), time_threads(ctx->nft), sm, st,
          (const double2 *)ctx->w_spec.p, (const double2 *)ctx->w_dspec.p, B, nrow, ctx->nt, ctx->nft,
          ctx->logn, ctx->dt, ctx->gauss, tshift, d_rf, ldrf, (double *)ctx->w_rftr.p,
          (const double2 *)ctx->d_tw.p);

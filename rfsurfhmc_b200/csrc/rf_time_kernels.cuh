@@ -17,29 +17,22 @@
 
 namespace rfs {
 
-// Parseval power of a real signal from its half spectrum: sum_t x_t^2 with x = irfft(X) (1/N incl.)
-RFS_DEVINL double half_power(const cd *X, int N, double *red) {
-  double l = 0.0;
-  for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
-    const double w = (k == 0 || k == N / 2) ? 1.0 : 2.0;
-    l += w * norm2(X[k]);
-  }
-  return block_reduce(l, red, false) / (double)N;
-}
-
-// dynamic smem: cd buf[nft] + cd Uf[n2] + cd Wf[n2] + double2 twiddle[n2] + cd P[n2] + 64 doubles
-__global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
+// Everything the iteration needs of u and w are two products: UW = U conj(W) and W2 = |W|^2:
+//   cross-correlation spectrum   R conj(W) = UW - dt W2 P              (R = U - dt P W)
+//   residual power (Parseval)    sum |R|^2 = sum |U|^2 - 2 dt Re(P conj(UW)) + dt^2 |P|^2 W2
+// dynamic smem: cd buf[nft] + cd UW[n2] + cd P[n2] + double W2[n2] + 64 doubles   (74 KB at nft = 2048:
+// three blocks per SM; the twiddle table stays in global memory / L1)
+__global__ void __launch_bounds__(256, 3) rf_time_kernel(const double2 *__restrict__ spec, const double2 *__restrict__ dspec,
                                long long B, int nrow, int nt, int nft, int logn, double dt,
                                double f0, double tshift, double *__restrict__ rf, long long ldrf,
                                double *__restrict__ traces, const double2 *__restrict__ tw) {
   extern __shared__ double smem[];
   const int n2 = nft / 2 + 1;
   cd *buf = reinterpret_cast<cd *>(smem);
-  cd *Uf = buf + nft;
-  cd *Wf = Uf + n2;
-  double2 *tws = reinterpret_cast<double2 *>(Wf + n2);  // twiddle table, nft/2 entries
-  cd *P = Wf + 2 * n2;
-  double *red = reinterpret_cast<double *>(P + n2);
+  cd *UW = buf + nft;
+  cd *P = UW + n2;
+  double *W2 = reinterpret_cast<double *>(P + n2);
+  double *red = W2 + n2;
   const int nrow1 = nrow + 1;
   const long long b = blockIdx.x / nrow1;
   const int r = (int)(blockIdx.x % nrow1);
@@ -47,6 +40,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
   const double minderr = (double)0.001f;
 
   // ---- spectra of u and w (the reference goes through the time domain: c2r drops Im of bins 0, N/2)
+  double lpu = 0.0, lpw = 0.0;
   for (int k = tid; k < n2; k += nth) {
     const double2 a21 = spec[(b * 2 + 0) * n2 + k], a22 = spec[(b * 2 + 1) * n2 + k];
     cd su, sw;
@@ -66,14 +60,18 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     const double freq = (double)k / (nft * dt);
     const double gx = 2 * RFS_PI32 * freq / f0;
     const double g = exp(-0.25 * (gx * gx));
-    Uf[k] = su * g;
-    Wf[k] = sw * g;  // also G * rfft(wcopy): the factor G of apply_gaussian(temp1) is the same g
+    const cd Uf = su * g;
+    const cd Wf = sw * g;  // also G * rfft(wcopy): the factor G of apply_gaussian(temp1) is the same g
+    const double wgt = (k == 0 || k == nft / 2) ? 1.0 : 2.0;
+    lpu += wgt * norm2(Uf);
+    lpw += wgt * norm2(Wf);
+    UW[k] = Uf * conj(Wf);
+    W2[k] = norm2(Wf);
     P[k] = cd(0.0, 0.0);
-    if (k < nft / 2) tws[k] = tw[k];
   }
-  __syncthreads();
-  const double pw = half_power(Wf, nft, red);
-  const double pu = half_power(Uf, nft, red);
+  const double su2 = block_reduce(lpu, red, false);  // sum_k w_k |U_k|^2 = N * sum_t u_t^2
+  const double pw = block_reduce(lpw, red, false) / (double)nft;
+  const double pu = su2 / (double)nft;
   const double invpw = 1. / pw / dt;
   const double invpu = 1. / pu / dt;
   double sumsq_i = 1.0;
@@ -81,12 +79,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
   for (int it = 1; it <= 200; it++) {
     if (fabs(d_error) <= minderr) break;
     // cuw = irfft( rfft(rflt) conj(rfft(wflt)) ) dt ,  rfft(rflt) = Uf - dt P Wc
-    const cd *z = block_irfft<true>(
-        [&](int k) {
-          const cd R = Uf[k] - dt * (P[k] * Wf[k]);
-          return R * conj(Wf[k]);
-        },
-        buf, nft, logn, tws);
+    const cd *z = block_irfft<false>([&](int k) { return UW[k] - (dt * W2[k]) * P[k]; }, buf, nft, logn, tw);
     // first maximum of |cuw| over the first nft/2 lags (maxloc, deconit.f90:178)
     double best = -1.0;
     int bi = 0x7fffffff;
@@ -133,18 +126,16 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     // P += amp * rfft(delta_idx);  new residual power by Parseval
     double l = 0.0;
     for (int k = tid; k < n2; k += nth) {
-      // exp(-2 pi i k idx / nft) from the twiddle table (second half of the circle by symmetry)
+      // exp(-2 pi i k idx / nft) from the twiddle table
       const int kk = (k * idx) & (nft - 1);  // nft is a power of two, k*idx < 2^24
-      const int hN = nft >> 1;
-      const double2 tf = tws[kk < hN ? kk : kk - hN];
-      const cd ph = (kk < hN) ? cd(tf.x, tf.y) : cd(-tf.x, -tf.y);
+      const cd ph = tw_lookup<false>(tw, kk, nft, -1);
       const cd pk = P[k] + amp * ph;
       P[k] = pk;
-      const cd R = Uf[k] - dt * (pk * Wf[k]);
+      const cd uw = UW[k];
       const double w = (k == 0 || k == nft / 2) ? 1.0 : 2.0;
-      l += w * (k == 0 || k == nft / 2 ? R.x * R.x : norm2(R));
+      l += w * (dt * W2[k] * norm2(pk) - 2.0 * (pk.x * uw.x + pk.y * uw.y));
     }
-    const double sumsq = block_reduce(l, red, false) / (double)nft * dt * invpu;
+    const double sumsq = (su2 + dt * block_reduce(l, red, false)) / (double)nft * dt * invpu;
     d_error = 100. * (sumsq_i - sumsq);
     sumsq_i = sumsq;
   }
@@ -158,7 +149,7 @@ __global__ void __launch_bounds__(512, 2) rf_time_kernel(const double2 *__restri
     P[k] = pk * cis(-((double)k / (nft * dt) * RFS_PI32 * 2 * tshift));
   }
   __syncthreads();
-  const cd *z = block_irfft<true>([&](int k) { return P[k]; }, buf, nft, logn, tws);
+  const cd *z = block_irfft<false>([&](int k) { return P[k]; }, buf, nft, logn, tw);
   double *dst = (r == 0) ? rf + b * ldrf : traces + (b * (long long)nrow + (r - 1)) * nt;
   for (int t = tid; t < nt; t += nth) dst[t] = irfft_at(z, t) / nft;
 }
