@@ -359,6 +359,10 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    # the contract is ONE line on stdout: library chatter (e.g. "NCCL version ...") goes to stderr
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from rfsurfhmc_b200._lib import Context
@@ -486,6 +490,8 @@ def main():
             ctx.config_obs(d)
             ho = ctx.hmc_run(sampler_id, ids, bounds, want_samples=False, want_syn=False, **kw)
             torch.cuda.synchronize()
+            t1a = time.perf_counter()
+            barrier()                      # ranks finish at different times: wait here, not inside the gather
             t1 = time.perf_counter()
             mis = Dm.gather_chains(ho["misfit"], total_chains)
             nit = Dm.gather_chains(ho["n_iter"], total_chains)
@@ -495,7 +501,7 @@ def main():
             barrier()
             t3 = time.perf_counter()
             complete = int((ho["n_acc"] >= kw["nsamples"] + kw["ndraws"]).sum()) if kw.get("max_iters", 0) == 0 else None
-            return {"t": t3 - t0, "t_gather": t2 - t1, "traj": float(nit.sum()), "acc": float(nac.sum()),
+            return {"t": t3 - t0, "t_gather": t2 - t1, "t_wait": t1 - t1a, "traj": float(nit.sum()), "acc": float(nac.sum()),
                     "evals": float(ho["evals"]), "steps": float(ho["global_steps"]), "chains": total_chains,
                     "misfit_shape": list(mis.shape), "complete_local": complete, "local_chains": len(ids)}
 
@@ -528,7 +534,7 @@ def main():
     if hmc is not None:
         hmc_out = {}
         for name, L in hmc.items():
-            vmax = torch.tensor([L["t"], L["t_gather"]], dtype=torch.float64, device=dev)
+            vmax = torch.tensor([L["t"], L["t_gather"], L["t_wait"]], dtype=torch.float64, device=dev)
             vsum = torch.tensor([L["evals"]], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
@@ -537,7 +543,8 @@ def main():
             hmc_out[name] = {"chains_total": L["chains"], "seconds": t, "trajectories_per_s": L["traj"] / t,
                              "accepted_samples_per_s": L["acc"] / t, "evals_per_s": float(vsum[0]) / t,
                              "global_steps_rank0": L["steps"],
-                             "nccl_gather_ms": 1e3 * float(vmax[1]), "gathered_misfit_shape": L["misfit_shape"]}
+                             "nccl_gather_ms": 1e3 * float(vmax[1]), "rank_imbalance_wait_ms": 1e3 * float(vmax[2]),
+                             "gathered_misfit_shape": L["misfit_shape"]}
         desc = {"c4_strong": "HamitonianMC, L=20, dt=0.02, 16 384 chains in total sharded over the GPUs (strong "
                              "scaling), %d trajectories per chain; includes chain initialisation, the NCCL "
                              "broadcast of the observations and the all-gathers of misfit / counters" % args.hmc_traj,
@@ -630,7 +637,10 @@ def main():
                                      "root_search_mapping": {"T": strong[2][0], "S": strong[2][1]},
                                      "note": "BASELINE config 4: 16 384 chains in total sharded over the GPUs; "
                                              "compare with `value` of the N=1 run"}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
     return 0
