@@ -933,28 +933,33 @@ static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const 
                      double ray_p, int nt, double dt, double gauss, double time_shift, int method,
                      double water, int rf_type, int par_type, int nq, double *rf, double *drf) {
   if (!ctx) return RFS_E_ARG;
-  // drop-in calls must not disturb the fused-path configuration: save / restore the RF fields
-  struct RfSave {
+  // drop-in calls must not disturb the fused-path configuration: the RF fields are restored when this
+  // guard leaves scope, on every return path (the CK / LAUNCH macros return directly on a CUDA error)
+  struct RfRestore {
+    rfs_ctx *c;
     int n_rf, nt, nft, logn, n2, rf_type, method;
     double ray_p, dt, gauss, tshift, water;
-  } saved = {ctx->n_rf, ctx->nt, ctx->nft, ctx->logn, ctx->n2, ctx->rf_type, ctx->method,
-             ctx->ray_p, ctx->dt, ctx->gauss, ctx->tshift, ctx->water};
+    explicit RfRestore(rfs_ctx *x)
+        : c(x), n_rf(x->n_rf), nt(x->nt), nft(x->nft), logn(x->logn), n2(x->n2), rf_type(x->rf_type),
+          method(x->method), ray_p(x->ray_p), dt(x->dt), gauss(x->gauss), tshift(x->tshift),
+          water(x->water) {}
+    ~RfRestore() {
+      c->n_rf = n_rf;
+      c->nt = nt;
+      c->nft = nft;
+      c->logn = logn;
+      c->n2 = n2;
+      c->rf_type = rf_type;
+      c->method = method;
+      c->ray_p = ray_p;
+      c->dt = dt;
+      c->gauss = gauss;
+      c->tshift = tshift;
+      c->water = water;
+    }
+  } restore_guard(ctx);
   int rc = set_rf_cfg(ctx, n, ray_p, nt, dt, gauss, time_shift, water, rf_type, method);
-  auto done = [&](int code) {
-    ctx->n_rf = saved.n_rf;
-    ctx->nt = saved.nt;
-    ctx->nft = saved.nft;
-    ctx->logn = saved.logn;
-    ctx->n2 = saved.n2;
-    ctx->rf_type = saved.rf_type;
-    ctx->method = saved.method;
-    ctx->ray_p = saved.ray_p;
-    ctx->dt = saved.dt;
-    ctx->gauss = saved.gauss;
-    ctx->tshift = saved.tshift;
-    ctx->water = saved.water;
-    return code;
-  };
+  auto done = [&](int code) { return code; };
   if (rc) return done(rc);
   if (nq == 1 && (par_type < 1 || par_type > 4))
     return done(fail(ctx, RFS_E_ARG, "par_type should be one of [vp,vs,rho,thick]"));
