@@ -336,9 +336,11 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
   if ((rc = ensure(ctx, ctx->w_kern, sizeof(double) * (size_t)nmo * P.nsolve * 4 * n * B)))
     return rc;
   const long long tot = B * P.nsolve * nmo;
+  // NMAX = 8: the Rayleigh up-sweep vectors live in shared memory ([48][128] doubles per block)
 #define EIG(NM)                                                                                 \
-  LAUNCH(swd_eigen_kernel<NM>, gridFor(tot, 128), 128, 0, st, P, d_swd, B, n, d_periods, nmo,  \
-         (const double *)ctx->w_croot.p, (double *)ctx->w_ugr.p, (double *)ctx->w_kern.p)
+  LAUNCH(swd_eigen_kernel<NM>, gridFor(tot, 128), 128, (NM <= 8 ? 128 * NM * 6 * sizeof(double) : 0), st, \
+         P, d_swd, B, n, d_periods, nmo, (const double *)ctx->w_croot.p, (double *)ctx->w_ugr.p,       \
+         (double *)ctx->w_kern.p)
   switch (nmax_for(n)) {
     case 8: EIG(8); break;
     case 16: EIG(16); break;

@@ -205,7 +205,13 @@ __global__ void __launch_bounds__(128, RFS_EIGEN_MINBLOCKS)
     for (int j = 0; j < 4 * n; j++) kp[(long long)j * B] = qnan;
     u = qnan;
   } else if (sq.ifunc == 2) {
-    rayleigh_solve<NMAX>(M, b, T, c, &u, kp, B);
+    if constexpr (NMAX <= 8) {
+      // up-sweep vectors of the block in shared memory: [NMAX*6][blockDim.x] doubles (48 KB at 128 threads)
+      extern __shared__ double eig_cd[];
+      rayleigh_solve<NMAX, true>(M, b, T, c, &u, kp, B, eig_cd + threadIdx.x, (int)blockDim.x);
+    } else {
+      rayleigh_solve<NMAX, false>(M, b, T, c, &u, kp, B);
+    }
   } else {
     love_solve<NMAX>(M, b, T, c, &u, kp, B);
   }

@@ -152,18 +152,28 @@ struct Eig4 {
 
 // Output of one Rayleigh solve.  kern points at [4][n] doubles with element stride `ks`
 // (order: dcda, dcdb, dcdr, dcdh), dcdh already converted to d/d(thickness) (suffix sums).
-template <int NMAX>
+// SHARED_CD: the up-sweep vectors live in shared memory as cds[(m*6+j)*cstride] (this thread's
+// column of a [NMAX*6][blockDim] array: conflict-free) and the varsv terms are recomputed in the
+// down-sweep instead of being parked in thread-local memory (1 152 B per thread at NMAX = 8: with
+// 1.8 M threads per launch that spilled 1.7 GB to DRAM per evaluation).  Otherwise: thread-local.
+template <int NMAX, bool SHARED_CD = false>
 RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double c, double *ugr_out,
-                               double *__restrict__ kern, long long ks) {
+                               double *__restrict__ kern, long long ks, double *cds = nullptr,
+                               int cstride = 1) {
   const int mmax = M.n;
   const double omega = (2.0 * RFS_PI32) / T;
   const double wvno = omega / c;
   const double wvno2 = wvno * wvno, om2 = omega * omega;
   const double iwv = 1.0 / wvno, iwv2 = iwv * iwv, iomega = 1.0 / omega, iom2 = iomega * iomega;
   const double slow = wvno * iomega;  // 1/c
-  double cdl[NMAX * 6];  // [m][0..4] = cd, [m][5] = exe   (thread-local, L1-backed)
-  double vsl[NMAX * 12]; // varsv results of the up-sweep, reused by the down-sweep:
-                         // [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S (r < 0 <=> imaginary), [m][10..11] = 1/r
+  constexpr bool shared_cd = SHARED_CD;
+  // thread-local variants: [m][0..4] = cd, [m][5] = exe; varsv results of the up-sweep, reused by the
+  // down-sweep: [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S (r < 0 <=> imaginary), [m][10..11] = 1/r
+  double cdl_local[SHARED_CD ? 1 : NMAX * 6];
+  double vsl[SHARED_CD ? 1 : NMAX * 12];
+  double *cdl = SHARED_CD ? cds : cdl_local;
+  const int cst = SHARED_CD ? cstride : 1;
+#define CDL(i) cdl[(i) * cst]
 
   // ---------------- up-sweep (:404-492): half-space vector from evalg (:736-768)
   {
@@ -183,12 +193,12 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     cd g5 = wvno2 * (wvno2 - rarb);
     const cd den = (-zr * zr * om2 * om2 * wvno2) * rarb;
     const cd q = 0.25 * cinv(den);
-    cdl[m * 6 + 0] = (g1 * q).x;
-    cdl[m * 6 + 1] = (g2 * q).x;
-    cdl[m * 6 + 2] = (g3 * q).x;
-    cdl[m * 6 + 3] = (g4 * q).x;
-    cdl[m * 6 + 4] = (g5 * q).x;
-    cdl[m * 6 + 5] = 0.0;
+    CDL(m * 6 + 0) = (g1 * q).x;
+    CDL(m * 6 + 1) = (g2 * q).x;
+    CDL(m * 6 + 2) = (g3 * q).x;
+    CDL(m * 6 + 3) = (g4 * q).x;
+    CDL(m * 6 + 4) = (g5 * q).x;
+    CDL(m * 6 + 5) = 0.0;
   }
   double exsum = 0.0;
   for (int m = mmax - 2; m >= 0; m--) {
@@ -196,7 +206,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     const bool wat = !(zb > 0.0);
     const double xka = omega * M.ld(F_IA, m, b), xkb = wat ? 0.0 : omega * M.ld(F_IB, m, b);
     const double irom2 = M.ld(F_IRHO, m, b) * iom2;
-    const VSV P = varsv_half(wvno2 - xka * xka, zd);
+    const VSV P = varsv_half(__fma_rn(-xka, xka, wvno2), zd);  // explicit: the down-sweep recomputes it
     VSV S;
     if (wat) {  // fluid layer: no SV wave (varsv :860-880)
       S.c = 1.0;
@@ -208,8 +218,9 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       S.e = 1.0;
       S.imag = false;
     } else {
-      S = varsv_half(wvno2 - xkb * xkb, zd);
+      S = varsv_half(__fma_rn(-xkb, xkb, wvno2), zd);
     }
+    if constexpr (!shared_cd) {
     vsl[m * 12 + 0] = P.c;
     vsl[m * 12 + 1] = P.rs;
     vsl[m * 12 + 2] = P.sr;
@@ -222,8 +233,9 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     vsl[m * 12 + 9] = S.imag ? -S.r : S.r;
     vsl[m * 12 + 10] = P.ri;
     vsl[m * 12 + 11] = S.ri;
-    const double d0 = cdl[(m + 1) * 6 + 0], d1 = cdl[(m + 1) * 6 + 1], d2 = cdl[(m + 1) * 6 + 2],
-                 d3 = cdl[(m + 1) * 6 + 3], d4 = cdl[(m + 1) * 6 + 4];
+    }
+    const double d0 = CDL((m + 1) * 6 + 0), d1 = CDL((m + 1) * 6 + 1), d2 = CDL((m + 1) * 6 + 2),
+                 d3 = CDL((m + 1) * 6 + 3), d4 = CDL((m + 1) * 6 + 4);
     double n0, n1, n2, n3, n4;
     if (wat) {
       // fluid compound matrix (dnka :555-572): only 9 non-zero entries
@@ -249,20 +261,20 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     const double sc = pow2_scale(max(max(max(RFS_ABSBITS(n0), RFS_ABSBITS(n1)),
                                          max(RFS_ABSBITS(n2), RFS_ABSBITS(n3))), RFS_ABSBITS(n4)), lsc);
     exsum = exsum + P.ex + S.ex + lsc;
-    cdl[m * 6 + 0] = n0 * sc;
-    cdl[m * 6 + 1] = n1 * sc;
-    cdl[m * 6 + 2] = n2 * sc;
-    cdl[m * 6 + 3] = n3 * sc;
-    cdl[m * 6 + 4] = n4 * sc;
-    cdl[m * 6 + 5] = exsum;
+    CDL(m * 6 + 0) = n0 * sc;
+    CDL(m * 6 + 1) = n1 * sc;
+    CDL(m * 6 + 2) = n2 * sc;
+    CDL(m * 6 + 3) = n3 * sc;
+    CDL(m * 6 + 4) = n4 * sc;
+    CDL(m * 6 + 5) = exsum;
   }
 
   // ---------------- fused down-sweep / eigenfunctions / energy integrals
-  const double f1213 = -cdl[1];
+  const double f1213 = -CDL(1);
   const double if1213 = 1.0 / f1213;
-  const double exe1 = cdl[5];
+  const double exe1 = CDL(5);
   Eig4 et;  // eigenfunction at the top of the current layer
-  et.ur = cdl[2] / cdl[1];
+  et.ur = CDL(2) / CDL(1);
   et.uz = 1.0;
   et.tz = 0.0;
   et.tr = 0.0;
@@ -287,7 +299,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     const double xmu = zr * zb * zb;
     const double xlam = zr * za * za - 2 * xmu;
     const double xka = omega * M.ld(F_IA, m, b), xkb = wat ? 0.0 : omega * M.ld(F_IB, m, b);
-    const double sa = wvno2 - xka * xka, sb = wvno2 - xkb * xkb;
+    const double sa = __fma_rn(-xka, xka, wvno2), sb = __fma_rn(-xkb, xkb, wvno2);
     const double rom2 = zr * om2, irho = M.ld(F_IRHO, m, b), irom2 = irho * iom2;
     // 1/(rho b^2), 1/(rho a^2) from the reciprocals of the model block (no divisions)
     const double ibm = wat ? 0.0 : M.ld(F_IB, m, b), iam = M.ld(F_IA, m, b);
@@ -332,12 +344,35 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     // ---- nu_a, nu_b of this layer; they come from the up-sweep when available
     cd ra, rb;
     double ria, rib;  // 1/|nu_a|, 1/|nu_b| (0 for a vanishing wavenumber)
-    if (!half) {
-      const double sra = vsl[m * 12 + 4], srb = vsl[m * 12 + 9];
+    VSV Pq, Sq;       // varsv terms of this layer (shared_cd: recomputed exactly as in the up-sweep)
+    Pq.c = Pq.rs = Pq.sr = Pq.ex = Pq.r = Pq.ri = Pq.e = 0.0;
+    Pq.imag = false;
+    Sq = Pq;
+    if (shared_cd && !half) {
+      Pq = varsv_half(sa, zd);
+      if (wat) {
+        Sq.c = 1.0;
+        Sq.rs = 0.0;
+        Sq.sr = 0.0;
+        Sq.ex = 0.0;
+        Sq.r = 0.0;
+        Sq.ri = 0.0;
+        Sq.e = 1.0;
+        Sq.imag = false;
+      } else {
+        Sq = varsv_half(sb, zd);
+      }
+      const double sra = Pq.imag ? -Pq.r : Pq.r, srb = Sq.imag ? -Sq.r : Sq.r;
       ra = mk(sra < 0.0 || (sra == 0.0 && sa < 0.0), fabs(sra));
       rb = mk(srb < 0.0 || (srb == 0.0 && sb < 0.0), fabs(srb));
-      ria = vsl[m * 12 + 10];
-      rib = vsl[m * 12 + 11];
+      ria = Pq.ri;
+      rib = Sq.ri;
+    } else if (!shared_cd && !half) {
+      const double sra = vsl[shared_cd ? 0 : m * 12 + 4], srb = vsl[shared_cd ? 0 : m * 12 + 9];
+      ra = mk(sra < 0.0 || (sra == 0.0 && sa < 0.0), fabs(sra));
+      rb = mk(srb < 0.0 || (srb == 0.0 && sb < 0.0), fabs(srb));
+      ria = vsl[shared_cd ? 0 : m * 12 + 10];
+      rib = vsl[shared_cd ? 0 : m * 12 + 11];
     } else {
       const double asa = fabs(sa), asb = fabs(sb);
       ria = (asa > 0.0) ? rsqrt_pos(asa) : 0.0;
@@ -351,14 +386,19 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     Eig4 eb = et;  // eigenfunction at the bottom of the layer (top of m+1)
     VSV P, S;
     if (!half) {
-      P.c = vsl[m * 12 + 0];
-      P.rs = vsl[m * 12 + 1];
-      P.sr = vsl[m * 12 + 2];
-      P.ex = vsl[m * 12 + 3];
-      S.c = vsl[m * 12 + 5];
-      S.rs = vsl[m * 12 + 6];
-      S.sr = vsl[m * 12 + 7];
-      S.ex = vsl[m * 12 + 8];
+      if constexpr (shared_cd) {
+        P = Pq;
+        S = Sq;
+      } else {
+        P.c = vsl[m * 12 + 0];
+        P.rs = vsl[m * 12 + 1];
+        P.sr = vsl[m * 12 + 2];
+        P.ex = vsl[m * 12 + 3];
+        S.c = vsl[m * 12 + 5];
+        S.rs = vsl[m * 12 + 6];
+        S.sr = vsl[m * 12 + 7];
+        S.ex = vsl[m * 12 + 8];
+      }
       double w0, w1, w2, w3;
       if (wat) {
         // fluid Haskell step (hska :930-944)
@@ -404,14 +444,14 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       exa_sum = exa_sum + P.ex + lsc;
       // ---- eigenfunction at the top of layer m+1 (svfunc :268-315)
       const int i = m + 1;
-      const double cd1 = cdl[i * 6 + 0], cd2 = cdl[i * 6 + 1], cd3 = cdl[i * 6 + 2], cd4 = -cd3,
-                   cd5 = cdl[i * 6 + 3], cd6 = cdl[i * 6 + 4];
+      const double cd1 = CDL(i * 6 + 0), cd2 = CDL(i * 6 + 1), cd3 = CDL(i * 6 + 2), cd4 = -cd3,
+                   cd5 = CDL(i * 6 + 3), cd6 = CDL(i * 6 + 4);
       const double tz1 = -v3, tz2 = -v2, tz3 = v1, tz4 = v0;
       const double uu1 = tz2 * cd6 - tz3 * cd5 + tz4 * cd4;
       const double uu2 = -tz1 * cd6 + tz3 * cd3 - tz4 * cd2;
       const double uu3 = tz1 * cd5 - tz2 * cd3 + tz4 * cd1;
       const double uu4 = -tz1 * cd4 + tz2 * cd2 - tz3 * cd1;
-      const double ext = exa_sum + cdl[i * 6 + 5] - exe1;
+      const double ext = exa_sum + CDL(i * 6 + 5) - exe1;
       if (ext > -80.0 && ext < 80.0) {
         const double fact = exp_cb(ext) * if1213;
         eb.ur = uu1 * fact;
@@ -605,6 +645,7 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     suffix += dfac * M.ld(F_DTP, m, b);     // dtp = 1 on a flat earth (sprayl :1619-1626 otherwise)
   }
   *ugr_out = ugr;
+#undef CDL
 }
 
 }  // namespace rfs
