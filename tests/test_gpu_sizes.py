@@ -338,3 +338,60 @@ def test_sampler_front_ends_accept_the_three_model_classes(ctx, tmp_path):
     U1 = rf.misfit_and_grad(x0 * 1.02)[0]
     rf.gauss = 2.5
     assert rf.misfit_and_grad(x0 * 1.02)[0] != U1
+
+
+def test_mode_list_and_ray_list_through_the_python_classes(ctx, oracle):
+    """SurfWD(mode=[...]) / ReceiverFunc(ray_p=[...]) (extensions of the reference's single mode / ray
+    parameter): data layout [mode][Rc,Rg,..] resp. [ray][nt], misfit and gradient = sums of the
+    single-valued objects', `forward` consistent with `misfit_and_grad`, and a joint model on top."""
+    from rfsurfhmc_b200.model.model_rf import ReceiverFunc
+    from rfsurfhmc_b200.model.model_surf import SurfWD
+    from rfsurfhmc_b200.model.model_rf_swd_vs_thk import Joint_RF_SWD
+    cfg = f1_config()
+    x0 = f1_true_model()
+    x = x0 * 1.03
+    T = np.arange(5., 13.)
+    rng = np.random.default_rng(4)
+    # --- modes
+    multi = SurfWD(mode=[0, 1], tRc=T, tRg=T)
+    assert multi.nt == 32
+    d = rng.normal(3.3, 0.1, 32)
+    multi.set_obsdata(d)
+    U, g, syn, ok = multi.misfit_and_grad(x)
+    assert ok and syn.shape == (32,) and g.shape == (14,)
+    Us, gs = 0.0, 0.0
+    for im, mode in enumerate((0, 1)):
+        one = SurfWD(mode=mode, tRc=T, tRg=T)
+        one.set_obsdata(d[16 * im:16 * (im + 1)])
+        u1, g1, s1, ok1 = one.misfit_and_grad(x)
+        assert ok1 and np.array_equal(s1, syn[16 * im:16 * (im + 1)])
+        Us, gs = Us + u1, gs + g1
+    assert np.isclose(U, Us, rtol=1e-12) and np.allclose(g, gs, rtol=1e-10, atol=1e-12 * np.abs(gs).max())
+    fwd, okf = multi.forward(x)
+    assert okf and np.allclose(fwd[:8], syn[:8], rtol=1e-12)          # Rc of mode 0 (forward passes tRc for all)
+    # --- ray parameters
+    rays = [0.04, 0.065]
+    rf = ReceiverFunc(rays, cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], "P", "freq")
+    assert rf.nt == 250 and rf.nt_trace == 125
+    dr = 0.01 * rng.standard_normal(250)
+    rf.set_obsdata(dr)
+    U, g, syn = rf.misfit_and_grad(x)
+    assert np.allclose(rf.forward(x), syn, rtol=0, atol=1e-12)
+    Us, gs = 0.0, 0.0
+    for ir, p in enumerate(rays):
+        one = ReceiverFunc(p, cfg["nt"], cfg["dt"], cfg["gauss"], cfg["time_shift"], cfg["water"], "P", "freq")
+        one.set_obsdata(dr[125 * ir:125 * (ir + 1)])
+        u1, g1, s1 = one.misfit_and_grad(x)
+        assert np.allclose(s1, syn[125 * ir:125 * (ir + 1)], rtol=0, atol=1e-14)
+        Us, gs = Us + u1, gs + g1
+    assert np.isclose(U, Us, rtol=1e-12) and np.allclose(g, gs, rtol=1e-10, atol=1e-12 * np.abs(gs).max())
+    # --- joint model over both lists: weights (sigma1/sigma2)^2 n1/n2 with the total data counts
+    joint = Joint_RF_SWD(1.0, 2.0, rf, multi)
+    joint.set_obsdata(dr, d)
+    Uj, gj, sj, okj = joint.misfit_and_grad(x)
+    wt = (1.0 / 2.0)**2 * 250 / 32
+    Ur, gr, _ = rf.misfit_and_grad(x)
+    Usw, gsw, _, _ = multi.misfit_and_grad(x)
+    assert okj and sj.shape == (282,)
+    assert np.isclose(Uj, Ur + wt * Usw, rtol=1e-12)
+    assert np.allclose(gj, gr + wt * gsw, rtol=1e-10, atol=1e-12 * np.abs(gj).max())
