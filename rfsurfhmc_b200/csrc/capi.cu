@@ -741,7 +741,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       V.B = Bc;
       V.n = n;
       if (use_rf && ctx->overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-      LAUNCH(joint_assemble_kernel, gridFor(Bc * n, 128), 128, 0, st, ctx->plan, V,
+      LAUNCH(joint_assemble_kernel, dim3(gridFor(Bc, 32), (unsigned)n), 32 * RFS_ASM_Q, 0, st, ctx->plan, V,
              (const int *)ctx->w_ierr.p, (const double *)ctx->w_chain.p, ctx->stale, which, n1,
              d_dobs, (const double *)ctx->w_urf.p, (const double *)ctx->w_grf.p, wt, U + off,
              grad + off * 2 * n, dsyn + off * ndata, flag + off, msel);

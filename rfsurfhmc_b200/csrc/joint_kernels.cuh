@@ -21,9 +21,14 @@ struct ModeSel {
 };
 
 // which: 0 joint, 1 RF only, 2 SWD only
-// One thread per (model, layer).  Layout of outputs (row-major per model, as the Python API):
+// RFS_ASM_Q threads per (model, layer): blocks of 32 models x RFS_ASM_Q period slices, one layer per
+// blockIdx.y; slice q contracts the periods k = q, q + Q, ... and the slices are summed in a fixed
+// order through shared memory (deterministic).  The loop over the Jacobian rows is a chain of dependent
+// global loads: four times the threads cut its latency (0.30 -> ~0.1 ms at C1).
+// Layout of outputs (row-major per model, as the Python API):
 //   U[B], grad[B][2n] (vs then thk), dsyn[B][ndata] with ndata = nt_rf + nsw (joint),
 //   flag[B] (1 ok, 0 failed SWD root search)
+#define RFS_ASM_Q 4
 __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__restrict__ ierr,
                                       const double *__restrict__ chain, int stale, int which,
                                       int nt_rf, const double *__restrict__ dobs,
@@ -32,21 +37,22 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
                                       double *__restrict__ U, double *__restrict__ grad,
                                       double *__restrict__ dsyn, unsigned char *__restrict__ flag,
                                       ModeSel ms) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  __shared__ double red[3][RFS_ASM_Q][32];
+  const int bl = threadIdx.x & 31, q = threadIdx.x >> 5;
   const long long B = V.B;
   const int n = V.n;
-  if (i >= B * n) return;
-  const long long b = i % B;
-  const int m = (int)(i / B);
+  const long long b = blockIdx.x * 32LL + bl;
+  const int m = blockIdx.y;
+  const bool live = b < B;
   const long long nB = (long long)n * B;
   const int nsw = (which == 1) ? 0 : plan.ndata * ms.n;
   const int n1 = (which == 2) ? 0 : nt_rf;
   const int ndata = n1 + nsw;
   bool ok = true;
-  if (which != 1)
+  if (which != 1 && live)
     for (int s = 0; s < plan.nseq; s++) ok = ok && (ierr[(long long)s * B + b] == 0);
   double gv = 0.0, gh = 0.0, us = 0.0;
-  if (which != 1 && ok) {
+  if (which != 1 && ok && live) {
     const double dadb = chain[0 * nB + m * B + b], drda = chain[1 * nB + m * B + b];
     for (int im = 0; im < ms.n; im++) {
       // view of mode ms.m[im]: results are laid out [mode][solve]...
@@ -58,7 +64,7 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
       const int doff = n1 + im * plan.ndata;
       for (int r = 0; r < plan.nrow; r++) {
         const SwdRow rw = plan.row[r];
-        for (int k = 0; k < rw.nper; k++) {
+        for (int k = q; k < rw.nper; k += RFS_ASM_Q) {
           const double d = swd_row_value(plan, Vm, rw, k, b);
           const double res = d - dobs[doff + rw.d_off + k];
           double K[4];
@@ -73,6 +79,19 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
         }
       }
     }
+  }
+  // fixed-order sum over the period slices
+  red[0][q][bl] = gv;
+  red[1][q][bl] = gh;
+  red[2][q][bl] = us;
+  __syncthreads();
+  if (q != 0 || !live) return;
+  gv = gh = us = 0.0;
+#pragma unroll
+  for (int j = 0; j < RFS_ASM_Q; j++) {
+    gv += red[0][j][bl];
+    gh += red[1][j][bl];
+    us += red[2][j][bl];
   }
   if (ok) {
     const double w = (which == 0) ? wt : 1.0;
