@@ -627,7 +627,13 @@ def main():
                "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": B * 2 * N_LAYERS * 8,
                        "d2h_bytes_per_step": B * (1 + 2 * N_LAYERS + nd) * 8 + B, "gpu_launches": launches_e2e,
                        "api": "rfsurfhmc_b200.batched.HostPipeline (2 slots: copies overlap the next batch)"},
-               "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+               "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+               "kernels_note": "ms / share: CUDA events around every launch in this run.  tflops = algorithmic "
+                               "flop by the frozen hand counts of BASELINE.md §3 (1 FMA = 2, div/sqrt/exp/sin/cos "
+                               "= 20 flop each; E_R and P_RF are generous per-layer counts) / kernel time; the FP64 "
+                               "pipe utilisation ncu measures for the same kernels is in profiles/r02_kernels.md "
+                               "(roots 52 %, eigen 54 %, RF propagate 66 %)",
+               "cpu_baseline": cpu,
                "hmc": hmc_out, "configs": configs, "failed_models_last_step": n_fail}
         if strong is not None:
             ms_s = float(tt[2])
