@@ -350,7 +350,11 @@ RFS_DEVINL double dunkin_water_top(const MT &M, long long b, double wvno, double
   const double w0 = -rho1 * P.w;
   return RFS_FMA(P.c, e0, RFS_MUL(w0, e1));
 }
-template <class MT>
+// PAIRED: two layer matrices are formed per trip (independent dependency chains: twice the ILP) and
+// applied in order -- the same operations and bits.  It costs ~40 registers: slower in the thread-mapped
+// kernel, where occupancy hides latency (measured in round 1), faster where a warp is alone on its
+// scheduler (team kernels whose lanes each evaluate a whole secular function, GL = 1).
+template <class MT, bool PAIRED = false>
 RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const MT &M, long long b,
                              int llw) {
   const int mmax = M.n;
@@ -362,8 +366,16 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const MT &M
   const double wvno2 = wvno * wvno;
   double e0, e1, e2, e3, e4;
   dunkin_halfspace(M, b, wvno, wvno2, omega, iom, e0, e1, e2, e3, e4);
-  // (forming two layer matrices per trip for more ILP was measured SLOWER: 166 registers or spills)
-  for (int m = mmax - 2; m >= llw - 1; m--) {
+  int m = mmax - 2;
+  if (PAIRED) {
+    for (; m - 1 >= llw - 1; m -= 2) {
+      const Dunkin Ca = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
+      const Dunkin Cb = dunkin_layer(M, b, m - 1, wvno, wvno2, omega, iom);
+      dunkin_apply(Ca, e0, e1, e2, e3, e4);
+      dunkin_apply(Cb, e0, e1, e2, e3, e4);
+    }
+  }
+  for (; m >= llw - 1; m--) {
     const Dunkin C = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
     dunkin_apply(C, e0, e1, e2, e3, e4);
   }

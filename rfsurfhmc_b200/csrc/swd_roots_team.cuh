@@ -77,7 +77,7 @@ RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double om
   const double wvno = omega_in / c;
   if (GL == 1) {
     return (ifunc == 1) ? dltar1_dev(wvno, omega_in, M, 0, llw)
-                        : dltar4_dev(wvno, omega_in, iomega_in, M, 0, llw);
+                        : dltar4_dev<SmemModel, true>(wvno, omega_in, iomega_in, M, 0, llw);
   }
   const int g = tl % GL;
   const int col0 = lane - g;  // column of my slot's first layer lane

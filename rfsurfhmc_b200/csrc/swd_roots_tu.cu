@@ -110,7 +110,8 @@ cudaError_t launch_roots_retry(const SwdPlan &P, const SwdBlocks &blk, long long
 }
 
 bool team_shape_supported(int T, int S) {
-  static const int ok[][2] = {{4, 1}, {4, 4}, {8, 1}, {8, 2}, {16, 1}, {16, 2}, {32, 1}, {32, 2}, {32, 4}};
+  static const int ok[][2] = {{2, 2}, {4, 1}, {4, 4}, {8, 1}, {8, 2}, {8, 8}, {16, 1}, {16, 2},
+                              {32, 1}, {32, 2}, {32, 4}};
   for (auto &p : ok)
     if (p[0] == T && p[1] == S) return true;
   return false;
@@ -141,7 +142,8 @@ cudaError_t launch_roots_team(int T, int S, const SwdPlan &P, const SwdBlocks &b
                               int *ierr, unsigned long long *counter, cudaStream_t st) {
 #define RFS_TEAM(TT, SS) \
   if (T == TT && S == SS) return launch_team<TT, SS>(P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter, st);
-  RFS_TEAM(4, 1) RFS_TEAM(4, 4) RFS_TEAM(8, 1) RFS_TEAM(8, 2) RFS_TEAM(16, 1) RFS_TEAM(16, 2)
+  RFS_TEAM(2, 2) RFS_TEAM(4, 1) RFS_TEAM(4, 4) RFS_TEAM(8, 1) RFS_TEAM(8, 2) RFS_TEAM(8, 8) RFS_TEAM(16, 1)
+  RFS_TEAM(16, 2)
   RFS_TEAM(32, 1) RFS_TEAM(32, 2) RFS_TEAM(32, 4)
 #undef RFS_TEAM
   return cudaErrorInvalidValue;
