@@ -88,7 +88,7 @@ def test_every_team_shape_all_wave_types_and_modes(tctx, T, S):
         assert _same(a, b)
 
 
-@pytest.mark.parametrize("T,S", [(8, 1), (16, 2), (32, 1), (32, 4)])
+@pytest.mark.parametrize("T,S", [(2, 2), (4, 4), (8, 1), (16, 2), (32, 1), (32, 4)])
 def test_team_roots_many_layers_water_and_sphere(tctx, T, S):
     """n = 40 (several build rounds per evaluation), n = 200, a water layer on top (llw = 2) and the
     earth-flattening model blocks."""

@@ -81,14 +81,14 @@ def main():
         rows = run(ctx, X, 0, 197, 3)
         res.append({"workload": "C1 joint n=7, 36 Rc + 36 Rg (3 sequences/model)", "B": B, "rows": rows})
         print(json.dumps(res[-1]), flush=True)
-    # ---- C2-like: n=40, 60 periods, four wave types, fundamental mode (10 sequences/model)
+    # ---- C2-like: n=40, 60 periods, four wave types, fundamental mode (6 sequences/model)
     Tp = np.geomspace(2, 100, 60)
     ctx2 = Context(0)
     ctx2.config_swd(40, Tp, Tp, Tp, Tp, mode=0)
     ctx2.config_obs(np.full(240, 3.0))
     for B in ([256] if a.quick else [64, 512, 4096]):
         rows = run(ctx2, layered(B, 40, 7), 2, 240, 2)
-        res.append({"workload": "C2-like SWD n=40, 60 periods x Rc,Rg,Lc,Lg (8 sequences/model)", "B": B, "rows": rows})
+        res.append({"workload": "C2-like SWD n=40, 60 periods x Rc,Rg,Lc,Lg (6 sequences/model)", "B": B, "rows": rows})
         print(json.dumps(res[-1]), flush=True)
     # ---- C5-like: n=200, 128 Rc + 128 Rg
     Tp = np.geomspace(1, 150, 128)
