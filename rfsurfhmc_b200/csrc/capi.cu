@@ -261,8 +261,8 @@ void pick_team(const rfs_ctx *ctx, long long jobs, int n, int &T, int &S) {
   S = 1;
   // jobs = (model, sequence) pairs in flight; thresholds: fastest mapping in the measured sweep
   if (n <= 16) {
-    if (jobs >= 18432) return;                      // thread-mapped
-    if (jobs >= 9216) { T = 4; S = 4; return; }     // one lane per scan point, no layer split
+    if (jobs >= 32768) return;                      // thread-mapped
+    if (jobs >= 9216) { T = 2; S = 2; return; }     // two lanes, one scan point each, no layer split
     if (jobs >= 4608) { T = 8; S = 2; return; }
     if (jobs >= 1536) { T = 16; S = 2; return; }
     T = 32; S = 4;
@@ -270,8 +270,8 @@ void pick_team(const rfs_ctx *ctx, long long jobs, int n, int &T, int &S) {
   }
   // many layers (n = 40 ... 200): the sequential 5-vector chain dominates; wide teams pay off longer
   if (jobs >= 12288) return;
-  if (jobs >= 1536) { T = 16; S = 2; return; }
-  T = 32; S = 4;
+  if (jobs >= 1536) { T = 16; S = (n <= 48) ? 2 : 1; return; }
+  T = 32; S = 2;
 }
 
 bool team_supported(int T, int S) { return team_shape_supported(T, S); }
