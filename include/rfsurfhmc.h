@@ -146,8 +146,7 @@ int rfs_set_hmc_options(rfs_ctx *ctx, long long resident_slots, double max_secon
  * rfs_measure_fp64_peak runs a DFMA micro-benchmark: the roofline denominator of the FP64 path. */
 int rfs_count_evals(rfs_ctx *ctx, int enable);
 /* Root-search mapping (no reference counterpart; results are bit-identical for every mapping):
- * T < 0 automatic by batch size (default), T = 0 one thread per (model, period sequence), T = 1 the
- * same with two layer matrices formed per trip (more ILP, more registers),
+ * T < 0 automatic by batch size (default), T = 0 one thread per (model, period sequence),
  * T in {2,4,8,16,32}: a team of T lanes per sequence, S speculative scan points per round
  * (csrc/swd_roots_team.cuh).  Environment override at rfs_create: RFS_ROOTS_TEAM="T,S". */
 int rfs_set_roots_team(rfs_ctx *ctx, int T, int S);

@@ -297,10 +297,10 @@ int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const 
   pick_team(ctx, jobs, n, T, S);
   ctx->last_team_T = T;
   ctx->last_team_S = S;
-  if (T <= 1) {  // T = 1: thread-mapped with two layer matrices per trip
+  if (T == 0) {
     LAUNCH_TU("swd_roots_kernel",
               launch_roots_thread(P, d_swd, B, n, d_periods, all_modes, (double *)ctx->w_croot.p,
-                                  (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p, cnt, st, T == 1));
+                                  (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p, cnt, st));
     return RFS_OK;
   }
   if (!team_shape_supported(T, S)) return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");

@@ -434,7 +434,6 @@ enum { PH_SETUP = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE, PH_DONE };
 // the last one is done; lanes that are finished evaluate look-ahead scan points c2+j*dc for one
 // scanning lane (same repeated additions, hence bit-identical grid) and hand the values over
 // through shared memory (`wsm`, 32 doubles per warp).  `valid` = this lane owns a sequence.
-template <bool PAIRED = false>
 RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &sq,
                                   const double *__restrict__ periods, int nmode, int all_modes,
                                   double *__restrict__ cout, long long cout_mode_stride,
@@ -577,7 +576,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     if (phase != PH_DONE || helper) {
       const double wv = e_om / e_c;
       val = (e_if == 1) ? dltar1_dev(wv, e_om, M, e_b, e_llw)
-                        : dltar4_dev<SwdModel, PAIRED>(wv, e_om, e_iom, M, e_b, e_llw);
+                        : dltar4_dev(wv, e_om, e_iom, M, e_b, e_llw);
     }
     if (nhelp) {
       if (helper) wsm[hj] = val;

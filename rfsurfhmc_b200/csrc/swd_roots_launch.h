@@ -12,11 +12,10 @@ namespace rfs {
 #define RFS_ROOTS_BLOCK 128
 #endif
 
-// one thread per (model, sequence); paired: two layer matrices per trip (shape "1x1")
+// one thread per (model, sequence)
 cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
                                 const double *periods, int all_modes, double *croot, double *cwork,
-                                int *ierr, unsigned long long *counter, cudaStream_t st,
-                                bool paired = false);
+                                int *ierr, unsigned long long *counter, cudaStream_t st);
 // T lanes per (model, sequence), S speculative scan points; false if (T,S) is not instantiated
 bool team_shape_supported(int T, int S);
 cudaError_t launch_roots_team(int T, int S, const SwdPlan &P, const SwdBlocks &blk, long long B, int n,

@@ -14,10 +14,7 @@ namespace rfs {
 #ifndef RFS_ROOTS_BLOCK
 #define RFS_ROOTS_BLOCK 128
 #endif
-// PAIRED: two layer matrices per trip (more ILP, ~168 registers: three blocks per SM instead of four --
-// no loss while the grid is below 0.75 waves, i.e. up to ~18 900 models of three sequences)
-template <bool PAIRED>
-__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, PAIRED ? 3 : RFS_ROOTS_MINBLOCKS)
+__global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
     swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
@@ -29,9 +26,9 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, PAIRED ? 3 : RFS_ROOTS_MINBLO
   const int s = valid ? (int)(i / B) : 0;
   SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
   unsigned int nev = 0;
-  const int e = swd_solve_sequence<PAIRED>(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                           (long long)plan.nsolve * B, cwork, B, nev, valid,
-                                           wsm_all[threadIdx.x >> 5], -1);
+  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
+                                   wsm_all[threadIdx.x >> 5], -1);
   if (valid) ierr[(long long)s * B + b] = e;
   if (neval_total) {
     // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
@@ -97,13 +94,9 @@ static inline unsigned grid_for(long long total, int block) {
 
 cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
                                 const double *periods, int all_modes, double *croot, double *cwork,
-                                int *ierr, unsigned long long *counter, cudaStream_t st, bool paired) {
-  if (paired)
-    swd_roots_kernel<true><<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
-        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
-  else
-    swd_roots_kernel<false><<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
-        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+                                int *ierr, unsigned long long *counter, cudaStream_t st) {
+  swd_roots_kernel<<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
+      P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
   return cudaGetLastError();
 }
 
@@ -117,7 +110,7 @@ cudaError_t launch_roots_retry(const SwdPlan &P, const SwdBlocks &blk, long long
 }
 
 bool team_shape_supported(int T, int S) {
-  static const int ok[][2] = {{1, 1}, {2, 2}, {4, 1}, {4, 4}, {8, 1}, {8, 2}, {8, 8}, {16, 1}, {16, 2},
+  static const int ok[][2] = {{2, 2}, {4, 1}, {4, 4}, {8, 1}, {8, 2}, {8, 8}, {16, 1}, {16, 2},
                               {32, 1}, {32, 2}, {32, 4}};
   for (auto &p : ok)
     if (p[0] == T && p[1] == S) return true;

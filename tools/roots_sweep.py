@@ -12,7 +12,7 @@ import torch
 from rfsurfhmc_b200._lib import Context
 from rfsurfhmc_b200.fixtures import f1_config, f1_true_model, driver_bounds, sorted_uniform_models
 
-TEAMS = [(0, 1), (1, 1), (2, 2), (4, 1), (4, 4), (8, 1), (8, 2), (8, 8), (16, 1), (16, 2), (32, 1), (32, 2), (32, 4)]
+TEAMS = [(0, 1), (2, 2), (4, 1), (4, 4), (8, 1), (8, 2), (8, 8), (16, 1), (16, 2), (32, 1), (32, 2), (32, 4)]
 
 
 def layered(B, n, seed):
