@@ -153,9 +153,9 @@ struct Eig4 {
 // Output of one Rayleigh solve.  kern points at [4][n] doubles with element stride `ks`
 // (order: dcda, dcdb, dcdr, dcdh), dcdh already converted to d/d(thickness) (suffix sums).
 // SHARED_CD: the up-sweep vectors live in shared memory as cds[(m*6+j)*cstride] (this thread's
-// column of a [NMAX*6][blockDim] array: conflict-free) and the varsv terms are recomputed in the
-// down-sweep instead of being parked in thread-local memory (1 152 B per thread at NMAX = 8: with
-// 1.8 M threads per launch that spilled 1.7 GB to DRAM per evaluation).  Otherwise: thread-local.
+// column of a [NMAX*6][blockDim] array: conflict-free); otherwise in thread-local memory.  The varsv
+// terms are recomputed in the down-sweep instead of being parked beside them (together 1 152 B per
+// thread at NMAX = 8: with 1.8 M threads per launch that spilled 1.7 GB to DRAM per evaluation).
 template <int NMAX, bool SHARED_CD = false>
 RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double c, double *ugr_out,
                                double *__restrict__ kern, long long ks, double *cds = nullptr,
@@ -167,10 +167,9 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   const double iwv = 1.0 / wvno, iwv2 = iwv * iwv, iomega = 1.0 / omega, iom2 = iomega * iomega;
   const double slow = wvno * iomega;  // 1/c
   constexpr bool shared_cd = SHARED_CD;
-  // thread-local variants: [m][0..4] = cd, [m][5] = exe; varsv results of the up-sweep, reused by the
-  // down-sweep: [m][0..4] = P (c, rs, sr, ex, +-r), [m][5..9] = S (r < 0 <=> imaginary), [m][10..11] = 1/r
+  // thread-local variant of the up-sweep vectors: [m][0..4] = cd, [m][5] = exe.  The varsv terms are
+  // never stored: the down-sweep recomputes them (12 doubles per layer less local-memory traffic)
   double cdl_local[SHARED_CD ? 1 : NMAX * 6];
-  double vsl[SHARED_CD ? 1 : NMAX * 12];
   double *cdl = SHARED_CD ? cds : cdl_local;
   const int cst = SHARED_CD ? cstride : 1;
 #define CDL(i) cdl[(i) * cst]
@@ -219,20 +218,6 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       S.imag = false;
     } else {
       S = varsv_half(__fma_rn(-xkb, xkb, wvno2), zd);
-    }
-    if constexpr (!shared_cd) {
-    vsl[m * 12 + 0] = P.c;
-    vsl[m * 12 + 1] = P.rs;
-    vsl[m * 12 + 2] = P.sr;
-    vsl[m * 12 + 3] = P.ex;
-    vsl[m * 12 + 4] = P.imag ? -P.r : P.r;
-    vsl[m * 12 + 5] = S.c;
-    vsl[m * 12 + 6] = S.rs;
-    vsl[m * 12 + 7] = S.sr;
-    vsl[m * 12 + 8] = S.ex;
-    vsl[m * 12 + 9] = S.imag ? -S.r : S.r;
-    vsl[m * 12 + 10] = P.ri;
-    vsl[m * 12 + 11] = S.ri;
     }
     const double d0 = CDL((m + 1) * 6 + 0), d1 = CDL((m + 1) * 6 + 1), d2 = CDL((m + 1) * 6 + 2),
                  d3 = CDL((m + 1) * 6 + 3), d4 = CDL((m + 1) * 6 + 4);
@@ -344,11 +329,11 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     // ---- nu_a, nu_b of this layer; they come from the up-sweep when available
     cd ra, rb;
     double ria, rib;  // 1/|nu_a|, 1/|nu_b| (0 for a vanishing wavenumber)
-    VSV Pq, Sq;       // varsv terms of this layer (shared_cd: recomputed exactly as in the up-sweep)
+    VSV Pq, Sq;       // varsv terms of this layer, recomputed exactly as in the up-sweep
     Pq.c = Pq.rs = Pq.sr = Pq.ex = Pq.r = Pq.ri = Pq.e = 0.0;
     Pq.imag = false;
     Sq = Pq;
-    if (shared_cd && !half) {
+    if (!half) {
       Pq = varsv_half(sa, zd);
       if (wat) {
         Sq.c = 1.0;
@@ -367,12 +352,6 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
       rb = mk(srb < 0.0 || (srb == 0.0 && sb < 0.0), fabs(srb));
       ria = Pq.ri;
       rib = Sq.ri;
-    } else if (!shared_cd && !half) {
-      const double sra = vsl[shared_cd ? 0 : m * 12 + 4], srb = vsl[shared_cd ? 0 : m * 12 + 9];
-      ra = mk(sra < 0.0 || (sra == 0.0 && sa < 0.0), fabs(sra));
-      rb = mk(srb < 0.0 || (srb == 0.0 && sb < 0.0), fabs(srb));
-      ria = vsl[shared_cd ? 0 : m * 12 + 10];
-      rib = vsl[shared_cd ? 0 : m * 12 + 11];
     } else {
       const double asa = fabs(sa), asb = fabs(sb);
       ria = (asa > 0.0) ? rsqrt_pos(asa) : 0.0;
@@ -386,19 +365,8 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
     Eig4 eb = et;  // eigenfunction at the bottom of the layer (top of m+1)
     VSV P, S;
     if (!half) {
-      if constexpr (shared_cd) {
-        P = Pq;
-        S = Sq;
-      } else {
-        P.c = vsl[m * 12 + 0];
-        P.rs = vsl[m * 12 + 1];
-        P.sr = vsl[m * 12 + 2];
-        P.ex = vsl[m * 12 + 3];
-        S.c = vsl[m * 12 + 5];
-        S.rs = vsl[m * 12 + 6];
-        S.sr = vsl[m * 12 + 7];
-        S.ex = vsl[m * 12 + 8];
-      }
+      P = Pq;
+      S = Sq;
       double w0, w1, w2, w3;
       if (wat) {
         // fluid Haskell step (hska :930-944)
