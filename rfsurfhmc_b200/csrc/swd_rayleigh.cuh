@@ -166,7 +166,6 @@ RFS_DEVINL void rayleigh_solve(const SwdModel &M, long long b, double T, double 
   const double wvno2 = wvno * wvno, om2 = omega * omega;
   const double iwv = 1.0 / wvno, iwv2 = iwv * iwv, iomega = 1.0 / omega, iom2 = iomega * iomega;
   const double slow = wvno * iomega;  // 1/c
-  constexpr bool shared_cd = SHARED_CD;
   // thread-local variant of the up-sweep vectors: [m][0..4] = cd, [m][5] = exe.  The varsv terms are
   // never stored: the down-sweep recomputes them (12 doubles per layer less local-memory traffic)
   double cdl_local[SHARED_CD ? 1 : NMAX * 6];
