@@ -31,13 +31,24 @@ struct Buf {
 
 }  // namespace
 
+// "Front" buffers of one chunk of a batch: model blocks and everything the root search produces.  They
+// are small (35 KB per model at n = 200), so a chunked batch keeps one set per chunk and runs the root
+// searches of ALL chunks concurrently before the memory-hungry eigen / RF stages go chunk by chunk.
+struct Front {
+  Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
+  Buf w_rstat;
+  Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ierr;
+  cudaEvent_t ev_prep = nullptr;   // model blocks of this chunk written
+  cudaEvent_t ev_ready = nullptr;  // root search of this chunk finished
+};
+
 struct rfs_ctx {
   int device = 0;
   std::string err;
   long long launches = 0;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
   cudaStream_t stream2 = nullptr; // RF branch of the joint evaluation runs concurrently with SWD
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_asm = nullptr;
   bool overlap = true;
   // ---- SWD configuration
   bool has_swd = false;
@@ -57,13 +68,13 @@ struct rfs_ctx {
   std::vector<double> dobs;
   Buf d_dobs;
   // ---- workspace (grown on demand, never shrunk)
-  Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
-  Buf w_rstat;
+  std::vector<Front *> fronts;  // fronts[0] always exists; F = the set the launch helpers use
+  Front *F = nullptr;
+  cudaStream_t stream_front[3] = {nullptr, nullptr, nullptr};  // root searches of later chunks
   Buf w_rfl;  // RfLayer table [B][n]
   Buf d_tw;   // FFT twiddle factors exp(-i pi j/(nft/2)), j < nft/2
   int tw_nft = 0;
-  Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ugr, w_kern, w_ierr, w_spec, w_dspec,
-      w_urf, w_grf, w_rftr;
+  Buf w_ugr, w_kern, w_spec, w_dspec, w_urf, w_grf, w_rftr;
   Buf io_x, io_U, io_grad, io_dsyn, io_flag, io_a, io_b, io_c, io_d, io_e, io_f;
   // ---- HMC
   long long hmc_evals = 0, hmc_steps = 0;
@@ -237,13 +248,13 @@ int make_blocks(rfs_ctx *ctx, const double *d_flat, long long B, int n, int sphe
   }
   int rc;
   for (int i = 0; i < 4; i++)
-    if ((rc = ensure(ctx, ctx->w_sph[i], sizeof(double) * SWD_NF * (size_t)n * B))) return rc;
-  LAUNCH(prep_sphere_kernel, gridFor(B, 128), 128, 0, st, d_flat, B, n, (double *)ctx->w_sph[0].p,
-         (double *)ctx->w_sph[1].p, (double *)ctx->w_sph[2].p, (double *)ctx->w_sph[3].p);
-  blk.root[0] = (const double *)ctx->w_sph[0].p;
-  blk.root[1] = (const double *)ctx->w_sph[1].p;
-  blk.eig[0] = (const double *)ctx->w_sph[2].p;
-  blk.eig[1] = (const double *)ctx->w_sph[3].p;
+    if ((rc = ensure(ctx, ctx->F->w_sph[i], sizeof(double) * SWD_NF * (size_t)n * B))) return rc;
+  LAUNCH(prep_sphere_kernel, gridFor(B, 128), 128, 0, st, d_flat, B, n, (double *)ctx->F->w_sph[0].p,
+         (double *)ctx->F->w_sph[1].p, (double *)ctx->F->w_sph[2].p, (double *)ctx->F->w_sph[3].p);
+  blk.root[0] = (const double *)ctx->F->w_sph[0].p;
+  blk.root[1] = (const double *)ctx->F->w_sph[1].p;
+  blk.eig[0] = (const double *)ctx->F->w_sph[2].p;
+  blk.eig[1] = (const double *)ctx->F->w_sph[3].p;
   return RFS_OK;
 }
 
@@ -299,39 +310,46 @@ int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const 
   ctx->last_team_S = S;
   if (T == 0) {
     LAUNCH_TU("swd_roots_kernel",
-              launch_roots_thread(P, d_swd, B, n, d_periods, all_modes, (double *)ctx->w_croot.p,
-                                  (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p, cnt, st));
+              launch_roots_thread(P, d_swd, B, n, d_periods, all_modes, (double *)ctx->F->w_croot.p,
+                                  (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, st));
     return RFS_OK;
   }
   if (!team_shape_supported(T, S)) return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
   LAUNCH_TU("swd_roots_team_kernel",
-            launch_roots_team(T, S, P, d_swd, B, n, d_periods, all_modes, (double *)ctx->w_croot.p,
-                              (double *)ctx->w_cwork.p, (int *)ctx->w_ierr.p, cnt, st));
+            launch_roots_team(T, S, P, d_swd, B, n, d_periods, all_modes, (double *)ctx->F->w_croot.p,
+                              (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, st));
   return RFS_OK;
 }
 
 // ---- SWD pipeline on a prepared model block: roots + eigen solves
-int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
-            long long B, int n, bool all_modes, bool want_eigen, cudaStream_t st) {
+// roots (+ retries) of the current front set, then (run_swd_eigen) the eigen solves
+int run_swd_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
+                  long long B, int n, bool all_modes, cudaStream_t st) {
   const int nmo = all_modes ? P.nmode : 1;
   int rc;
   // the kernels index the model block with 32-bit element offsets (SwdModel::ld)
   if ((long long)SWD_NF * n * B > 2147483647LL)
     return fail(ctx, RFS_E_ARG, "SWD batch too large: 10*layers*models must stay below 2^31 per call");
-  if ((rc = ensure(ctx, ctx->w_croot, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
-  if ((rc = ensure(ctx, ctx->w_cwork, sizeof(double) * (size_t)P.nsolve * B))) return rc;
-  if ((rc = ensure(ctx, ctx->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
+  if ((rc = ensure(ctx, ctx->F->w_croot, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
+  if ((rc = ensure(ctx, ctx->F->w_cwork, sizeof(double) * (size_t)P.nsolve * B))) return rc;
+  if ((rc = ensure(ctx, ctx->F->w_ierr, sizeof(int) * (size_t)P.nseq * B))) return rc;
   if ((rc = launch_roots(ctx, P, d_periods, d_swd, B, n, all_modes ? 1 : 0, st))) return rc;
   // per-period retries of failed fundamental-mode searches (rare; idle warps exit at once)
-  if ((rc = ensure(ctx, ctx->w_rstat, sizeof(int) * (size_t)P.nsolve * B))) return rc;
+  if ((rc = ensure(ctx, ctx->F->w_rstat, sizeof(int) * (size_t)P.nsolve * B))) return rc;
   LAUNCH_TU("swd_retry_kernel",
-            launch_roots_retry(P, d_swd, B, n, d_periods, all_modes ? 1 : 0, (double *)ctx->w_croot.p,
-                               (double *)ctx->w_cwork.p, (const int *)ctx->w_ierr.p,
-                               (int *)ctx->w_rstat.p,
+            launch_roots_retry(P, d_swd, B, n, d_periods, all_modes ? 1 : 0, (double *)ctx->F->w_croot.p,
+                               (double *)ctx->F->w_cwork.p, (const int *)ctx->F->w_ierr.p,
+                               (int *)ctx->F->w_rstat.p,
                                ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr, st));
   LAUNCH(swd_retry_finish_kernel, gridFor(B * P.nseq, 128), 128, 0, st, P, B, all_modes ? 1 : 0,
-         (double *)ctx->w_croot.p, (int *)ctx->w_ierr.p, (const int *)ctx->w_rstat.p);
-  if (!want_eigen) return RFS_OK;
+         (double *)ctx->F->w_croot.p, (int *)ctx->F->w_ierr.p, (const int *)ctx->F->w_rstat.p);
+  return RFS_OK;
+}
+
+int run_swd_eigen(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
+                  long long B, int n, bool all_modes, cudaStream_t st) {
+  const int nmo = all_modes ? P.nmode : 1;
+  int rc;
   if ((rc = ensure(ctx, ctx->w_ugr, sizeof(double) * (size_t)nmo * P.nsolve * B))) return rc;
   if ((rc = ensure(ctx, ctx->w_kern, sizeof(double) * (size_t)nmo * P.nsolve * 4 * n * B)))
     return rc;
@@ -339,7 +357,7 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
   // NMAX = 8: the Rayleigh up-sweep vectors live in shared memory ([48][128] doubles per block)
 #define EIG(NM)                                                                                 \
   LAUNCH(swd_eigen_kernel<NM>, gridFor(tot, 128), 128, (NM <= 8 ? 128 * NM * 6 * sizeof(double) : 0), st, \
-         P, d_swd, B, n, d_periods, nmo, (const double *)ctx->w_croot.p, (double *)ctx->w_ugr.p,       \
+         P, d_swd, B, n, d_periods, nmo, (const double *)ctx->F->w_croot.p, (double *)ctx->w_ugr.p,       \
          (double *)ctx->w_kern.p)
   switch (nmax_for(n)) {
     case 8: EIG(8); break;
@@ -350,6 +368,13 @@ int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBl
   }
 #undef EIG
   return RFS_OK;
+}
+
+int run_swd(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
+            long long B, int n, bool all_modes, bool want_eigen, cudaStream_t st) {
+  int rc = run_swd_roots(ctx, P, d_periods, d_swd, B, n, all_modes, st);
+  if (rc || !want_eigen) return rc;
+  return run_swd_eigen(ctx, P, d_periods, d_swd, B, n, all_modes, st);
 }
 
 // ---- RF pipeline on a prepared model block (freq method)
@@ -477,16 +502,29 @@ int set_rf_cfg(rfs_ctx *ctx, int n, double ray_p, int nt, double dt, double gaus
 }
 
 // bytes of workspace one model needs in the fused path (used to size chunks)
+// bytes of workspace one model needs in the fused path: front = model blocks + root-search results
+// (kept for the whole batch), back = eigen / RF workspaces (sized per chunk)
+size_t per_model_front_bytes(const rfs_ctx *ctx, int which) {
+  size_t s = 0;
+  const int n = (which != 1) ? ctx->n_swd : ctx->n_rf;
+  if (which != 1 && ctx->has_swd) {
+    const SwdPlan &P = ctx->plan;
+    const size_t nmo = ctx->modes.size() > 1 ? (size_t)P.nmode : 1;
+    s += sizeof(double) * ((size_t)SWD_NF * n * (ctx->sphere ? 5 : 1) + (1 + nmo) * (size_t)P.nsolve) +
+         sizeof(int) * ((size_t)P.nseq + P.nsolve);
+  }
+  if (which != 2 && ctx->has_rf) s += sizeof(double) * (4 * (size_t)n);
+  return s + sizeof(double) * 2 * (size_t)n;
+}
 size_t per_model_bytes(const rfs_ctx *ctx, int which) {
   size_t s = 0;
   if (which != 1 && ctx->has_swd) {
     const SwdPlan &P = ctx->plan;
     const size_t nmo = ctx->modes.size() > 1 ? (size_t)P.nmode : 1;
-    s += sizeof(double) * ((size_t)SWD_NF * ctx->n_swd + (1 + 2 * nmo) * (size_t)P.nsolve +
-                           nmo * (size_t)P.nsolve * 4 * ctx->n_swd) + sizeof(int) * P.nseq;
+    s += sizeof(double) * (nmo * (size_t)P.nsolve + nmo * (size_t)P.nsolve * 4 * ctx->n_swd);
   }
   if (which != 2 && ctx->has_rf) {
-    s += sizeof(double) * (6 * (size_t)ctx->n_rf) + sizeof(RfLayer) * (size_t)ctx->n_rf +
+    s += sizeof(RfLayer) * (size_t)ctx->n_rf +
          sizeof(double2) * ((size_t)2 * ctx->n2 + (size_t)2 * ctx->n_rf * ctx->n2) +
          sizeof(double) * (1 + 2 * (size_t)ctx->n_rf);
     if (ctx->method == 0)
@@ -514,10 +552,16 @@ int rfs_create(rfs_ctx **out, int device) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_asm, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream_front[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream_front[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream_front[2], cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return RFS_E_CUDA;
   }
+  ctx->fronts.push_back(new Front());
+  ctx->F = ctx->fronts[0];
   if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
   // RFS_ROOTS_TEAM="T,S" pins the root-search mapping (0 = thread-mapped); default: by batch size
   if (const char *e = getenv("RFS_ROOTS_TEAM")) {
@@ -546,20 +590,31 @@ int rfs_create(rfs_ctx **out, int device) {
 void rfs_destroy(rfs_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_swd,  &ctx->w_rfm,  &ctx->w_chain, &ctx->w_rfl, &ctx->d_tw,
-                &ctx->w_croot, &ctx->w_cwork, &ctx->w_ugr, &ctx->w_kern, &ctx->w_ierr,
+  Buf *all[] = {&ctx->d_periods, &ctx->d_dobs, &ctx->w_rfl, &ctx->d_tw,
+                &ctx->w_ugr, &ctx->w_kern,
                 &ctx->w_spec,    &ctx->w_dspec, &ctx->w_urf,  &ctx->w_grf,  &ctx->w_rftr, &ctx->io_x,
                 &ctx->io_U,      &ctx->io_grad, &ctx->io_dsyn, &ctx->io_flag, &ctx->io_a, &ctx->io_b,
                 &ctx->io_c,      &ctx->io_d,    &ctx->io_e,   &ctx->io_f,   &ctx->h_state,
-                &ctx->h_misc,    &ctx->h_out,  &ctx->d_counter, &ctx->w_sph[0], &ctx->w_sph[1],
-                &ctx->w_sph[2],  &ctx->w_sph[3], &ctx->w_rstat};
+                &ctx->h_misc,    &ctx->h_out,  &ctx->d_counter};
   for (Buf *b : all)
     if (b->p) cudaFree(b->p);
+  for (Front *f : ctx->fronts) {
+    Buf *fb[] = {&f->w_sph[0], &f->w_sph[1], &f->w_sph[2], &f->w_sph[3], &f->w_rstat, &f->w_swd,
+                 &f->w_rfm,    &f->w_chain,  &f->w_croot,  &f->w_cwork,  &f->w_ierr};
+    for (Buf *b : fb)
+      if (b->p) cudaFree(b->p);
+    if (f->ev_ready) cudaEventDestroy(f->ev_ready);
+    if (f->ev_prep) cudaEventDestroy(f->ev_prep);
+    delete f;
+  }
+  for (cudaStream_t sf : ctx->stream_front)
+    if (sf) cudaStreamDestroy(sf);
   for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_asm) cudaEventDestroy(ctx->ev_asm);
   delete ctx;
 }
 
@@ -651,9 +706,16 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   if ((int)ctx->dobs.size() != ndata) return fail(ctx, RFS_E_CONFIG, "dobs length != ndata");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t pm = per_model_bytes(ctx, which);
-  long long Bmax = (long long)std::max<size_t>(32, ctx->ws_budget / pm);
+  // chunking: the front buffers (model blocks, roots) are kept for the whole batch, the eigen / RF
+  // workspaces are sized per chunk against what is left of the budget; chunks are balanced
+  const size_t pm = per_model_bytes(ctx, which), pmf = per_model_front_bytes(ctx, which);
+  const size_t front_total = pmf * (size_t)B + (pmf * (size_t)B) / 8;
+  const size_t budget = std::max(ctx->ws_budget > front_total ? ctx->ws_budget - front_total : (size_t)0,
+                                 ctx->ws_budget / 4);
+  long long Bmax = (long long)std::max<size_t>(32, budget / (pm + pm / 8));
   Bmax = std::min(Bmax, 2147483647LL / ((long long)SWD_NF * n));  // 32-bit offsets in SwdModel::ld
+  const int nch = (int)((B + Bmax - 1) / Bmax);
+  const long long Bch = (B + nch - 1) / nch;
   const double *d_dobs = (const double *)ctx->d_dobs.p;
   double tshift = ctx->tshift;
   if (ctx->rf_type == 2) tshift = -tshift;  // src/RF/main.cpp:35
@@ -669,24 +731,62 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   if (multi_mode)
     for (int i = 0; i < nmsel; i++) msel.m[i] = ctx->modes[i];
   const double ray_p_saved = ctx->ray_p;
-  for (long long off = 0; off < B; off += Bmax) {
-    const long long Bc = std::min(Bmax, B - off);
+  while ((int)ctx->fronts.size() < nch) ctx->fronts.push_back(new Front());
+  // ctx->F is switched chunk by chunk; whatever happens it points at fronts[0] again on return
+  struct FrontGuard {
+    rfs_ctx *c;
+    ~FrontGuard() { c->F = c->fronts[0]; }
+  } front_guard{ctx};
+  std::vector<SwdBlocks> blks((size_t)nch);
+  const bool side = ctx->overlap && nch > 1;  // root searches of later chunks on side streams
+
+  // ---- pass A: model blocks and root search of EVERY chunk.  A chunk's root search is latency-bound
+  // when the chunk is small against the machine (n = 200: ~290 ms for anything up to ~25 k models), so
+  // the chunks' searches run concurrently instead of one after the other.
+  CK(cudaEventRecord(ctx->ev_fork, st));  // everything this call launches comes after what is on `st`
+  for (int k = 0; k < nch; k++) {
+    const long long off = (long long)k * Bch, Bc = std::min(Bch, B - off);
+    Front *F = ctx->fronts[k];
+    ctx->F = F;
+    cudaStream_t sk = (k == 0 || !side) ? st : ctx->stream_front[(k - 1) % 3];
+    if (sk != st) CK(cudaStreamWaitEvent(sk, ctx->ev_fork, 0));
     int rc;
     const size_t nB = (size_t)n * Bc;
-    if (use_swd && (rc = ensure(ctx, ctx->w_swd, sizeof(double) * SWD_NF * nB))) return rc;
-    if (use_rf && (rc = ensure(ctx, ctx->w_rfm, sizeof(double) * 4 * nB))) return rc;
-    if ((rc = ensure(ctx, ctx->w_chain, sizeof(double) * 2 * nB))) return rc;
-    LAUNCH(prep_models_kernel, gridFor(Bc * n, 256), 256, 0, st, x + off * 2 * n, Bc, n,
-           use_swd ? (double *)ctx->w_swd.p : nullptr, use_rf ? (double *)ctx->w_rfm.p : nullptr,
-           (double *)ctx->w_chain.p);
+    if (use_swd && (rc = ensure(ctx, F->w_swd, sizeof(double) * SWD_NF * nB))) return rc;
+    if (use_rf && (rc = ensure(ctx, F->w_rfm, sizeof(double) * 4 * nB))) return rc;
+    if ((rc = ensure(ctx, F->w_chain, sizeof(double) * 2 * nB))) return rc;
+    LAUNCH(prep_models_kernel, gridFor(Bc * n, 256), 256, 0, sk, x + off * 2 * n, Bc, n,
+           use_swd ? (double *)F->w_swd.p : nullptr, use_rf ? (double *)F->w_rfm.p : nullptr,
+           (double *)F->w_chain.p);
+    if (!F->ev_prep) CK(cudaEventCreateWithFlags(&F->ev_prep, cudaEventDisableTiming));
+    if (!F->ev_ready) CK(cudaEventCreateWithFlags(&F->ev_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(F->ev_prep, sk));
+    if (use_swd) {
+      if ((rc = make_blocks(ctx, (const double *)F->w_swd.p, Bc, n, ctx->sphere, blks[k], sk))) return rc;
+      if ((rc = run_swd_roots(ctx, ctx->plan, (const double *)ctx->d_periods.p, blks[k], Bc, n, multi_mode, sk)))
+        return rc;
+    }
+    CK(cudaEventRecord(F->ev_ready, sk));
+  }
+
+  // ---- pass B: the memory-hungry stages chunk by chunk (RF branch beside the SWD branch)
+  for (int k = 0; k < nch; k++) {
+    const long long off = (long long)k * Bch, Bc = std::min(Bch, B - off);
+    Front *F = ctx->fronts[k];
+    ctx->F = F;
+    int rc;
+    const size_t nB = (size_t)n * Bc;
     if (use_rf) {
-      // the RF branch is independent of the SWD branch: run it on a second stream so that its
-      // kernels fill the SMs the (latency-bound, < 1 wave) root-search kernel leaves idle
+      // the RF branch only needs the chunk's model blocks: it runs on a second stream, beside the
+      // (latency-bound, < 1 wave) root search and the eigen solves
       cudaStream_t sr = st;
       if (use_swd && ctx->overlap) {
         sr = ctx->stream2;
-        CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(sr, ctx->ev_fork, 0));
+        // RF workspaces and outputs are shared by the chunks: wait for the previous chunk's assemble
+        CK(cudaStreamWaitEvent(sr, k == 0 ? ctx->ev_fork : ctx->ev_asm, 0));
+        CK(cudaStreamWaitEvent(sr, F->ev_prep, 0));
+      } else {
+        CK(cudaStreamWaitEvent(sr, F->ev_prep, 0));
       }
       if ((rc = ensure(ctx, ctx->w_urf, sizeof(double) * Bc))) return rc;
       if ((rc = ensure(ctx, ctx->w_grf, sizeof(double) * 2 * nB))) return rc;
@@ -696,7 +796,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       // ReceiverFunc has one ray parameter, model/model_rf.py:5-18; the list is BASELINE config 3)
       for (int ir = 0; ir < nray; ir++) {
         ctx->ray_p = ctx->ray_ps[ir];
-        rc = run_rf_spectra(ctx, (const double *)ctx->w_rfm.p, (const double *)ctx->w_chain.p, nullptr,
+        rc = run_rf_spectra(ctx, (const double *)F->w_rfm.p, (const double *)F->w_chain.p, nullptr,
                             nullptr, Bc, n, rf_time ? 4 : 2, sigma, sr, rf_time ? RFS_PI64 : RFS_PI32);
         double *dsyn_r = dsyn + off * ndata + (size_t)ir * ctx->nt;
         const double *dobs_r = d_dobs + (size_t)ir * ctx->nt;
@@ -709,7 +809,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
             if (!rc) {
               prof_begin(ctx, "rf_trace_grad_kernel", sr);
               rf_trace_grad_kernel<<<gridFor(Bc * n, 128), 128, 0, sr>>>(
-                  (const double *)ctx->w_rftr.p, (const double *)ctx->w_chain.p,
+                  (const double *)ctx->w_rftr.p, (const double *)F->w_chain.p,
                   (const double *)dsyn_r, (long long)ndata, dobs_r, Bc, n, ctx->nt, Uo, go, ir > 0);
               ctx->launches++;
               prof_end(ctx, sr);
@@ -727,14 +827,13 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       if (sr != st) CK(cudaEventRecord(ctx->ev_join, sr));
     }
     if (use_swd) {
-      SwdBlocks blk;
-      if ((rc = make_blocks(ctx, (const double *)ctx->w_swd.p, Bc, n, ctx->sphere, blk, st))) return rc;
-      if ((rc = run_swd(ctx, ctx->plan, (const double *)ctx->d_periods.p, blk, Bc, n, multi_mode, true, st)))
+      CK(cudaStreamWaitEvent(st, F->ev_ready, 0));
+      if ((rc = run_swd_eigen(ctx, ctx->plan, (const double *)ctx->d_periods.p, blks[k], Bc, n, multi_mode, st)))
         return rc;
       SwdView V;
-      V.blk = blk;
+      V.blk = blks[k];
       V.fwd = 0;
-      V.croot = (const double *)ctx->w_croot.p;
+      V.croot = (const double *)F->w_croot.p;
       V.ugr = (const double *)ctx->w_ugr.p;
       V.kern = (const double *)ctx->w_kern.p;
       V.periods = (const double *)ctx->d_periods.p;
@@ -742,9 +841,10 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
       V.n = n;
       if (use_rf && ctx->overlap) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
       LAUNCH(joint_assemble_kernel, dim3(gridFor(Bc, 32), (unsigned)n), 32 * RFS_ASM_Q, 0, st, ctx->plan, V,
-             (const int *)ctx->w_ierr.p, (const double *)ctx->w_chain.p, ctx->stale, which, n1,
+             (const int *)F->w_ierr.p, (const double *)F->w_chain.p, ctx->stale, which, n1,
              d_dobs, (const double *)ctx->w_urf.p, (const double *)ctx->w_grf.p, wt, U + off,
              grad + off * 2 * n, dsyn + off * ndata, flag + off, msel);
+      CK(cudaEventRecord(ctx->ev_asm, st));
     }
   }
   return RFS_OK;
@@ -836,13 +936,13 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
       blk[F_DTP * nB + (size_t)m * B + b] = 1.0;
       blk[F_RTP * nB + (size_t)m * B + b] = 1.0;
     }
-  if ((rc = ensure(ctx, ctx->w_swd, sizeof(double) * blk.size()))) return rc;
+  if ((rc = ensure(ctx, ctx->F->w_swd, sizeof(double) * blk.size()))) return rc;
   if ((rc = ensure(ctx, ctx->io_a, sizeof(double) * periods.size()))) return rc;
-  CK(cudaMemcpyAsync(ctx->w_swd.p, blk.data(), sizeof(double) * blk.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->F->w_swd.p, blk.data(), sizeof(double) * blk.size(), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->io_a.p, periods.data(), sizeof(double) * periods.size(),
                      cudaMemcpyHostToDevice, st));
   SwdBlocks dblk;
-  if ((rc = make_blocks(ctx, (const double *)ctx->w_swd.p, B, n, sphere ? 1 : 0, dblk, st))) return rc;
+  if ((rc = make_blocks(ctx, (const double *)ctx->F->w_swd.p, B, n, sphere ? 1 : 0, dblk, st))) return rc;
   if ((rc = run_swd(ctx, P, (const double *)ctx->io_a.p, dblk, B, n, all_modes, want_eigen, st)))
     return rc;
   const int nmo = all_modes ? P.nmode : 1;
@@ -856,7 +956,7 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
   }
   for (int mo = 0; mo < nmo; mo++) {
     SwdView V;
-    V.croot = (const double *)ctx->w_croot.p + (size_t)mo * P.nsolve * B;
+    V.croot = (const double *)ctx->F->w_croot.p + (size_t)mo * P.nsolve * B;
     V.ugr = want_eigen ? (const double *)ctx->w_ugr.p + (size_t)mo * P.nsolve * B : nullptr;
     V.kern = want_eigen ? (const double *)ctx->w_kern.p + (size_t)mo * P.nsolve * 4 * n * B : nullptr;
     V.periods = (const double *)ctx->io_a.p;
@@ -894,7 +994,7 @@ static int surf_common(rfs_ctx *ctx, long long B, int n, const double *thk, cons
     }
   }
   std::vector<int> ierr((size_t)P.nseq * B);
-  CK(cudaMemcpyAsync(ierr.data(), ctx->w_ierr.p, sizeof(int) * ierr.size(), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ierr.data(), ctx->F->w_ierr.p, sizeof(int) * ierr.size(), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (ok)
     for (long long b = 0; b < B; b++) {
@@ -979,9 +1079,9 @@ static int rf_common(rfs_ctx *ctx, long long B, int n, const double *thk, const 
       blk[4 * nB + (size_t)m * B + b] = qa[b * n + m];
       blk[5 * nB + (size_t)m * B + b] = qb[b * n + m];
     }
-  if ((rc = ensure(ctx, ctx->w_rfm, sizeof(double) * 6 * nB))) return done(rc);
-  CK(cudaMemcpyAsync(ctx->w_rfm.p, blk.data(), sizeof(double) * 6 * nB, cudaMemcpyHostToDevice, st));
-  const double *d_rfm = (const double *)ctx->w_rfm.p;
+  if ((rc = ensure(ctx, ctx->F->w_rfm, sizeof(double) * 6 * nB))) return done(rc);
+  CK(cudaMemcpyAsync(ctx->F->w_rfm.p, blk.data(), sizeof(double) * 6 * nB, cudaMemcpyHostToDevice, st));
+  const double *d_rfm = (const double *)ctx->F->w_rfm.p;
   double tshift = time_shift;
   if (rf_type == 2) tshift = -tshift;
   const double sigma = (method == 0) ? 0.0 : 1.0 / dt / ctx->nft * 4.;
