@@ -38,7 +38,6 @@ struct Front {
   Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
   Buf w_rstat;
   Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ierr;
-  Buf w_key, w_perm;  // length-sorted job order of the thread-mapped root search
   cudaEvent_t ev_prep = nullptr;   // model blocks of this chunk written
   cudaEvent_t ev_ready = nullptr;  // root search of this chunk finished
 };
@@ -89,9 +88,6 @@ struct rfs_ctx {
   // (model, sequence) with team_S speculative scan slots (swd_roots_team.cuh)
   int team_T = -1, team_S = 1;
   int last_team_T = 0, last_team_S = 1;  // what the last launch used (reported by bench.py)
-  // length-sorted scheduling of the thread-mapped search: -1 automatic (large batches), 0 off, 1 on
-  int sched = -1;
-  int last_sched = 0;
   // per-kernel timing (rfs_profile_eval): CUDA events around every launch while `prof` is set
   struct ProfRec {
     const char *name;
@@ -304,9 +300,6 @@ bool team_supported(int T, int S) { return team_shape_supported(T, S); }
     }                                                           \
   } while (0)
 
-#ifndef RFS_SCHED_MIN_JOBS
-#define RFS_SCHED_MIN_JOBS 24576
-#endif
 int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
                  long long B, int n, int all_modes, cudaStream_t st) {
   unsigned long long *cnt = ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr;
@@ -315,27 +308,10 @@ int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const 
   pick_team(ctx, jobs, n, T, S);
   ctx->last_team_T = T;
   ctx->last_team_S = S;
-  ctx->last_sched = 0;
   if (T == 0) {
-    // large batches are throughput-bound: order the jobs by predicted length so that the 32 lanes of
-    // a warp finish together (swd_roots_tu.cu); below RFS_SCHED_MIN_JOBS the search is latency-bound
-    // and the order cannot matter
-    const int *perm = nullptr;
-    if (ctx->sched > 0 || (ctx->sched < 0 && jobs >= RFS_SCHED_MIN_JOBS)) {
-      const long long Bp = (B + 31) / 32 * 32;
-      int rc;
-      if ((rc = ensure(ctx, ctx->F->w_key, sizeof(unsigned int) * (size_t)jobs))) return rc;
-      if ((rc = ensure(ctx, ctx->F->w_perm, sizeof(int) * (size_t)Bp * P.nseq))) return rc;
-      LAUNCH_TU("swd_roots_sched_key_kernel",
-                launch_sched_keys(P, d_swd, B, n, d_periods, (unsigned int *)ctx->F->w_key.p, st));
-      LAUNCH_TU("swd_roots_sched_sort_kernel",
-                launch_sched_sort(P, B, (const unsigned int *)ctx->F->w_key.p, (int *)ctx->F->w_perm.p, st));
-      perm = (const int *)ctx->F->w_perm.p;
-      ctx->last_sched = 1;
-    }
     LAUNCH_TU("swd_roots_kernel",
               launch_roots_thread(P, d_swd, B, n, d_periods, all_modes, (double *)ctx->F->w_croot.p,
-                                  (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, perm, st));
+                                  (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, st));
     return RFS_OK;
   }
   if (!team_shape_supported(T, S)) return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
@@ -535,7 +511,7 @@ size_t per_model_front_bytes(const rfs_ctx *ctx, int which) {
     const SwdPlan &P = ctx->plan;
     const size_t nmo = ctx->modes.size() > 1 ? (size_t)P.nmode : 1;
     s += sizeof(double) * ((size_t)SWD_NF * n * (ctx->sphere ? 5 : 1) + (1 + nmo) * (size_t)P.nsolve) +
-         sizeof(int) * ((size_t)3 * P.nseq + P.nsolve);  // ierr, sched key + perm, rstat
+         sizeof(int) * ((size_t)P.nseq + P.nsolve);
   }
   if (which != 2 && ctx->has_rf) s += sizeof(double) * (4 * (size_t)n);
   return s + sizeof(double) * 2 * (size_t)n;
@@ -595,7 +571,6 @@ int rfs_create(rfs_ctx **out, int device) {
       ctx->team_S = s2;
     }
   }
-  if (const char *e = getenv("RFS_ROOTS_SCHED")) ctx->sched = atoi(e);  // -1 auto, 0 off, 1 on
   // workspace budget per chunk of the fused path; batches larger than what fits are chunked.  Default:
   // 60 % of the memory free on this GPU now (a B200 has 180 GB: the Jacobians of 8 192 models of 200
   // layers fit in two chunks), overridden in MiB by RFS_WS_BUDGET_MB
@@ -625,8 +600,7 @@ void rfs_destroy(rfs_ctx *ctx) {
     if (b->p) cudaFree(b->p);
   for (Front *f : ctx->fronts) {
     Buf *fb[] = {&f->w_sph[0], &f->w_sph[1], &f->w_sph[2], &f->w_sph[3], &f->w_rstat, &f->w_swd,
-                 &f->w_rfm,    &f->w_chain,  &f->w_croot,  &f->w_cwork,  &f->w_ierr,  &f->w_key,
-                 &f->w_perm};
+                 &f->w_rfm,    &f->w_chain,  &f->w_croot,  &f->w_cwork,  &f->w_ierr};
     for (Buf *b : fb)
       if (b->p) cudaFree(b->p);
     if (f->ev_ready) cudaEventDestroy(f->ev_ready);
@@ -1231,12 +1205,6 @@ int rfs_set_roots_team(rfs_ctx *ctx, int T, int S) {
   ctx->team_S = T > 0 ? S : 1;
   return RFS_OK;
 }
-int rfs_set_roots_sched(rfs_ctx *ctx, int mode) {
-  if (!ctx || mode < -1 || mode > 1) return RFS_E_ARG;
-  ctx->sched = mode;
-  return RFS_OK;
-}
-int rfs_last_roots_sched(rfs_ctx *ctx) { return ctx ? ctx->last_sched : 0; }
 int rfs_last_roots_team(rfs_ctx *ctx, int *T, int *S) {
   if (!ctx || !T || !S) return RFS_E_ARG;
   *T = ctx->last_team_T;

@@ -15,14 +15,7 @@ namespace rfs {
 // one thread per (model, sequence)
 cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
                                 const double *periods, int all_modes, double *croot, double *cwork,
-                                int *ierr, unsigned long long *counter, const int *perm,
-                                cudaStream_t st);
-// length-sorted job order for launch_roots_thread: key [nseq][B] = predicted scan length of every
-// job; perm [nseq][ceil32(B)] = model indices of each sequence, longest first, -1 padded
-cudaError_t launch_sched_keys(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
-                              const double *periods, unsigned int *key, cudaStream_t st);
-cudaError_t launch_sched_sort(const SwdPlan &P, long long B, const unsigned int *key, int *perm,
-                              cudaStream_t st);
+                                int *ierr, unsigned long long *counter, cudaStream_t st);
 // T lanes per (model, sequence), S speculative scan points; false if (T,S) is not instantiated
 bool team_shape_supported(int T, int S);
 cudaError_t launch_roots_team(int T, int S, const SwdPlan &P, const SwdBlocks &blk, long long B, int n,

@@ -143,45 +143,3 @@ def test_mapping_is_chosen_by_batch_size(tctx):
     assert ctx.last_roots_team()[0] > 0
     for a, b in zip(big, small):
         assert _same(a[:64], b)
-
-
-def test_length_sorted_schedule_is_bit_identical(tctx):
-    """Large batches run the thread-mapped search in length-sorted job order (swd_sched_*_kernel):
-    which lane solves which (model, sequence) changes, nothing else.  Every output bit and the
-    evaluation count must equal the unsorted run — ragged batch size (not a multiple of 32), wild
-    models (failed modes, retries), multi-mode and spherical configurations included."""
-    ctx = tctx
-    cfg, x0 = f1_config(), f1_true_model()
-    try:
-        for B, modes, sphere in [(40000 + 13, 0, False), (9001, [0, 1], False), (8192 + 5, 0, True)]:
-            X = sorted_uniform_models(driver_bounds(x0), B, seed=77)
-            X[B // 2:] = _wild(B - B // 2, 9)
-            ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"], tLc=cfg["tRc"][:11], mode=modes, sphere=sphere)
-            nd = (72 + 11) * (len(modes) if isinstance(modes, list) else 1)
-            ctx.config_obs(np.full(nd, 3.0))
-            ctx.set_roots_team(0)
-            ctx.set_roots_sched(0)
-            ctx.count_evals(True)
-            ref = ctx.misfit_grad_host(X, which=2)
-            nev0 = ctx.read_evals()
-            assert not ctx.last_roots_sched()
-            ctx.set_roots_sched(1)
-            ctx.count_evals(True)
-            got = ctx.misfit_grad_host(X, which=2)
-            nev1 = ctx.read_evals()
-            assert ctx.last_roots_sched()
-            for a, b in zip(ref, got):
-                assert _same(a, b), (B, modes, sphere)
-            assert nev0 == nev1
-        # automatic: on for the large thread-mapped batch, off for a small one
-        ctx.set_roots_sched(-1)
-        ctx.set_roots_team(-1)
-        ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"])
-        ctx.config_obs(np.full(72, 3.0))
-        ctx.misfit_grad_host(sorted_uniform_models(driver_bounds(x0), 16384, seed=3), which=2)
-        assert ctx.last_roots_sched() and ctx.last_roots_team() == (0, 1)
-        ctx.misfit_grad_host(sorted_uniform_models(driver_bounds(x0), 512, seed=3), which=2)
-        assert not ctx.last_roots_sched()
-    finally:
-        ctx.count_evals(False)
-        ctx.set_roots_sched(-1)
