@@ -88,7 +88,6 @@ struct rfs_ctx {
   // (model, sequence) with team_S speculative scan slots (swd_roots_team.cuh)
   int team_T = -1, team_S = 1;
   int last_team_T = 0, last_team_S = 1;  // what the last launch used (reported by bench.py)
-  int rf_block = 128;  // threads per block of rf_propagate_kernel (RFS_RF_BLOCK: experiment)
   // per-kernel timing (rfs_profile_eval): CUDA events around every launch while `prof` is set
   struct ProfRec {
     const char *name;
@@ -395,7 +394,7 @@ int run_rf_spectra(rfs_ctx *ctx, const double *d_rfm, const double *d_chain, con
          (RfLayer *)ctx->w_rfl.p);
   const long long tot = B * n2;
 #define PROP(NM, NQ)                                                                             \
-  LAUNCH((rf_propagate_kernel<NM, NQ>), gridFor(tot, ctx->rf_block), ctx->rf_block, 0, st,       \
+  LAUNCH((rf_propagate_kernel<NM, NQ>), gridFor(tot, 128), 128, 0, st,                           \
          (const RfLayer *)ctx->w_rfl.p, d_chain, B, n, n2, ctx->nft, ctx->dt, ctx->ray_p, sigma, \
          pi_used, ctx->rf_type, (double2 *)ctx->w_spec.p, dsp)
 #define PROPQ(NM)    \
@@ -564,10 +563,6 @@ int rfs_create(rfs_ctx **out, int device) {
   ctx->fronts.push_back(new Front());
   ctx->F = ctx->fronts[0];
   if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
-  if (const char *e = getenv("RFS_RF_BLOCK")) {
-    const int v = atoi(e);
-    if (v == 32 || v == 64 || v == 128) ctx->rf_block = v;
-  }
   // RFS_ROOTS_TEAM="T,S" pins the root-search mapping (0 = thread-mapped); default: by batch size
   if (const char *e = getenv("RFS_ROOTS_TEAM")) {
     int t = -1, s2 = 1;
