@@ -45,6 +45,18 @@ struct SwdModel {
   }
 };
 
+// The same seven root-search fields of the NT threads of a block staged in shared memory,
+// [layer][field][thread]: thread-constant base, one multiply per layer, immediate field offsets.
+#define RFS_ROOT_NF 7  // F_D .. F_IRHO
+template <int NT>
+struct SmemColModel {
+  const double *p;  // [n][RFS_ROOT_NF][NT]
+  int n;
+  RFS_DEVINL double ld(int f, int m, long long col) const {
+    return p[(m * RFS_ROOT_NF + f) * NT + (int)col];
+  }
+};
+
 // ---- Love secular function: Haskell 2-vector from the half-space up (surfdisp96.f:727-787)
 // love_layer builds the layer terms, love_apply propagates + normalises the 2-vector; the split
 // lets the team kernel (swd_roots_team.cuh) build layers in parallel with the same operations.
@@ -434,7 +446,10 @@ enum { PH_SETUP = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE, PH_DONE };
 // the last one is done; lanes that are finished evaluate look-ahead scan points c2+j*dc for one
 // scanning lane (same repeated additions, hence bit-identical grid) and hand the values over
 // through shared memory (`wsm`, 32 doubles per warp).  `valid` = this lane owns a sequence.
-RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &sq,
+// MT: model accessor; mb = this lane's model index for M.ld (the batch index b for the global block,
+// the thread's column for a block staged in shared memory); b always indexes the outputs.
+template <class MT>
+RFS_DEVINL int swd_solve_sequence(const MT &M, long long b, long long mb, const SwdSeq &sq,
                                   const double *__restrict__ periods, int nmode, int all_modes,
                                   double *__restrict__ cout, long long cout_mode_stride,
                                   double *__restrict__ cwork, long long stride,
@@ -445,11 +460,11 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
   const int ifunc = sq.ifunc;
   const int kmax = sq.nper;
   // ---- prologue of surfdisp96 (:128-220): extremal velocities and float32 start value
-  const int llw = (M.ld(F_B, 0, b) <= 0.0) ? 2 : 1;
+  const int llw = (M.ld(F_B, 0, mb) <= 0.0) ? 2 : 1;
   int jmn = 0, jsol = 1;
   float betmx = -1.e20f, betmn = 1.e20f;
   for (int i = 0; i < mmax; i++) {
-    const float bi = (float)M.ld(F_B, i, b), ai = (float)M.ld(F_A, i, b);
+    const float bi = (float)M.ld(F_B, i, mb), ai = (float)M.ld(F_A, i, mb);
     if (bi > 0.01f && bi < betmn) {
       betmn = bi;
       jmn = i;
@@ -465,7 +480,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
   if (jsol == 0)
     cc1 = betmn;
   else
-    cc1 = gtsolh_dev((float)M.ld(F_A, jmn, b), (float)M.ld(F_B, jmn, b));
+    cc1 = gtsolh_dev((float)M.ld(F_A, jmn, mb), (float)M.ld(F_B, jmn, mb));
   cc1 = __fmul_rn(0.95f, cc1);
   cc1 = __fmul_rn(0.90f, cc1);
   const double cc = (double)cc1;
@@ -546,7 +561,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     int nhelp = 0, hsrc = 0, hj = 0;
     bool helper = false;
     double e_c = ceval, e_om = omega, e_iom = iomega;
-    long long e_b = b;
+    long long e_b = mb;
     int e_llw = llw, e_if = ifunc;
     if (done_mask != 0u && want_mask != 0u) {
       hsrc = __ffs(want_mask) - 1;
@@ -554,7 +569,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
       const double c_h = __shfl_sync(FULL, ceval, hsrc);
       const double om_h = __shfl_sync(FULL, omega, hsrc);
       const double iom_h = __shfl_sync(FULL, iomega, hsrc);
-      const long long b_h = __shfl_sync(FULL, b, hsrc);
+      const long long b_h = __shfl_sync(FULL, mb, hsrc);
       const int llw_h = __shfl_sync(FULL, llw, hsrc);
       const int if_h = __shfl_sync(FULL, ifunc, hsrc);
       if (phase == PH_DONE) {
@@ -593,7 +608,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     // one upward/downward scan step given Delta(c2) (getsol :457-479)
     auto scan_step = [&](double v) {
       del2 = v;
-      if (sgn1(del1) != sgn1(del2)) {
+      if (neg1(del1) != neg1(del2)) {
         c3 = 0.5 * (c1 + c2);  // bracketed -> nevill: initial half
         ceval = c3;
         nev = 1;
@@ -621,8 +636,8 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     if (phase == PH_G_FIRST) {
       del1 = val;
       if (ifirst == 1) del1st = del1;
-      const double plmn = sgn1(del1st) * sgn1(del1);
-      idir = (ifirst == 1 || plmn >= 0.0) ? +1 : -1;
+      // plmn = dsign(1, del1st) * dsign(1, del1) >= 0 (:452-456)
+      idir = (ifirst == 1 || neg1(del1st) == neg1(del1)) ? +1 : -1;
       for (;;) {  // label 1000 (:457-470)
         c2 = (idir > 0) ? c1 + dc : c1 - dc;
         if (c2 <= clow) {
@@ -664,7 +679,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
     if (body) {
       const double s13 = del1 - del3;
       const double s32 = del3 - del2;
-      if (sgn1(del3) * sgn1(del1) < 0.0) {
+      if (neg1(del3) != neg1(del1)) {
         c2 = c3;
         del2 = del3;
       } else {
@@ -674,7 +689,7 @@ RFS_DEVINL int swd_solve_sequence(const SwdModel &M, long long b, const SwdSeq &
       if (fabs(c1 - c2) <= 1.e-6 * c1) {
         iret = 2;
       } else {
-        if (sgn1(s13) != sgn1(s32)) nev = 0;
+        if (neg1(s13) != neg1(s32)) nev = 0;
         const double ss1 = fabs(del1), ss2 = fabs(del2);
         const double s1 = (double)0.01f * ss1, s2 = (double)0.01f * ss2;
         bool do_half = (s1 > ss2 || s2 > ss1 || nev == 0);

@@ -14,21 +14,42 @@ namespace rfs {
 #ifndef RFS_ROOTS_BLOCK
 #define RFS_ROOTS_BLOCK 128
 #endif
+#ifndef RFS_ROOTS_STAGE_NMAX
+#define RFS_ROOTS_STAGE_NMAX 8
+#endif
+// STAGED: the seven root-search fields of the block's models are copied to shared memory first
+// ([n][7][128] doubles, n <= RFS_ROOTS_STAGE_NMAX) and every secular evaluation reads them from there
+// (one LDS with an immediate offset per value instead of index arithmetic + a global load).
+template <bool STAGED>
 __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
     swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
                      int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
   __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
+  extern __shared__ double stage[];
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool valid = i < B * plan.nseq;
   const long long b = valid ? i % B : 0;
   const int s = valid ? (int)(i / B) : 0;
   SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
   unsigned int nev = 0;
-  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
-                                   (long long)plan.nsolve * B, cwork, B, nev, valid,
-                                   wsm_all[threadIdx.x >> 5], -1);
+  int e;
+  if (STAGED) {
+    for (int m = 0; m < n; m++)
+#pragma unroll
+      for (int f = 0; f < RFS_ROOT_NF; f++)
+        stage[(m * RFS_ROOT_NF + f) * RFS_ROOTS_BLOCK + threadIdx.x] = M.ld(f, m, b);
+    __syncwarp();  // a lane only ever reads columns of its own warp (its own, or the lane it helps)
+    SmemColModel<RFS_ROOTS_BLOCK> Ms{stage, n};
+    e = swd_solve_sequence(Ms, b, (long long)threadIdx.x, plan.seq[s], periods, plan.nmode, all_modes,
+                           croot, (long long)plan.nsolve * B, cwork, B, nev, valid,
+                           wsm_all[threadIdx.x >> 5], -1);
+  } else {
+    e = swd_solve_sequence(M, b, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+                           (long long)plan.nsolve * B, cwork, B, nev, valid,
+                           wsm_all[threadIdx.x >> 5], -1);
+  }
   if (valid) ierr[(long long)s * B + b] = e;
   if (neval_total) {
     // one aggregated atomic per warp: algorithmic-work counter for the roofline (bench.py)
@@ -76,7 +97,7 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
   }
   SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
   unsigned int nev = 0;
-  const int e = swd_solve_sequence(M, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
+  const int e = swd_solve_sequence(M, b, b, plan.seq[s], periods, plan.nmode, all_modes, croot,
                                    (long long)plan.nsolve * B, cwork, B, nev, valid,
                                    wsm_all[threadIdx.x >> 5], k);
   if (inrange) rstat[(long long)solve * B + b] = valid ? e : -1;
@@ -95,8 +116,18 @@ static inline unsigned grid_for(long long total, int block) {
 cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
                                 const double *periods, int all_modes, double *croot, double *cwork,
                                 int *ierr, unsigned long long *counter, cudaStream_t st) {
-  swd_roots_kernel<<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
-      P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+  if (n <= RFS_ROOTS_STAGE_NMAX) {
+    const size_t sm = sizeof(double) * RFS_ROOT_NF * (size_t)n * RFS_ROOTS_BLOCK;
+    if (sm > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(swd_roots_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return e;
+    }
+    swd_roots_kernel<true><<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, sm, st>>>(
+        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+  } else {
+    swd_roots_kernel<false><<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
+        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+  }
   return cudaGetLastError();
 }
 
