@@ -425,6 +425,7 @@ def main():
     ctx.count_evals(False)
     n_fail = int((Fl == 0).sum().item())
     mapping_main = ctx.last_roots_team()
+    sorted_main = ctx.last_roots_sched()
 
     # ---- per-kernel timing, live: CUDA events around every launch of one evaluation (RF branch
     # serialised for these calls so that each kernel is timed alone), median of 5 calls
@@ -598,9 +599,13 @@ def main():
                     "note": "all measured in this run: peak = DFMA micro-benchmark (MEASURED_PEAKS.json has no "
                             "FP64 figure); achieved = secular evaluations counted on device x (n-1) layer steps x "
                             "F_R=375 flop / kernel time from CUDA events around the launch (median of 5 "
-                            "rfs_profile_eval calls, RF branch serialised so that the kernel runs alone)",
+                            "rfs_profile_eval calls, RF branch serialised so that the kernel runs alone); "
+                            "kernel_ms is the whole root-search stage: the search kernel plus the two small "
+                            "kernels that build the length-sorted job order, whose 7 evaluations per job are "
+                            "NOT counted as algorithmic work",
                     "secular_evals_per_launch": evals_per_launch,
-                    "root_search_mapping": {"T": mapping_main[0], "S": mapping_main[1]}}
+                    "root_search_mapping": {"T": mapping_main[0], "S": mapping_main[1],
+                                            "length_sorted_job_order": bool(sorted_main)}}
         for fn in ("r02_traffic.json", "r01_traffic.json"):
             tr = os.path.join(ROOT, "profiles", fn)
             if os.path.exists(tr):

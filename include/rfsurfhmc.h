@@ -151,6 +151,15 @@ int rfs_count_evals(rfs_ctx *ctx, int enable);
  * (csrc/swd_roots_team.cuh).  Environment override at rfs_create: RFS_ROOTS_TEAM="T,S". */
 int rfs_set_roots_team(rfs_ctx *ctx, int T, int S);
 int rfs_last_roots_team(rfs_ctx *ctx, int *T, int *S);
+/* Length-sorted job order of the thread-mapped root search (no reference counterpart): large batches
+ * are solved longest-job-first through a permutation built on the device (a bisection estimate of the
+ * phase velocity at the longest period predicts the scan length of every (model, sequence) job).  The
+ * order changes which lane solves which job and nothing else: results are bit-identical.
+ * mode < 0 automatic (on for large, throughput-bound batches; default), 0 off, 1 on.
+ * rfs_last_roots_sched: 1 if the last root search ran in sorted order.  Environment override at
+ * rfs_create: RFS_ROOTS_SCHED. */
+int rfs_set_roots_sched(rfs_ctx *ctx, int mode);
+int rfs_last_roots_sched(rfs_ctx *ctx);
 long long rfs_read_evals(rfs_ctx *ctx);
 int rfs_read_eval_stats(rfs_ctx *ctx, long long *out3); /* total, slowest thread, threads > 2000 */
 int rfs_measure_fp64_peak(rfs_ctx *ctx, double *tflops);

@@ -104,6 +104,10 @@ def load_library():
         L.rfs_profile_kernel_name.argtypes = [C.c_int]
         L.rfs_set_roots_team.restype = C.c_int
         L.rfs_set_roots_team.argtypes = [_vp, C.c_int, C.c_int]
+        L.rfs_set_roots_sched.restype = C.c_int
+        L.rfs_set_roots_sched.argtypes = [_vp, C.c_int]
+        L.rfs_last_roots_sched.restype = C.c_int
+        L.rfs_last_roots_sched.argtypes = [_vp]
         L.rfs_last_roots_team.restype = C.c_int
         L.rfs_last_roots_team.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.rfs_selftest_math.restype = C.c_int
@@ -120,7 +124,8 @@ def exported_symbols():
             "rfs_surf_adjoint_kernel_modes", "rfs_rf_forward", "rfs_rf_kernel", "rfs_rf_kernel_all",
             "rfs_hmc_run", "rfs_hmc_last_evals", "rfs_count_evals", "rfs_read_evals",
             "rfs_measure_fp64_peak", "rfs_read_eval_stats", "rfs_selftest_math",
-            "rfs_set_roots_team", "rfs_last_roots_team", "rfs_profile_eval", "rfs_profile_kernel_name",
+            "rfs_set_roots_team", "rfs_last_roots_team", "rfs_set_roots_sched",
+            "rfs_last_roots_sched", "rfs_profile_eval", "rfs_profile_kernel_name",
             "rfs_config_swd_modes", "rfs_config_rf_rays", "rfs_hmc_last_steps", "rfs_set_hmc_options"]
 
 
@@ -185,6 +190,14 @@ class Context:
         """Pin the root-search mapping: T<0 automatic, 0 thread-mapped, else T lanes per sequence with
         S speculative scan points (results are bit-identical for every mapping)."""
         self._ck(self.L.rfs_set_roots_team(self.h, int(T), int(S)))
+
+    def set_roots_sched(self, mode=-1):
+        """Length-sorted job order of the thread-mapped root search: -1 automatic (large batches), 0 off,
+        1 on.  Results are bit-identical either way."""
+        self._ck(self.L.rfs_set_roots_sched(self.h, int(mode)))
+
+    def last_roots_sched(self):
+        return bool(self.L.rfs_last_roots_sched(self.h))
 
     def last_roots_team(self):
         t, s = C.c_int(0), C.c_int(0)

@@ -38,7 +38,9 @@ struct Front {
   Buf w_sph[4];  // spherical earth: rootR, rootL, eigR, eigL model blocks
   Buf w_rstat;
   Buf w_swd, w_rfm, w_chain, w_croot, w_cwork, w_ierr;
-  cudaEvent_t ev_prep = nullptr;   // model blocks of this chunk written
+  Buf w_key, w_perm;  // length-sorted job order of the thread-mapped root search
+  cudaEvent_t ev_prep = nullptr;   // model blocks of this chunk written, its root search about to be enqueued
+  bool prep_pending = false;       // ev_prep still to be recorded (release_rf_branch)
   cudaEvent_t ev_ready = nullptr;  // root search of this chunk finished
 };
 
@@ -88,6 +90,10 @@ struct rfs_ctx {
   // (model, sequence) with team_S speculative scan slots (swd_roots_team.cuh)
   int team_T = -1, team_S = 1;
   int last_team_T = 0, last_team_S = 1;  // what the last launch used (reported by bench.py)
+  // length-sorted job order of the thread-mapped search: -1 automatic (large batches), 0 off, 1 on
+  int sched = -1;
+  int last_sched = 0;
+  int nsm = 148;  // SMs of the device
   // per-kernel timing (rfs_profile_eval): CUDA events around every launch while `prof` is set
   struct ProfRec {
     const char *name;
@@ -300,6 +306,22 @@ bool team_supported(int T, int S) { return team_shape_supported(T, S); }
     }                                                           \
   } while (0)
 
+// The RF branch of a chunk (second stream) is released by the event ev_prep.  It is recorded right
+// before the root-search kernel is launched, not right after the model preparation: the RF kernels
+// have large grids and would otherwise take every SM while the short scheduling kernels of the sorted
+// order run, leaving the latency-bound root search to trickle in behind them.
+static inline void release_rf_branch(rfs_ctx *ctx, cudaStream_t st) {
+  if (ctx->F->prep_pending && ctx->F->ev_prep) {
+    cudaEventRecord(ctx->F->ev_prep, st);
+    ctx->F->prep_pending = false;
+  }
+}
+
+// batches from this many (model, sequence) jobs on are throughput-bound in the thread mapping: below,
+// the job order does not matter (tools/gpu_r2_s.sh: no gain at 36 864 jobs, 8 % at 49 152, 11 % at 196 608)
+#ifndef RFS_SCHED_MIN_JOBS
+#define RFS_SCHED_MIN_JOBS 32768
+#endif
 int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const SwdBlocks &d_swd,
                  long long B, int n, int all_modes, cudaStream_t st) {
   unsigned long long *cnt = ctx->count_evals ? (unsigned long long *)ctx->d_counter.p : nullptr;
@@ -308,13 +330,29 @@ int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const 
   pick_team(ctx, jobs, n, T, S);
   ctx->last_team_T = T;
   ctx->last_team_S = S;
+  ctx->last_sched = 0;
   if (T == 0) {
+    const int *perm = nullptr;
+    if ((ctx->sched > 0 || (ctx->sched < 0 && jobs >= RFS_SCHED_MIN_JOBS)) && jobs < 2147483647LL) {
+      int rc;
+      if ((rc = ensure(ctx, ctx->F->w_key, sizeof(unsigned int) * (size_t)jobs))) return rc;
+      if ((rc = ensure(ctx, ctx->F->w_perm, sizeof(int) * (size_t)jobs))) return rc;
+      LAUNCH_TU("swd_roots_sched_key_kernel",
+                launch_sched_keys(P, d_swd, B, n, d_periods, (unsigned int *)ctx->F->w_key.p, st));
+      LAUNCH_TU("swd_roots_sched_sort_kernel",
+                launch_sched_sort(P, B, (const unsigned int *)ctx->F->w_key.p, (int *)ctx->F->w_perm.p, st));
+      perm = (const int *)ctx->F->w_perm.p;
+      ctx->last_sched = 1;
+    }
+    release_rf_branch(ctx, st);
     LAUNCH_TU("swd_roots_kernel",
               launch_roots_thread(P, d_swd, B, n, d_periods, all_modes, (double *)ctx->F->w_croot.p,
-                                  (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, st));
+                                  (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, perm,
+                                  ctx->nsm, st));
     return RFS_OK;
   }
   if (!team_shape_supported(T, S)) return fail(ctx, RFS_E_ARG, "unsupported root-search team shape");
+  release_rf_branch(ctx, st);
   LAUNCH_TU("swd_roots_team_kernel",
             launch_roots_team(T, S, P, d_swd, B, n, d_periods, all_modes, (double *)ctx->F->w_croot.p,
                               (double *)ctx->F->w_cwork.p, (int *)ctx->F->w_ierr.p, cnt, st));
@@ -511,7 +549,7 @@ size_t per_model_front_bytes(const rfs_ctx *ctx, int which) {
     const SwdPlan &P = ctx->plan;
     const size_t nmo = ctx->modes.size() > 1 ? (size_t)P.nmode : 1;
     s += sizeof(double) * ((size_t)SWD_NF * n * (ctx->sphere ? 5 : 1) + (1 + nmo) * (size_t)P.nsolve) +
-         sizeof(int) * ((size_t)P.nseq + P.nsolve);
+         sizeof(int) * ((size_t)3 * P.nseq + P.nsolve);  // ierr, sched key + perm, rstat
   }
   if (which != 2 && ctx->has_rf) s += sizeof(double) * (4 * (size_t)n);
   return s + sizeof(double) * 2 * (size_t)n;
@@ -563,6 +601,11 @@ int rfs_create(rfs_ctx **out, int device) {
   ctx->fronts.push_back(new Front());
   ctx->F = ctx->fronts[0];
   if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
+  if (const char *e = getenv("RFS_ROOTS_SCHED")) ctx->sched = atoi(e) < 0 ? -1 : (atoi(e) > 0 ? 1 : 0);
+  {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->nsm = v;
+  }
   // RFS_ROOTS_TEAM="T,S" pins the root-search mapping (0 = thread-mapped); default: by batch size
   if (const char *e = getenv("RFS_ROOTS_TEAM")) {
     int t = -1, s2 = 1;
@@ -600,7 +643,8 @@ void rfs_destroy(rfs_ctx *ctx) {
     if (b->p) cudaFree(b->p);
   for (Front *f : ctx->fronts) {
     Buf *fb[] = {&f->w_sph[0], &f->w_sph[1], &f->w_sph[2], &f->w_sph[3], &f->w_rstat, &f->w_swd,
-                 &f->w_rfm,    &f->w_chain,  &f->w_croot,  &f->w_cwork,  &f->w_ierr};
+                 &f->w_rfm,    &f->w_chain,  &f->w_croot,  &f->w_cwork,  &f->w_ierr,  &f->w_key,
+                 &f->w_perm};
     for (Buf *b : fb)
       if (b->p) cudaFree(b->p);
     if (f->ev_ready) cudaEventDestroy(f->ev_ready);
@@ -760,12 +804,14 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
            (double *)F->w_chain.p);
     if (!F->ev_prep) CK(cudaEventCreateWithFlags(&F->ev_prep, cudaEventDisableTiming));
     if (!F->ev_ready) CK(cudaEventCreateWithFlags(&F->ev_ready, cudaEventDisableTiming));
-    CK(cudaEventRecord(F->ev_prep, sk));
+    F->prep_pending = true;  // recorded by launch_roots right before the search kernel
+    if (!use_swd) release_rf_branch(ctx, sk);
     if (use_swd) {
       if ((rc = make_blocks(ctx, (const double *)F->w_swd.p, Bc, n, ctx->sphere, blks[k], sk))) return rc;
       if ((rc = run_swd_roots(ctx, ctx->plan, (const double *)ctx->d_periods.p, blks[k], Bc, n, multi_mode, sk)))
         return rc;
     }
+    release_rf_branch(ctx, sk);
     CK(cudaEventRecord(F->ev_ready, sk));
   }
 
@@ -1205,6 +1251,12 @@ int rfs_set_roots_team(rfs_ctx *ctx, int T, int S) {
   ctx->team_S = T > 0 ? S : 1;
   return RFS_OK;
 }
+int rfs_set_roots_sched(rfs_ctx *ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return RFS_E_ARG;
+  ctx->sched = mode;
+  return RFS_OK;
+}
+int rfs_last_roots_sched(rfs_ctx *ctx) { return ctx ? ctx->last_sched : 0; }
 int rfs_last_roots_team(rfs_ctx *ctx, int *T, int *S) {
   if (!ctx || !T || !S) return RFS_E_ARG;
   *T = ctx->last_team_T;

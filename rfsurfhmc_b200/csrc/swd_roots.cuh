@@ -430,6 +430,36 @@ RFS_DEVINL float gtsolh_dev(float a, float b) {
 }
 
 // phases of the flattened getsol/nevill state machine
+// prologue of surfdisp96 (:128-220): water-layer flag, largest S velocity and the float32 start
+// value cc1 = 0.90 * 0.95 * (Rayleigh velocity of the slowest layer as a half space) -- all REAL*4
+template <class MT>
+RFS_DEVINL void swd_start_values(const MT &M, long long mb, int &llw, float &betmx, float &cc1) {
+  const int mmax = M.n;
+  llw = (M.ld(F_B, 0, mb) <= 0.0) ? 2 : 1;
+  int jmn = 0, jsol = 1;
+  float betmn = 1.e20f;
+  betmx = -1.e20f;
+  for (int i = 0; i < mmax; i++) {
+    const float bi = (float)M.ld(F_B, i, mb), ai = (float)M.ld(F_A, i, mb);
+    if (bi > 0.01f && bi < betmn) {
+      betmn = bi;
+      jmn = i;
+      jsol = 1;
+    } else if (bi <= 0.01f && ai < betmn) {
+      betmn = ai;
+      jmn = i;
+      jsol = 0;
+    }
+    if (bi > betmx) betmx = bi;
+  }
+  if (jsol == 0)
+    cc1 = betmn;
+  else
+    cc1 = gtsolh_dev((float)M.ld(F_A, jmn, mb), (float)M.ld(F_B, jmn, mb));
+  cc1 = __fmul_rn(0.95f, cc1);
+  cc1 = __fmul_rn(0.90f, cc1);
+}
+
 enum { PH_SETUP = 0, PH_G_FIRST, PH_G_SCAN, PH_N_TOP, PH_N_OUTSIDE, PH_DONE };
 
 // Solve all modes 1..nmode of sequence `sq` for model b.
@@ -456,33 +486,12 @@ RFS_DEVINL int swd_solve_sequence(const MT &M, long long b, long long mb, const 
                                   unsigned int &n_evals, bool valid, double *wsm, int only_k) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int mmax = M.n;
   const int ifunc = sq.ifunc;
   const int kmax = sq.nper;
   // ---- prologue of surfdisp96 (:128-220): extremal velocities and float32 start value
-  const int llw = (M.ld(F_B, 0, mb) <= 0.0) ? 2 : 1;
-  int jmn = 0, jsol = 1;
-  float betmx = -1.e20f, betmn = 1.e20f;
-  for (int i = 0; i < mmax; i++) {
-    const float bi = (float)M.ld(F_B, i, mb), ai = (float)M.ld(F_A, i, mb);
-    if (bi > 0.01f && bi < betmn) {
-      betmn = bi;
-      jmn = i;
-      jsol = 1;
-    } else if (bi <= 0.01f && ai < betmn) {
-      betmn = ai;
-      jmn = i;
-      jsol = 0;
-    }
-    if (bi > betmx) betmx = bi;
-  }
-  float cc1;
-  if (jsol == 0)
-    cc1 = betmn;
-  else
-    cc1 = gtsolh_dev((float)M.ld(F_A, jmn, mb), (float)M.ld(F_B, jmn, mb));
-  cc1 = __fmul_rn(0.95f, cc1);
-  cc1 = __fmul_rn(0.90f, cc1);
+  int llw;
+  float betmx, cc1;
+  swd_start_values(M, mb, llw, betmx, cc1);
   const double cc = (double)cc1;
   const double dc = (double)0.005f;
   const double one = 1.0e-2, onea = 1.5;

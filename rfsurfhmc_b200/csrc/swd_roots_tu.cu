@@ -25,11 +25,25 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
     swd_roots_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
                      const double *__restrict__ periods, int all_modes,
                      double *__restrict__ croot, double *__restrict__ cwork,
-                     int *__restrict__ ierr, unsigned long long *__restrict__ neval_total) {
+                     int *__restrict__ ierr, unsigned long long *__restrict__ neval_total,
+                     const int *__restrict__ perm, int nsm) {
   __shared__ double wsm_all[RFS_ROOTS_BLOCK / 32][33];
   extern __shared__ double stage[];
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const bool valid = i < B * plan.nseq;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  bool valid = i < B * plan.nseq;
+  if (perm) {
+    // length-sorted order (see swd_sched_key_kernel): perm lists the jobs longest first; a block takes
+    // four adjacent warps of that list, and rounds of nsm blocks (one per SM) alternate between the
+    // longest and the shortest blocks left, so that an SM holds long + short + medium blocks of about
+    // equal total work and its short block retires early (room for the RF branch beside it)
+    const long long J = B * plan.nseq, W = (J + 31) / 32;
+    const long long Q = (W + RFS_ROOTS_BLOCK / 32 - 1) / (RFS_ROOTS_BLOCK / 32);
+    const long long q = blockIdx.x, t = q / nsm, pos = q % nsm;
+    const long long rank = (t & 1) ? (Q - 1 - ((t - 1) / 2) * nsm - pos) : ((t / 2) * nsm + pos);
+    const long long j = (rank * (RFS_ROOTS_BLOCK / 32) + (threadIdx.x >> 5)) * 32 + (threadIdx.x & 31);
+    valid = j < J;
+    i = valid ? __ldg(perm + j) : 0;
+  }
   const long long b = valid ? i % B : 0;
   const int s = valid ? (int)(i / B) : 0;
   SwdModel M(blk.root[plan.seq[s].ifunc == 2 ? 0 : 1], B, n);
@@ -59,6 +73,118 @@ __global__ void __launch_bounds__(RFS_ROOTS_BLOCK, RFS_ROOTS_MINBLOCKS)
     atomicMax(neval_total + 1, (unsigned long long)nev);          // slowest thread
     if (nev > 2000u) atomicAdd(neval_total + 2, 1ull);            // heavy threads (> 2000 evals)
   }
+}
+
+// ---- length-sorted scheduling of the thread-mapped search (large, throughput-bound batches).
+// A sequence costs about (c(T_longest) - cc) / dc scan steps plus a fixed number of refinement steps
+// per period (the scan of period k starts 1.5 dc below the root of period k-1, surfdisp96.f:271), and
+// models differ: on the C1 sampler set 830 +- 125 secular evaluations per sequence (556 ... 1 136), so a
+// warp of 32 unrelated models waits for its slowest lane.  swd_sched_key_kernel estimates c(T_longest)
+// of every job with RFS_SCHED_BISECT bisection steps of the real secular function between the start
+// value cc and the fastest layer (7 evaluations against ~830); swd_sched_sort_kernel orders the jobs
+// by that estimate, longest first, Rayleigh jobs before Love jobs (a warp must not mix the two secular
+// functions); swd_roots_kernel then takes its jobs through that list.  The order changes which lane
+// solves which job and nothing else: every job is solved by the same code on the same inputs, so
+// the results are bit-identical (GPU test).
+#define RFS_SCHED_BISECT 6
+#define RFS_SCHED_BINS 1024
+__global__ void __launch_bounds__(128)
+    swd_sched_key_kernel(SwdPlan plan, SwdBlocks blk, long long B, int n,
+                         const double *__restrict__ periods, unsigned int *__restrict__ key) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= B * plan.nseq) return;
+  const long long b = i % B;
+  const SwdSeq sq = plan.seq[(int)(i / B)];
+  SwdModel M(blk.root[sq.ifunc == 2 ? 0 : 1], B, n);
+  int llw;
+  float betmx, cc1;
+  swd_start_values(M, b, llw, betmx, cc1);
+  double tmax = 0.0;
+  for (int k = 0; k < sq.nper; k++) tmax = fmax(tmax, __ldg(periods + sq.per_off + k));
+  unsigned int kv = 0;
+  if (sq.nper > 0 && tmax > 0.0 && betmx > cc1) {
+    const double omega = 2.0 * RFS_PI64 / (tmax * sq.scale), iomega = 1.0 / omega;
+    auto f = [&](double c) {
+      const double wv = omega / c;
+      return (sq.ifunc == 1) ? dltar1_dev(wv, omega, M, b, llw) : dltar4_dev(wv, omega, iomega, M, b, llw);
+    };
+    double lo = (double)cc1, hi = (double)betmx;
+    const bool s0 = neg1(f(lo));
+    for (int it = 0; it < RFS_SCHED_BISECT; it++) {
+      const double mid = 0.5 * (lo + hi);
+      if (neg1(f(mid)) != s0) hi = mid; else lo = mid;
+    }
+    const double steps = (0.5 * (lo + hi) - (double)cc1) / (double)0.005f;
+    kv = (unsigned int)fmin(fmax(steps, 0.0), 1.0e6);
+  }
+  key[i] = kv;
+}
+
+// ONE block: counting sort of the J = nseq * B keys, largest first, Rayleigh (ifunc 2) before Love;
+// perm[J] = job ids (sequence * B + model).  With both wave families present each gets half the bins.
+__global__ void __launch_bounds__(RFS_SCHED_BINS)
+    swd_sched_sort_kernel(SwdPlan plan, const unsigned int *__restrict__ key, long long B,
+                          int *__restrict__ perm) {
+  __shared__ unsigned int s_lo[2], s_hi[2];
+  __shared__ int hist[RFS_SCHED_BINS];
+  __shared__ int wsum[32];
+  const int t = threadIdx.x;
+  const long long J = B * plan.nseq;
+  auto cls_of = [&](long long j) { return plan.seq[(int)(j / B)].ifunc == 1 ? 1 : 0; };
+  if (t < 2) { s_lo[t] = 0xffffffffu; s_hi[t] = 0u; }
+  for (int j = t; j < RFS_SCHED_BINS; j += blockDim.x) hist[j] = 0;
+  __syncthreads();
+  unsigned int lo[2] = {0xffffffffu, 0xffffffffu}, hi[2] = {0u, 0u};
+  for (long long j = t; j < J; j += blockDim.x) {
+    const unsigned int v = __ldg(key + j);
+    const int c = cls_of(j);
+    lo[c] = min(lo[c], v);
+    hi[c] = max(hi[c], v);
+  }
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+    if ((t & 31) == 0) {
+      atomicMin(&s_lo[c], lo[c]);
+      atomicMax(&s_hi[c], hi[c]);
+    }
+  }
+  __syncthreads();
+  const bool two = (s_hi[0] >= s_lo[0]) && (s_hi[1] >= s_lo[1]);  // both families have jobs
+  const int nb = two ? RFS_SCHED_BINS / 2 : RFS_SCHED_BINS;
+  auto bin_of = [&](long long j) {
+    const int c = cls_of(j);
+    const unsigned int l0 = s_lo[c];
+    const unsigned long long span = (unsigned long long)(s_hi[c] - l0) + 1ull;
+    const int inner = nb - 1 - (int)(((unsigned long long)(__ldg(key + j) - l0) * nb) / span);
+    return (two && c == 1 ? nb : 0) + inner;
+  };
+  for (long long j = t; j < J; j += blockDim.x) atomicAdd(&hist[bin_of(j)], 1);
+  __syncthreads();
+  // exclusive prefix sum over the bins (blockDim.x == RFS_SCHED_BINS)
+  const int h = hist[t];
+  int inc = h;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((t & 31) >= o) inc += u;
+  }
+  if ((t & 31) == 31) wsum[t >> 5] = inc;
+  __syncthreads();
+  if (t < 32) {
+    int w = wsum[t];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (t >= o) w += u;
+    }
+    wsum[t] = w;
+  }
+  __syncthreads();
+  hist[t] = inc - h + ((t >> 5) ? wsum[(t >> 5) - 1] : 0);
+  __syncthreads();
+  for (long long j = t; j < J; j += blockDim.x) perm[atomicAdd(&hist[bin_of(j)], 1)] = (int)j;
 }
 
 // ---- per-period retries of _surfdisp (surfdisp.cpp:93-100): when the fundamental mode failed in
@@ -115,7 +241,9 @@ static inline unsigned grid_for(long long total, int block) {
 
 cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
                                 const double *periods, int all_modes, double *croot, double *cwork,
-                                int *ierr, unsigned long long *counter, cudaStream_t st) {
+                                int *ierr, unsigned long long *counter, const int *perm, int nsm,
+                                cudaStream_t st) {
+  if (nsm < 1) nsm = 1;
   if (n <= RFS_ROOTS_STAGE_NMAX) {
     const size_t sm = sizeof(double) * RFS_ROOT_NF * (size_t)n * RFS_ROOTS_BLOCK;
     if (sm > 48 * 1024) {
@@ -123,11 +251,23 @@ cudaError_t launch_roots_thread(const SwdPlan &P, const SwdBlocks &blk, long lon
       if (e != cudaSuccess) return e;
     }
     swd_roots_kernel<true><<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, sm, st>>>(
-        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter, perm, nsm);
   } else {
     swd_roots_kernel<false><<<grid_for(B * P.nseq, RFS_ROOTS_BLOCK), RFS_ROOTS_BLOCK, 0, st>>>(
-        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter);
+        P, blk, B, n, periods, all_modes, croot, cwork, ierr, counter, perm, nsm);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sched_keys(const SwdPlan &P, const SwdBlocks &blk, long long B, int n,
+                              const double *periods, unsigned int *key, cudaStream_t st) {
+  swd_sched_key_kernel<<<grid_for(B * P.nseq, 128), 128, 0, st>>>(P, blk, B, n, periods, key);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sched_sort(const SwdPlan &P, long long B, const unsigned int *key, int *perm,
+                              cudaStream_t st) {
+  swd_sched_sort_kernel<<<1, RFS_SCHED_BINS, 0, st>>>(P, key, B, perm);
   return cudaGetLastError();
 }
 

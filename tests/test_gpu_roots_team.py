@@ -143,3 +143,63 @@ def test_mapping_is_chosen_by_batch_size(tctx):
     assert ctx.last_roots_team()[0] > 0
     for a, b in zip(big, small):
         assert _same(a[:64], b)
+
+
+def test_length_sorted_schedule_is_bit_identical(tctx):
+    """Large batches run the thread-mapped search in length-sorted job order (swd_sched_*_kernel in
+    csrc/swd_roots_tu.cu): which lane solves which (model, sequence) changes, nothing else.  Every output
+    bit and the evaluation count must equal the unsorted run — ragged batch sizes, wild models (failed
+    modes, retries), Love + Rayleigh in one objective, several modes, spherical earth, n > 8 (model not
+    staged in shared memory) included."""
+    ctx = tctx
+    cfg, x0 = f1_config(), f1_true_model()
+    Tl = np.asarray(cfg["tRc"])[:11]
+    cases = [(40000 + 13, 0, False, None), (9001, [0, 1], False, Tl), (8192 + 5, 0, True, Tl)]
+    try:
+        for B, modes, sphere, tL in cases:
+            X = sorted_uniform_models(driver_bounds(x0), B, seed=77)
+            X[B // 2:] = _wild(B - B // 2, 9)
+            ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"], tLc=tL, mode=modes, sphere=sphere)
+            ctx.config_obs(np.full(ctx.n_swd_data, 3.0))
+            ctx.set_roots_team(0)
+            out = []
+            for mode in (0, 1):
+                ctx.set_roots_sched(mode)
+                ctx.count_evals(True)
+                res = ctx.misfit_grad_host(X, which=2)
+                out.append((res, ctx.read_evals()))
+                assert ctx.last_roots_sched() == bool(mode)
+            names = ("U", "grad", "dsyn", "flag")
+            for nm, a, b in zip(names, out[0][0], out[1][0]):
+                assert _same(a, b), (B, modes, sphere, nm, int(np.sum(~np.isclose(a, b, rtol=0, atol=0, equal_nan=True))))
+            assert out[0][1] == out[1][1]
+        # n = 40 (global-memory model accessor), four wave types
+        Tp = np.geomspace(2, 100, 20)
+        rng = np.random.default_rng(3)
+        B, n = 3000, 40
+        i = np.arange(n - 1)
+        thk = np.hstack((0.5 + 0.75 * i / n, [0.0]))[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (B, n)))
+        thk[:, -1] = 0.0
+        vs = np.clip((2.0 + 2.7 * (np.arange(n) / (n - 1.0))**0.7)[None, :] * (1 + 0.04 * rng.standard_normal((B, n))), 1.5, 5.0)
+        X = np.hstack((vs, thk))
+        ctx.config_swd(n, Tp, Tp, Tp, Tp, mode=0)
+        ctx.config_obs(np.full(80, 3.0))
+        ctx.set_roots_team(0)
+        res = []
+        for mode in (0, 1):
+            ctx.set_roots_sched(mode)
+            res.append(ctx.misfit_grad_host(X, which=2))
+        for a, b in zip(*res):
+            assert _same(a, b)
+        # automatic: on for a large thread-mapped batch, off for a small one
+        ctx.set_roots_sched(-1)
+        ctx.set_roots_team(-1)
+        ctx.config_swd(7, tRc=cfg["tRc"], tRg=cfg["tRg"])
+        ctx.config_obs(np.full(72, 3.0))
+        ctx.misfit_grad_host(sorted_uniform_models(driver_bounds(x0), 16384, seed=3), which=2)
+        assert ctx.last_roots_sched() and ctx.last_roots_team() == (0, 1)
+        ctx.misfit_grad_host(sorted_uniform_models(driver_bounds(x0), 512, seed=3), which=2)
+        assert not ctx.last_roots_sched()
+    finally:
+        ctx.count_evals(False)
+        ctx.set_roots_sched(-1)
