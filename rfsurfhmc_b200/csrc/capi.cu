@@ -333,7 +333,11 @@ int launch_roots(rfs_ctx *ctx, const SwdPlan &P, const double *d_periods, const 
   ctx->last_sched = 0;
   if (T == 0) {
     const int *perm = nullptr;
-    if ((ctx->sched > 0 || (ctx->sched < 0 && jobs >= RFS_SCHED_MIN_JOBS)) && jobs < 2147483647LL) {
+    // automatic: only where the kernel stages the models in shared memory (n <= RFS_ROOTS_STAGE_NMAX).
+    // With more layers every evaluation reads the model block from global memory, coalesced over
+    // consecutive models; the sorted order scatters those reads (C2, n = 40: 716 -> 1 110 ms).
+    const bool auto_on = ctx->sched < 0 && jobs >= RFS_SCHED_MIN_JOBS && n <= RFS_ROOTS_STAGE_NMAX;
+    if ((ctx->sched > 0 || auto_on) && jobs < 2147483647LL) {
       int rc;
       if ((rc = ensure(ctx, ctx->F->w_key, sizeof(unsigned int) * (size_t)jobs))) return rc;
       if ((rc = ensure(ctx, ctx->F->w_perm, sizeof(int) * (size_t)jobs))) return rc;

@@ -11,6 +11,11 @@ namespace rfs {
 #ifndef RFS_ROOTS_BLOCK
 #define RFS_ROOTS_BLOCK 128
 #endif
+// layer counts up to this one have their root-search model fields staged in shared memory by the
+// thread-mapped kernel ([n][7][128] doubles per block)
+#ifndef RFS_ROOTS_STAGE_NMAX
+#define RFS_ROOTS_STAGE_NMAX 8
+#endif
 
 // one thread per (model, sequence); perm != NULL: jobs taken in the length-sorted order of
 // launch_sched_sort (nsm = SMs of the device, for the block-to-SM composition)

@@ -14,9 +14,6 @@ namespace rfs {
 #ifndef RFS_ROOTS_BLOCK
 #define RFS_ROOTS_BLOCK 128
 #endif
-#ifndef RFS_ROOTS_STAGE_NMAX
-#define RFS_ROOTS_STAGE_NMAX 8
-#endif
 // STAGED: the seven root-search fields of the block's models are copied to shared memory first
 // ([n][7][128] doubles, n <= RFS_ROOTS_STAGE_NMAX) and every secular evaluation reads them from there
 // (one LDS with an immediate offset per value instead of index arithmetic + a global load).
