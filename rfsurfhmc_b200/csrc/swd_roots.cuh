@@ -297,8 +297,10 @@ RFS_DEVINL Dunkin dunkin_layer(const MT &M, long long b, int m, double wvno, dou
 // (integer pipe, no rounding) and normalised once at the top (dunkin_finish): the same value in exact
 // arithmetic, one division per evaluation instead of one per layer, and a layer-to-layer critical path
 // of 4 dependent FP64 operations instead of ~25.
+// rescale = false skips the power-of-two step for this layer: the scalings are exact and cancel in
+// dunkin_finish, so they are only needed often enough to stay far from overflow (every second layer)
 RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2, double &e3,
-                             double &e4) {
+                             double &e4, bool rescale) {
 #define RFS_ROW(a0_, a1_, a2_, a3_, a4_)                                                      \
   RFS_FMA(e4, a4_, RFS_ADD(RFS_FMA(e0, a0_, RFS_MUL(e1, a1_)), RFS_FMA(e2, a2_, RFS_MUL(e3, a3_))))
   const double n0 = RFS_ROW(C.c11, C.c21, C.c31, C.c41, C.c51);
@@ -307,6 +309,14 @@ RFS_DEVINL void dunkin_apply(const Dunkin &C, double &e0, double &e1, double &e2
   const double n3 = RFS_ROW(C.c14, C.c24, C.c34, C.c22, C.c21);
   const double n4 = RFS_ROW(C.c15, C.c14, C.c35, C.c12, C.c11);
 #undef RFS_ROW
+  if (!rescale) {
+    e0 = n0;
+    e1 = n1;
+    e2 = n2;
+    e3 = n3;
+    e4 = n4;
+    return;
+  }
   const double sc = pow2_unscale(
       max(max(max(RFS_HIABS(n0), RFS_HIABS(n1)), max(RFS_HIABS(n2), RFS_HIABS(n3))), RFS_HIABS(n4)));
   e0 = n0 * sc;
@@ -383,13 +393,13 @@ RFS_DEVINL double dltar4_dev(double wvno, double omga, double iomga, const MT &M
     for (; m - 1 >= llw - 1; m -= 2) {
       const Dunkin Ca = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
       const Dunkin Cb = dunkin_layer(M, b, m - 1, wvno, wvno2, omega, iom);
-      dunkin_apply(Ca, e0, e1, e2, e3, e4);
-      dunkin_apply(Cb, e0, e1, e2, e3, e4);
+      dunkin_apply(Ca, e0, e1, e2, e3, e4, false);
+      dunkin_apply(Cb, e0, e1, e2, e3, e4, true);
     }
   }
   for (; m >= llw - 1; m--) {
     const Dunkin C = dunkin_layer(M, b, m, wvno, wvno2, omega, iom);
-    dunkin_apply(C, e0, e1, e2, e3, e4);
+    dunkin_apply(C, e0, e1, e2, e3, e4, (m & 3) == 3);
   }
   if (mmax - 2 >= llw - 1) dunkin_finish(e0, e1, e2, e3, e4);
   if (llw != 1) return dunkin_water_top(M, b, wvno, omega, e0, e1);

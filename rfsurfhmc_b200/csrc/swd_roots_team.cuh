@@ -128,14 +128,14 @@ RFS_DEVINL double team_secular(const SmemModel &M, int ifunc, int llw, double om
     int s = 0;
     if (cnt & 1) {
       const Dunkin A = dunkin_ld(cm, col0);
-      dunkin_apply(A, e0, e1, e2, e3, e4);
+      dunkin_apply(A, e0, e1, e2, e3, e4, true);
       s = 1;
     }
     for (; s < cnt; s += 2) {
       const Dunkin A = dunkin_ld(cm, col0 + s);
       const Dunkin B2 = dunkin_ld(cm, col0 + s + 1);
-      dunkin_apply(A, e0, e1, e2, e3, e4);
-      dunkin_apply(B2, e0, e1, e2, e3, e4);
+      dunkin_apply(A, e0, e1, e2, e3, e4, false);
+      dunkin_apply(B2, e0, e1, e2, e3, e4, true);
     }
   }
   if (nl > 0) dunkin_finish(e0, e1, e2, e3, e4);
