@@ -94,6 +94,10 @@ struct rfs_ctx {
   int sched = -1;
   int last_sched = 0;
   int nsm = 148;  // SMs of the device
+  // experiment knob (RFS_FRONT_MODE): 0 search of the first chunk on the caller's stream; 1 on a front
+  // stream; +2: a 25 us delay kernel ahead of the RF branch; front streams high priority unless
+  // RFS_FRONT_PRIO=0
+  int front_mode = 1;
   // per-kernel timing (rfs_profile_eval): CUDA events around every launch while `prof` is set
   struct ProfRec {
     const char *name;
@@ -596,6 +600,7 @@ int rfs_create(rfs_ctx **out, int device) {
   // launches is a race: 8.07 or 8.38 ms per step at 16 384 chains, by process)
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (const char *e = getenv("RFS_FRONT_PRIO")) if (atoi(e) == 0) prio_hi = prio_lo;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -610,6 +615,7 @@ int rfs_create(rfs_ctx **out, int device) {
   ctx->fronts.push_back(new Front());
   ctx->F = ctx->fronts[0];
   if (const char *e = getenv("RFS_NO_OVERLAP")) ctx->overlap = !(e[0] == '1');
+  if (const char *e = getenv("RFS_FRONT_MODE")) ctx->front_mode = atoi(e);
   if (const char *e = getenv("RFS_ROOTS_SCHED")) ctx->sched = atoi(e) < 0 ? -1 : (atoi(e) > 0 ? 1 : 0);
   {
     int v = 0;
@@ -741,6 +747,16 @@ int rfs_config_obs(rfs_ctx *ctx, double sigma1, double sigma2, const double *dob
   return RFS_OK;
 }
 
+// holds a stream for about `ns` nanoseconds (one warp)
+__global__ void rfs_delay_kernel(unsigned ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
 int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, double *U,
                         double *grad, double *dsyn, unsigned char *flag, void *stream) {
   if (!ctx) return RFS_E_ARG;
@@ -793,7 +809,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
   std::vector<SwdBlocks> blks((size_t)nch);
   // root searches on the (high-priority) front streams: always for chunks after the first, and for the
   // first one too when an RF branch competes with it for the SMs
-  const bool side = ctx->overlap && (nch > 1 || (use_swd && use_rf));
+  const bool side = ctx->overlap && (nch > 1 || (use_swd && use_rf && (ctx->front_mode & 1)));
 
   // ---- pass A: model blocks and root search of EVERY chunk.  A chunk's root search is latency-bound
   // when the chunk is small against the machine (n = 200: ~290 ms for anything up to ~25 k models), so
@@ -803,7 +819,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
     const long long off = (long long)k * Bch, Bc = std::min(Bch, B - off);
     Front *F = ctx->fronts[k];
     ctx->F = F;
-    cudaStream_t sk = side ? ctx->stream_front[k % 3] : st;
+    cudaStream_t sk = (side && (k > 0 || (ctx->front_mode & 1))) ? ctx->stream_front[k % 3] : st;
     if (sk != st) CK(cudaStreamWaitEvent(sk, ctx->ev_fork, 0));
     int rc;
     const size_t nB = (size_t)n * Bc;
@@ -842,6 +858,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
         // RF workspaces and outputs are shared by the chunks: wait for the previous chunk's assemble
         CK(cudaStreamWaitEvent(sr, k == 0 ? ctx->ev_fork : ctx->ev_asm, 0));
         CK(cudaStreamWaitEvent(sr, F->ev_prep, 0));
+        if (ctx->front_mode & 2) LAUNCH(rfs_delay_kernel, 1, 32, 0, sr, 25000u);
       } else {
         CK(cudaStreamWaitEvent(sr, F->ev_prep, 0));
       }
