@@ -94,10 +94,12 @@ struct rfs_ctx {
   int sched = -1;
   int last_sched = 0;
   int nsm = 148;  // SMs of the device
-  // experiment knob (RFS_FRONT_MODE): 0 search of the first chunk on the caller's stream; 1 on a front
-  // stream; +2: a 25 us delay kernel ahead of the RF branch; front streams high priority unless
-  // RFS_FRONT_PRIO=0
-  int front_mode = 1;
+  // where the root search of a joint evaluation runs (RFS_FRONT_MODE, diagnosis only): bit 0 = on a
+  // high-priority front stream also for the first chunk, bit 1 = the RF branch starts behind a 25 us
+  // hold kernel, so that the search's blocks are placed on the SMs before the RF kernels' large grids
+  // (tools/gpu_r2_x.sh, ms per step / e2e / HMC evaluations per s: mode 0 7.99-8.13 / 2.19 M / 1.86 M;
+  // 1 10.6 / 2.25 M / 1.87 M; 2 7.98 / 2.20 M / 1.92 M; 3 8.00 / 2.31 M / 1.92 M)
+  int front_mode = 3;
   // per-kernel timing (rfs_profile_eval): CUDA events around every launch while `prof` is set
   struct ProfRec {
     const char *name;
@@ -596,11 +598,9 @@ int rfs_create(rfs_ctx **out, int device) {
   rfs_ctx *ctx = new rfs_ctx();
   ctx->device = device;
   // the root search runs on high-priority streams: when its blocks and the RF branch's blocks are
-  // pending together, the latency-bound search is placed first (without this the order of the two
-  // launches is a race: 8.07 or 8.38 ms per step at 16 384 chains, by process)
+  // pending together, the latency-bound search is placed first
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (const char *e = getenv("RFS_FRONT_PRIO")) if (atoi(e) == 0) prio_hi = prio_lo;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -747,16 +747,6 @@ int rfs_config_obs(rfs_ctx *ctx, double sigma1, double sigma2, const double *dob
   return RFS_OK;
 }
 
-// holds a stream for about `ns` nanoseconds (one warp)
-__global__ void rfs_delay_kernel(unsigned ns) {
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  do {
-    __nanosleep(1000);
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-  } while (t1 - t0 < ns);
-}
-
 int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, double *U,
                         double *grad, double *dsyn, unsigned char *flag, void *stream) {
   if (!ctx) return RFS_E_ARG;
@@ -858,7 +848,7 @@ int rfs_misfit_grad_dev(rfs_ctx *ctx, long long B, const double *x, int which, d
         // RF workspaces and outputs are shared by the chunks: wait for the previous chunk's assemble
         CK(cudaStreamWaitEvent(sr, k == 0 ? ctx->ev_fork : ctx->ev_asm, 0));
         CK(cudaStreamWaitEvent(sr, F->ev_prep, 0));
-        if (ctx->front_mode & 2) LAUNCH(rfs_delay_kernel, 1, 32, 0, sr, 25000u);
+        if (ctx->front_mode & 2) LAUNCH(rf_branch_hold_kernel, 1, 32, 0, sr, 25000u);
       } else {
         CK(cudaStreamWaitEvent(sr, F->ev_prep, 0));
       }

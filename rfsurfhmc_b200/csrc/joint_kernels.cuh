@@ -120,4 +120,17 @@ __global__ void joint_assemble_kernel(SwdPlan plan, SwdView V, const int *__rest
   }
 }
 
+// Holds a stream for about `ns` nanoseconds (one warp).  Launched ahead of the RF branch of a joint
+// evaluation: the RF kernels have grids of thousands of 255-register blocks, the root search one
+// partial wave of latency-bound blocks; whichever is placed first keeps the SMs, and the search has to
+// be first (10.6 instead of 8.0 ms per step when the RF kernels win the race).
+__global__ void rf_branch_hold_kernel(unsigned ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
 }  // namespace rfs
