@@ -637,7 +637,7 @@ def main():
                                "flop by the frozen hand counts of BASELINE.md §3 (1 FMA = 2, div/sqrt/exp/sin/cos "
                                "= 20 flop each; E_R and P_RF are generous per-layer counts) / kernel time; the FP64 "
                                "pipe utilisation ncu measures for the same kernels is in profiles/r02_kernels.md "
-                               "(roots 52 %, eigen 54 %, RF propagate 66 %)",
+                               "(roots 58 %, eigen 54 %, RF propagate 66 %)",
                "cpu_baseline": cpu,
                "hmc": hmc_out, "configs": configs, "failed_models_last_step": n_fail}
         if strong is not None:
