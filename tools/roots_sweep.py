@@ -12,7 +12,8 @@ import torch
 from rfsurfhmc_b200._lib import Context
 from rfsurfhmc_b200.fixtures import f1_config, f1_true_model, driver_bounds, sorted_uniform_models
 
-TEAMS = [(0, 1), (2, 2), (4, 1), (4, 4), (8, 1), (8, 2), (8, 8), (16, 1), (16, 2), (32, 1), (32, 2), (32, 4)]
+# (T, S); T = 0: thread-mapped, S = 1 with the length-sorted job order forced on, S = 0 forced off
+TEAMS = [(0, 0), (0, 1), (2, 2), (4, 1), (4, 4), (8, 1), (8, 2), (8, 8), (16, 1), (16, 2), (32, 1), (32, 2), (32, 4)]
 
 
 def layered(B, n, seed):
@@ -37,7 +38,8 @@ def run(ctx, X, which, nd, reps):
     rows = []
     ref = None
     for T, S in TEAMS:
-        ctx.set_roots_team(T, S)
+        ctx.set_roots_team(T, max(S, 1))
+        ctx.set_roots_sched(S if T == 0 else -1)
         try:
             ctx.profile_eval(B, xd.data_ptr(), which, U.data_ptr(), G.data_ptr(), D.data_ptr(), F.data_ptr(), st)
         except Exception as e:  # shape not available for this layer count (shared memory)
@@ -58,6 +60,7 @@ def run(ctx, X, which, nd, reps):
         rows.append({"T": T, "S": S, "roots_ms": float(np.median(ms_r)), "eval_ms": float(np.median(ms_t)),
                      "bit_identical_to_thread": bool(same)})
     ctx.set_roots_team(-1)
+    ctx.set_roots_sched(-1)
     return rows
 
 
